@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/sec for GwcNet @256x512, D=192 (BASELINE.json metric), 1..8 x B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one GwcNet inference forward (2D backbone -> cost volume -> 3D aggregation -> soft-argmin) over one batch
+of B=8 synthetic SceneFlow-shaped pairs per GPU (BASELINE.json configs[1]); batches shard over the GPUs (weak scaling,
+independent pairs) and ONE NCCL all_gather of the per-image EPE partial sums closes the timed region, as in the
+reference's eval loop (stereo/modeling/trainer_template.py:313-329).
+
+Reported in one JSON line (rank 0):
+  value      pairs/s, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public model call with PINNED HOST inputs: H2D copy of the images + ground truth
+             and D2H read-back of the per-image EPE inside the timed region, every step
+  roofline   the cost-volume kernel named by the metric (HBM-bound), timed live with CUDA events around its launch
+             inside the timed steps, against MEASURED_PEAKS.json hbm_gbs
+  roofline_dominant  the kernel that dominates the step (3x3x3 Conv3d, fp32-FMA-bound), same live timing
+  cpu_baseline  the oracle port of the reference (same aten CPU kernels) on the host cores, bounded sample
+--impl reference times that oracle port as the reference arm (the reference is pure Python/PyTorch and cannot travel;
+oracle/__init__.py explains the provenance).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stereo_pairs_per_sec_gwcnet_256x512_d192"
+CFG = {"MAX_DISP": 192, "USE_CONCAT_VOLUME": True, "CONCAT_CHANNELS": 12, "DOWNSAMPLE": 4, "NUM_GROUPS": 40}
+H, W = 256, 512
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def synthetic_weights(model, seed=1):
+    """Architecture-shaped random weights (no checkpoints ship with the reference; no network).  Variance-preserving
+    normal conv weights and randomised BN statistics, so activations stay O(1) -- default init collapses the logits."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = model.state_dict()
+    for key in sorted(sd):
+        t = sd[key]
+        if key.endswith("num_batches_tracked") or "disp_regression" in key:
+            continue
+        if key.endswith("running_var"):
+            v = torch.rand(t.shape, generator=gen) + 0.5
+        elif key.endswith("running_mean") or (t.dim() == 1 and not key.endswith("weight")):
+            v = torch.randn(t.shape, generator=gen) * 0.1
+        elif t.dim() == 1:
+            v = torch.rand(t.shape, generator=gen) * 0.5 + 0.5
+        else:
+            fan_in = t[0].numel()
+            v = torch.randn(t.shape, generator=gen) * (1.0 / fan_in) ** 0.5
+        sd[key] = v.to(t.dtype)
+    sd["DispProcessor.classif3.2.weight"] = sd["DispProcessor.classif3.2.weight"] * 145.0
+    model.load_state_dict(sd)
+    return model
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.proc, self.path = None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self, n_gpus):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8 or not f[0].isdigit() or int(f[0]) >= n_gpus:
+                    continue
+                try:
+                    power = float(f[3])
+                    clk = float(f[1])
+                except ValueError:
+                    continue
+                mx = float(f[2])
+                if power > 250.0:                                  # sample taken under load
+                    clocks.append(clk)
+                for name, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            out["sm_mhz"] = statistics.median(clocks)
+        out["sm_max_mhz"] = mx
+        out["reasons"] = sorted(reasons)
+        out["samples_under_load"] = len(clocks)
+        return out
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    elif n_gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun (one process per GPU); WORLD_SIZE is 1" % n_gpus)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def oracle_model():
+    from oracle import models as omodels                           # CPU oracle: cpu_baseline / reference arm only
+    m = omodels.GwcNet(CFG["MAX_DISP"], CFG["USE_CONCAT_VOLUME"], CFG["CONCAT_CHANNELS"], CFG["DOWNSAMPLE"],
+                       CFG["NUM_GROUPS"]).eval()
+    return synthetic_weights(m)
+
+
+def time_cpu(model, pairs_per_step, steps, warmup):
+    gen = torch.Generator().manual_seed(0)
+    x = {"left": torch.randn(pairs_per_step, 3, H, W, generator=gen), "right": torch.randn(pairs_per_step, 3, H, W, generator=gen)}
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(dict(x))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            model(dict(x))
+        dt = time.perf_counter() - t0
+    return dt
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of the reference's CPU path with every host thread, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = oracle_model()
+    pairs = 1                                                       # bounded sample: one pair of the B=8 batch per step
+    dt = time_cpu(model, pairs, args.steps, min(args.warmup, 2))
+    value = pairs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GwcNet cfgs/gwcnet_sceneflow 256x512 D=192 (configs[1]); CPU step = 1 pair sample",
+                   "global_batch": pairs, "parallelism": "cpu-threads"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d forward(s) of 1 pair, oracle port of the reference (same aten CPU kernels)" % args.steps},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.allow_tf32 = False                         # fp32 end to end (cfg AMP: false; 1e-3 px EPE bar)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    from openstereo_b200 import _lib, host_models, ops
+
+    B = args.batch
+    model = synthetic_weights(host_models.GwcNet(CFG)).eval().to(dev)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    rot = args.rotate                                               # distinct input batches: rot * 12.6 MB > L2 (126 MB)
+    host_left = [torch.randn(B, 3, H, W, generator=gen).pin_memory() for _ in range(rot)]
+    host_right = [torch.randn(B, 3, H, W, generator=gen).pin_memory() for _ in range(rot)]
+    host_gt = [(torch.rand(B, H, W, generator=gen) * 190 + 1).pin_memory() for _ in range(rot)]
+    dev_left = [t.to(dev) for t in host_left]
+    dev_right = [t.to(dev) for t in host_right]
+    dev_gt = [t.to(dev) for t in host_gt]
+    host_epe = torch.empty(B, 2).pin_memory()
+
+    def step_resident(i):
+        k = i % rot
+        with torch.no_grad():
+            disp = model({"left": dev_left[k], "right": dev_right[k]})["disp_pred"]
+            return ops.epe_partial(disp, dev_gt[k], CFG["MAX_DISP"])
+
+    def step_e2e(i):
+        k = i % rot
+        with torch.no_grad():
+            left = host_left[k].to(dev, non_blocking=True)
+            right = host_right[k].to(dev, non_blocking=True)
+            gt = host_gt[k].to(dev, non_blocking=True)
+            disp = model({"left": left, "right": right})["disp_pred"]
+            part = ops.epe_partial(disp, gt, CFG["MAX_DISP"])
+            host_epe.copy_(part, non_blocking=True)
+            torch.cuda.current_stream().synchronize()               # the caller reads the metric every step
+            return part
+
+    def gather(part):
+        if world == 1:
+            return part
+        import torch.distributed as dist
+        out = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(out, part)                                  # the single collective of the path
+        return torch.cat(out, 0)
+
+    def timed(step_fn, steps, profile):
+        barrier(world)
+        torch.cuda.synchronize()
+        if profile:
+            ops.profile_start()
+        launches0 = _lib.launch_count()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        part = None
+        for i in range(steps):
+            part = step_fn(i)
+        allparts = gather(part)
+        stop.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        ms = start.elapsed_time(stop)
+        prof = ops.profile_stop() if profile else None
+        launches = _lib.launch_count() - launches0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, launches = mx[0].item(), int(sm[1].item())
+        return ms, launches, prof, allparts
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+        step_e2e(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    ms, launches, prof, parts = timed(step_resident, args.steps, profile=True)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, profile=False)
+    clocks = sampler.stop(args.gpus) if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    pairs = B * world * args.steps
+    value = pairs / (ms / 1e3)
+    e2e_value = pairs / (ms_e2e / 1e3)
+    epe = (parts[:, 0] / parts[:, 1].clamp(min=1)).mean().item()
+    hbm_peak, peak_src, sm_max = measured_peaks()
+
+    def kernel_stats(name):
+        ev = prof.get(name, [])
+        t = [a.elapsed_time(b) for a, b in ev]
+        return (sum(t) / len(t), len(t), sum(t)) if t else (None, 0, 0.0)
+
+    step_ms = ms / args.steps
+    vol_ms, vol_n, vol_total = kernel_stats("osb_gwc_concat_volume_fwd")
+    vol_bytes = 4 * (2 * B * (320 + 12) * 64 * 128 + B * 64 * 48 * 64 * 128)
+    roofline = None
+    if vol_ms:
+        ach = vol_bytes / vol_ms / 1e6
+        roofline = {"kernel": "volume_kernel (gwc+concat fused, osb_gwc_concat_volume_fwd)", "bound": "hbm",
+                    "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
+                    "frac_of_8TBs_nominal": round(ach / 8000.0, 4), "peak_source": peak_src,
+                    "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4), "traffic": None,
+                    "share_of_step": round(vol_total / ms, 4)}
+    conv_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd"]
+    conv_total = sum(kernel_stats(n)[2] for n in conv_names)
+    conv_flops = 2 * 116.30e9 * B                                   # 116.30 GMAC/pair
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                 # derived: SMs x fp32 lanes x 2 x max clock
+    roof_dom = None
+    if conv_total > 0:
+        ach = conv_flops * args.steps / (conv_total / 1e3) / 1e12
+        roof_dom = {"kernel": "conv3d_k3_kernel + deconv3d_kernel + conv3d_1x1_kernel (3D aggregation, 30 launches/step)",
+                    "bound": "fp32_fma", "achieved": round(ach, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(ach / fp32_peak, 4), "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
+                    "alg_flops_per_step": conv_flops, "share_of_step": round(conv_total / ms, 4), "traffic": None}
+    shares = {}
+    for name, ev in prof.items():
+        shares[name] = round(sum(a.elapsed_time(b) for a, b in ev) / ms, 4)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cm = oracle_model()
+        n = 4
+        dt = time_cpu(cm, 1, n, 1)
+        cpu = {"value": round(n / dt, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": "%d forwards of 1 pair (of the B=%d batch) through the oracle port of the reference GwcNet "
+                         "(same aten CPU kernels), %d threads" % (n, B, cores)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GwcNet cfgs/gwcnet/gwcnet_sceneflow.yaml, batch %d/GPU @256x512 D=192 (BASELINE configs[1])" % B,
+                   "global_batch": B * world, "parallelism": "dp%d batch-shard, 1 all_gather of per-image EPE" % world,
+                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activations ~6 GB" % (rot, rot * 2 * B * 3 * H * W * 4 / 1e6),
+                   "weights": "synthetic seeded init (no checkpoints ship with the reference)"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                "h2d_bytes_per_step": (2 * B * 3 * H * W + B * H * W) * 4, "d2h_bytes_per_step": B * 2 * 4},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_dominant": roof_dom, "kernel_share_of_step": shares,
+        "cpu_baseline": cpu, "mean_epe_vs_synthetic_gt": round(epe, 3),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--rotate", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

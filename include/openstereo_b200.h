@@ -1,0 +1,136 @@
+/*
+ * openstereo_b200.h -- C ABI of the B200-native cost-volume hot path for OpenStereo.
+ *
+ * Drop-in boundary.  The reference (XiandaGuo/OpenStereo) has no operator registry: the hot path is
+ * a set of plain Python callables on torch.Tensor.  The reference's own
+ * convention for native ops is "a compiled extension called from a thin Python wrapper on the
+ * current CUDA stream" (stereo/libs/AANet/deform_conv/deform_conv.py:9,44-56;
+ * stereo/modeling/models/nmrf/ops/functions/ms_deform_attn_func.py:11-47).  This header is that
+ * extension's surface, expressed as a C ABI: plain device pointers, sizes and a stream handle --
+ * no torch types.  openstereo_b200/ops.py binds it with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to dense fp32 data in the reference's layout
+ *     (NCHW features, NCDHW volumes), unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - inputs are borrowed and never written; outputs are caller-allocated;
+ *   - return value 0 = success, otherwise an OSB_E* code; osb_last_error() returns a
+ *     thread-local message.  Nothing falls back to a CPU path: without a CUDA device every
+ *     compute entry point fails with OSB_ECUDA.
+ */
+#ifndef OPENSTEREO_B200_H_
+#define OPENSTEREO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_OK 0
+#define OSB_EINVAL 1  /* bad shape / argument (the reference raises AssertionError / ValueError) */
+#define OSB_ECUDA 2   /* CUDA runtime / driver error, incl. "no device" */
+#define OSB_EUNSUPPORTED 3
+
+#define OSB_ACT_NONE 0
+#define OSB_ACT_RELU 1
+#define OSB_ACT_LEAKY 2 /* LeakyReLU(0.01), nn.LeakyReLU default used by StereoBase */
+
+typedef void* osb_stream_t;
+
+int osb_abi_version(void);
+const char* osb_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it). */
+uint64_t osb_launch_count(void);
+
+/* ---------------------------------------------------------------- cost-volume constructors --- */
+
+/* build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups)
+ *   stereo/modeling/cost_volume/cost_volume.py:68-78, gwcnet/gwcnet_cost_processor.py:22-39
+ * ref,tgt: (B,C,H,W) -> out: (B,G,D,H,W); out[b,g,d,h,w] = mean_k ref[b,gK+k,h,w]*tgt[b,gK+k,h,w-d]
+ * for w >= d, exact 0 otherwise.  C % G != 0 -> OSB_EINVAL (reference: assert, cost_volume.py:61). */
+int osb_gwc_volume_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W,
+                       int D, int G, osb_stream_t stream);
+
+/* build_concat_volume(refimg_fea, targetimg_fea, maxdisp)   cost_volume.py:81-92
+ * == cat_fms(start_disp=0, dilation=1)                       psmnet/psmnet_cost_processor.py:9-50
+ * out: (B,2C,D,H,W).  mask_left=1: canonical form (left half zero for w<d);
+ * mask_left=0: IGEV-family form (igev/submodule.py:216-227). */
+int osb_concat_volume_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H,
+                          int W, int D, int mask_left, osb_stream_t stream);
+
+/* GwcVolumeCostProcessor.forward: torch.cat((gwc, concat), 1) written in ONE pass
+ *   gwcnet/gwcnet_cost_processor.py:55-68, stereobase/stereobase_gru.py:142-160
+ * out: (B, G + 2*Cc, D, H, W). */
+int osb_gwc_concat_volume_fwd(const float* ref_gwc, const float* tgt_gwc, const float* ref_cat,
+                              const float* tgt_cat, float* out, int B, int Cg, int Cc, int H, int W,
+                              int D, int G, osb_stream_t stream);
+
+/* correlation_volume(left, right, max_disp)   cost_volume.py:32-41   out: (B,D,H,W) */
+int osb_corr_volume_fwd(const float* left, const float* right, float* out, int B, int C, int H,
+                        int W, int D, osb_stream_t stream);
+
+/* ------------------------------------------------------------------------ soft-argmin tails --- */
+
+/* softmax over D fused with the expectation (one pass over the cost):
+ *   disparity_regression(F.softmax(x,1), D)    disp_pred/disp_regression.py:8-12,
+ *                                              gwcnet/gwcnet_disp_processor.py:22-26
+ *   FasterSoftArgmin.forward                   psmnet/psmnet_disp_processor.py:51-74
+ * cost: (B,D,H,W) -> out: (B,H,W); sample value of bin d is start + d*step; cost is multiplied by
+ * alpha first; normalize=0 skips the softmax (sum_d cost*value). */
+int osb_softargmin_fwd(const float* cost, float* out, int B, int D, int H, int W, float alpha,
+                       float start, float step, int normalize, osb_stream_t stream);
+
+/* F.interpolate(cost,[D,H,W],'trilinear',align_corners) -> softmax(dim=1) -> expectation, fused;
+ * the upsampled (B,D,H,W) tensor is never materialised.
+ *   gwcnet/gwcnet_disp_processor.py:129-133 (align_corners=0)
+ *   psmnet/psmnet_cost_processor.py:203-214 + psmnet_disp_processor.py:64-73 (align_corners=1)
+ * cost: (B,1,Dl,Hl,Wl) -> out: (B,H,W). */
+int osb_upsample_softargmin_fwd(const float* cost, float* out, int B, int Dl, int Hl, int Wl, int D,
+                                int H, int W, int align_corners, osb_stream_t stream);
+
+/* epe_metric partial sums   stereo/evaluation/metric_per_image.py:32-41 with the eval mask of
+ * trainer_template.py:288 (0 < gt < maxdisp).  out: (B,2) = {sum |pred-gt| over valid, #valid}. */
+int osb_epe_partial_fwd(const float* pred, const float* gt, float* out, int B, int HW, float maxdisp,
+                        osb_stream_t stream);
+
+/* ------------------------------------------------------------------------- 3D aggregation ----- */
+
+/* Conv3d(k=3, pad=1, stride in {1,2}, bias=False) + folded eval BatchNorm3d + optional residual +
+ * activation + optional channel gate:
+ *     y = act( conv(x) * scale[co] + shift[co] + residual ) * gate[b,co,h,w]
+ *   convbn_3d gwcnet/hourglass.py:5-16; conv3d_bn(_relu) psmnet/submodule.py:68-83,160-177;
+ *   BasicConv3d common/basic_block_3d.py:5-20; FeatureAtt stereobase/igev_blocks.py:35-48.
+ * x: (B,Cin,D,H,W); w_packed: (Cin,27,Cout) = weight.permute(1,2,3,4,0) of the (Cout,Cin,3,3,3)
+ * parameter; scale/shift: (Cout) or NULL (= 1 / 0); residual: like y or NULL;
+ * gate: (B,Cout,Ho,Wo) already sigmoid-ed, or NULL.  y: (B,Cout,Do,Ho,Wo), Do=(D-1)/stride+1. */
+int osb_conv3d_k3_bn_act_fwd(const float* x, const float* w_packed, const float* scale,
+                             const float* shift, const float* residual, const float* gate, float* y,
+                             int B, int Cin, int Cout, int D, int H, int W, int stride, int act,
+                             osb_stream_t stream);
+
+/* ConvTranspose3d(stride=2, bias=False) + folded BN + residual + activation.
+ *   kernel=3: padding=1, output_padding=1 (gwcnet/hourglass.py:35-41, psmnet deconv3d_bn)
+ *   kernel=4: padding=1                   (stereobase/hourglass.py:39-49)
+ * x: (B,Cin,D,H,W) -> y: (B,Cout,2D,2H,2W); w_packed: (Cin,k^3,Cout) = weight.permute(0,2,3,4,1)
+ * of the (Cin,Cout,k,k,k) parameter. */
+int osb_deconv3d_bn_act_fwd(const float* x, const float* w_packed, const float* scale,
+                            const float* shift, const float* residual, float* y, int B, int Cin,
+                            int Cout, int D, int H, int W, int kernel, int act, osb_stream_t stream);
+
+/* Conv3d(k=1) + folded BN + residual + activation + gate (redir1/2 gwcnet/hourglass.py:43-44,
+ * agg_0[0]/agg_1[0] stereobase/hourglass.py:51-66).  Also serves the 2D 1x1 convs of FeatureAtt
+ * with D=1.  x may be given as two channel slabs (x0: Cin0 channels, x1: Cin-Cin0 channels) so the
+ * torch.cat of stereobase/hourglass.py:91,96 is never materialised; x1 NULL -> single input.
+ * w_packed: (Cin,Cout).  sigmoid_out=1 applies a final sigmoid (FeatureAtt gate). */
+int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const float* w_packed,
+                              const float* scale, const float* shift, const float* residual,
+                              const float* gate, float* y, int B, int Cin, int Cout, int D, int H,
+                              int W, int act, int sigmoid_out, osb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENSTEREO_B200_H_ */

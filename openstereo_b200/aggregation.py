@@ -1,0 +1,237 @@
+"""Hot-path engines: run the reference's 3D aggregation modules with the sm_100a kernels.
+
+Each engine is built FROM an existing module tree (the reference's own ``GwcDispProcessor`` /
+``PSMAggregator`` / StereoBase ``Hourglass``, or the host mirrors in host_models.py): it reads the
+module's parameters by the reference's attribute names, pre-packs them once (weights to
+(Cin, taps, Cout); eval BatchNorm folded to scale/shift) and then executes the forward graph as a
+sequence of fused kernels.  cfg -> constructor -> load_state_dict stay untouched, so unchanged
+checkpoints and YAML configs keep working.
+
+Graphs restated (file:line of the reference forward each engine replaces):
+  GwcAggregation        gwcnet/gwcnet_disp_processor.py:83-91,128-140 + gwcnet/hourglass.py:46-56
+  PSMAggregation        psmnet/psmnet_cost_processor.py:181-221,108-132 + psmnet_disp_processor.py:107-118
+  StereoBaseAggregation stereobase/hourglass.py:79-104 + stereobase_gru.py:161-164
+"""
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
+
+
+class _Packed:
+    """One conv/deconv (+BN) layer, packed for the kernels."""
+    __slots__ = ("w", "scale", "shift", "stride", "kernel", "transposed")
+
+    def __init__(self, conv, bn=None):
+        self.transposed = isinstance(conv, (torch.nn.ConvTranspose3d, torch.nn.ConvTranspose2d))
+        self.kernel = int(conv.kernel_size[0])
+        self.stride = int(conv.stride[0])
+        wt = conv.weight
+        if wt.dim() == 4:                                       # Conv2d 1x1 (FeatureAtt)
+            wt = wt.unsqueeze(2)
+        if self.transposed:
+            self.w = ops.pack_deconv_weight(wt)
+        else:
+            self.w = ops.pack_conv_weight(wt)
+        if self.kernel == 1:
+            self.w = self.w.reshape(self.w.shape[0], self.w.shape[2]).contiguous()
+        self.scale, self.shift = (None, None)
+        if bn is not None:
+            if bn.training:
+                raise RuntimeError("BatchNorm folding is only valid in eval mode (call model.eval())")
+            self.scale, self.shift = ops.fold_bn(bn)
+        if getattr(conv, "bias", None) is not None:
+            bias = conv.bias.detach().float()
+            self.shift = bias.contiguous() if self.shift is None else (self.shift + bias * self.scale).contiguous()
+
+
+def _conv(layer, x, act=ACT_NONE, residual=None, gate=None):
+    if layer.kernel == 1:
+        return ops.conv3d_1x1(x, layer.w, layer.scale, layer.shift, residual, gate, act)
+    return ops.conv3d_k3(x, layer.w, layer.scale, layer.shift, residual, gate, layer.stride, act)
+
+
+def _deconv(layer, x, act=ACT_NONE, residual=None):
+    return ops.deconv3d(x, layer.w, layer.scale, layer.shift, residual, layer.kernel, act)
+
+
+def _versions(module):
+    return tuple(p._version for p in module.parameters()) + tuple(b._version for b in module.buffers())
+
+
+class _Engine:
+    """Pre-pack on first use; re-pack when any parameter/buffer was modified in place or moved."""
+
+    def __init__(self, module):
+        self.module = module
+        self._stamp = None
+
+    def _ensure(self, device):
+        stamp = (str(device), _versions(self.module), tuple(p.data_ptr() for p in self.module.parameters()))
+        if stamp != self._stamp:
+            if self.module.training:
+                raise RuntimeError("openstereo_b200 engines run inference only: call model.eval()")
+            with torch.no_grad():
+                self._pack()
+            self._stamp = stamp
+
+    @staticmethod
+    def _check(x):
+        if not x.is_cuda:
+            raise RuntimeError("openstereo_b200: not implemented on the CPU (no fallback); move the model to CUDA")
+        return x.detach().float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------ GwcNet
+class _GwcHourglass:
+    def __init__(self, m):
+        self.conv1, self.conv2 = _Packed(m.conv1[0][0], m.conv1[0][1]), _Packed(m.conv2[0][0], m.conv2[0][1])
+        self.conv3, self.conv4 = _Packed(m.conv3[0][0], m.conv3[0][1]), _Packed(m.conv4[0][0], m.conv4[0][1])
+        self.conv5, self.conv6 = _Packed(m.conv5[0], m.conv5[1]), _Packed(m.conv6[0], m.conv6[1])
+        self.redir1, self.redir2 = _Packed(m.redir1[0], m.redir1[1]), _Packed(m.redir2[0], m.redir2[1])
+
+    def __call__(self, x):
+        c1 = _conv(self.conv1, x, ACT_RELU)
+        c2 = _conv(self.conv2, c1, ACT_RELU)
+        c3 = _conv(self.conv3, c2, ACT_RELU)
+        c4 = _conv(self.conv4, c3, ACT_RELU)
+        c5 = _deconv(self.conv5, c4, ACT_RELU, residual=_conv(self.redir2, c2))
+        return _deconv(self.conv6, c5, ACT_RELU, residual=_conv(self.redir1, x))
+
+
+class GwcAggregation(_Engine):
+    """Eval branch of GwcDispProcessor: volume (B,64,D',H',W') -> disparity (B,H,W)."""
+
+    def _pack(self):
+        m = self.module
+        self.dres0 = [_Packed(m.dres0[0][0], m.dres0[0][1]), _Packed(m.dres0[2][0], m.dres0[2][1])]
+        self.dres1 = [_Packed(m.dres1[0][0], m.dres1[0][1]), _Packed(m.dres1[2][0], m.dres1[2][1])]
+        self.hg = [_GwcHourglass(m.dres2), _GwcHourglass(m.dres3), _GwcHourglass(m.dres4)]
+        self.classif3 = [_Packed(m.classif3[0][0], m.classif3[0][1]), _Packed(m.classif3[2])]
+
+    def logits(self, volume):
+        volume = self._check(volume)
+        self._ensure(volume.device)
+        c = _conv(self.dres0[1], _conv(self.dres0[0], volume, ACT_RELU), ACT_RELU)
+        cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+        out = cost0
+        for hg in self.hg:
+            out = hg(out)
+        return _conv(self.classif3[1], _conv(self.classif3[0], out, ACT_RELU))
+
+    def __call__(self, volume, h, w):
+        return ops.upsample_softargmin(self.logits(volume), self.module.maxdisp, h, w, align_corners=False)
+
+
+# ------------------------------------------------------------------------------------------------------ PSMNet
+class _PSMHourglass:
+    def __init__(self, m):
+        self.conv1, self.conv2 = _Packed(m.conv1[0], m.conv1[1]), _Packed(m.conv2[0], m.conv2[1])
+        self.conv3, self.conv4 = _Packed(m.conv3[0], m.conv3[1]), _Packed(m.conv4[0], m.conv4[1])
+        self.conv5, self.conv6 = _Packed(m.conv5[0], m.conv5[1]), _Packed(m.conv6[0], m.conv6[1])
+
+    def __call__(self, x, presqu, postsqu, skip):
+        out = _conv(self.conv1, x, ACT_RELU)
+        pre = _conv(self.conv2, out, ACT_RELU, residual=postsqu)
+        out = _conv(self.conv4, _conv(self.conv3, pre, ACT_RELU), ACT_RELU)
+        post = _deconv(self.conv5, out, ACT_RELU, residual=presqu if presqu is not None else pre)
+        # `out_i = hourglass(...) + cost0` (psmnet_cost_processor.py:188-194) rides on conv6's epilogue
+        return _deconv(self.conv6, post, ACT_NONE, residual=skip), pre, post
+
+
+class PSMAggregation(_Engine):
+    """PSMAggregator + FasterSoftArgmin: raw concat volume -> [disp1, disp2, disp3], each (B,H,W)."""
+
+    def _pack(self):
+        m = self.module
+        self.dres0 = [_Packed(m.dres0[0][0], m.dres0[0][1]), _Packed(m.dres0[1][0], m.dres0[1][1])]
+        self.dres1 = [_Packed(m.dres1[0][0], m.dres1[0][1]), _Packed(m.dres1[1][0], m.dres1[1][1])]
+        self.hg = [_PSMHourglass(m.dres2), _PSMHourglass(m.dres3), _PSMHourglass(m.dres4)]
+        self.heads = [[_Packed(c[0][0], c[0][1]), _Packed(c[1])] for c in (m.classif1, m.classif2, m.classif3)]
+
+    def logits(self, raw_cost):
+        raw_cost = self._check(raw_cost)
+        self._ensure(raw_cost.device)
+        c = _conv(self.dres0[1], _conv(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
+        cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+        out1, pre1, post1 = self.hg[0](cost0, None, None, cost0)
+        out2, pre2, post2 = self.hg[1](out1, pre1, post1, cost0)
+        out3, pre3, post3 = self.hg[2](out2, pre2, post2, cost0)
+        cost1 = _conv(self.heads[0][1], _conv(self.heads[0][0], out1, ACT_RELU))
+        cost2 = _conv(self.heads[1][1], _conv(self.heads[1][0], out2, ACT_RELU), residual=cost1)
+        cost3 = _conv(self.heads[2][1], _conv(self.heads[2][0], out3, ACT_RELU), residual=cost2)
+        return [cost1, cost2, cost3]
+
+    def __call__(self, raw_cost):
+        b, c, d, h, w = raw_cost.shape
+        max_disp = self.module.max_disp
+        return [ops.upsample_softargmin(cost, max_disp, 4 * h, 4 * w, align_corners=True)
+                for cost in self.logits(raw_cost)]
+
+
+# -------------------------------------------------------------------------------------------------- StereoBase
+class _FeatureAtt:
+    def __init__(self, m):
+        blk = m.feat_att[0].block
+        self.a = _Packed(blk[0], blk[1])
+        self.b = _Packed(m.feat_att[1])
+
+    def __call__(self, feat):
+        hidden = ops.conv3d_1x1(feat, self.a.w, self.a.scale, self.a.shift, act=ACT_LEAKY)
+        return ops.conv3d_1x1(hidden, self.b.w, self.b.scale, self.b.shift, sigmoid_out=True)   # (B, cv_chan, H, W)
+
+
+def _block(m):
+    layers = list(m.block)
+    bn = layers[1] if len(layers) > 1 and isinstance(layers[1], torch.nn.BatchNorm3d) else None
+    act = ACT_LEAKY if any(isinstance(l, torch.nn.LeakyReLU) for l in layers) else ACT_NONE
+    return _Packed(layers[0], bn), act
+
+
+class StereoBaseAggregation(_Engine):
+    """Hourglass(volume_channel, backbone_channels) with FeatureAtt gates: (B,C,D',H',W') + 2D features -> same shape."""
+
+    def _pack(self):
+        m = self.module
+        self.conv = {name: [_block(b) for b in getattr(m, name)] for name in ("conv1", "conv2", "conv3", "agg_0", "agg_1")}
+        self.up = {name: _block(getattr(m, name)) for name in ("conv3_up", "conv2_up", "conv1_up")}
+        self.att = {name: _FeatureAtt(getattr(m, "feature_att_" + name)) for name in ("8", "16", "32", "up_16", "up_8")}
+
+    def _pair(self, name, x, gate):
+        (l0, a0), (l1, a1) = self.conv[name]
+        return _conv(l1, _conv(l0, x, a0), a1, gate=gate)
+
+    def _agg(self, name, up, skip, gate):
+        (l0, a0), (l1, a1), (l2, a2) = self.conv[name]
+        # torch.cat((up, skip), 1) -> 1x1 conv, without materialising the concat (hourglass.py:91-92,96-97)
+        x = ops.conv3d_1x1(up, l0.w, l0.scale, l0.shift, act=a0, x1=skip)
+        return _conv(l2, _conv(l1, x, a1), a2, gate=gate)
+
+    def __call__(self, x, features):
+        x = self._check(x)
+        self._ensure(x.device)
+        feats = [self._check(f) for f in features]
+        g8, g16, g32 = self.att["8"](feats[1]), self.att["16"](feats[2]), self.att["32"](feats[3])
+        conv1 = self._pair("conv1", x, g8)
+        conv2 = self._pair("conv2", conv1, g16)
+        conv3 = self._pair("conv3", conv2, g32)
+        l, a = self.up["conv3_up"]
+        conv2 = self._agg("agg_0", _deconv(l, conv3, a), conv2, self.att["up_16"](feats[2]))
+        l, a = self.up["conv2_up"]
+        conv1 = self._agg("agg_1", _deconv(l, conv2, a), conv1, self.att["up_8"](feats[1]))
+        l, a = self.up["conv1_up"]
+        return _deconv(l, conv1, a)
+
+
+class StereoBaseCostHead(_Engine):
+    """classifier Conv3d(C,1,3) -> softmax -> disparity_regression (stereobase_gru.py:101,163-164).
+    ``module`` is the nn.Conv3d classifier."""
+
+    def _pack(self):
+        self.layer = _Packed(self.module)
+
+    def __call__(self, geo, maxdisp_lowres):
+        geo = self._check(geo)
+        self._ensure(geo.device)
+        logits = _conv(self.layer, geo)                         # (B,1,D',H',W')
+        return ops.softargmin(logits.squeeze(1), maxdisp_lowres, keepdim=True)

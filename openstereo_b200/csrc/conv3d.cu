@@ -1,0 +1,499 @@
+// Direct (im2col-free) fp32 3D convolutions for the hourglass aggregation, sm_100a.
+//
+//   Conv3d k3 s1/s2 + BN + act (+residual, +gate)   convbn_3d gwcnet/hourglass.py:5-16, gwcnet_disp_processor.py:8-19
+//                                                   conv3d_bn(_relu) psmnet/submodule.py:68-83,160-177
+//                                                   BasicConv3d common/basic_block_3d.py:5-20
+//   ConvTranspose3d k3 s2 p1 op1 / k4 s2 p1 + BN    gwcnet/hourglass.py:35-41, psmnet deconv3d_bn submodule.py:86-100,
+//                                                   BasicDeconv3d stereobase/hourglass.py:39-49
+//   Conv3d k1 (+ channel concat of two inputs)      redir1/2 gwcnet/hourglass.py:43-44, agg_0/agg_1 stereobase/hourglass.py:51-66
+//
+// Numerics: IEEE fp32 FMA accumulation on the CUDA cores.  TF32/BF16 tensor-core operands break the 1e-3 px EPE bar
+// of the north star (2.2e-2 / 1.8e-1 px), so the 3x3x3 path stays on the fp32 pipe.
+//
+// Register tiling: one thread owns 8 consecutive output voxels along W x 8 output channels (64 accumulators).  Per
+// (input channel, kd, kh) it reads a 10-float input row segment and 3x8 weights from shared memory and issues 192 FMAs
+// (~22 FMA per shared-memory load instruction), so the kernel is bound by the fp32 FMA pipe, not by LDS or HBM.
+// BatchNorm (eval) is folded into a per-channel scale/shift epilogue together with the residual add, the activation
+// and StereoBase's sigmoid channel gate, so no elementwise pass ever touches HBM.
+#include "common.cuh"
+
+namespace osb {
+
+struct ConvParams {
+  const float* x;
+  const float* x1;       // second channel slab (1x1 only)
+  const float* w;        // packed (Cin, taps, Cout)
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  const float* gate;
+  float* y;
+  int B, Cin, Cin0, Cout;
+  int D, H, W;           // input extent
+  int Do, Ho, Wo;        // output extent
+  int tiles_w, tiles_h, tiles_d;
+  int act, sigmoid_out, vec_ok;
+};
+
+__device__ __forceinline__ float activate(float v, int act) {
+  if (act == OSB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == OSB_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+// Shared epilogue: acc[c][v] -> y for TCO channels x 8 consecutive output columns.
+template <int TCO>
+__device__ __forceinline__ void epilogue(const ConvParams& p, float (&acc)[TCO][8], int b, int co_first, int od, int oh,
+                                         int ow_first) {
+  if (od >= p.Do || oh >= p.Ho || ow_first >= p.Wo) return;
+#pragma unroll
+  for (int c = 0; c < TCO; ++c) {
+    const int co = co_first + c;
+    if (co >= p.Cout) break;
+    const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+    const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
+    const size_t row = (((size_t)(b * p.Cout + co) * p.Do + od) * p.Ho + oh) * p.Wo + ow_first;
+    const float* grow = p.gate ? p.gate + ((size_t)(b * p.Cout + co) * p.Ho + oh) * p.Wo + ow_first : nullptr;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(acc[c][i], sc, sh);
+    if (p.vec_ok && ow_first + 7 < p.Wo) {
+      if (p.residual) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.residual + row));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.residual + row + 4));
+        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w, v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = activate(v[i], p.act);
+      if (grow) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(grow));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(grow + 4));
+        v[0] *= g0.x, v[1] *= g0.y, v[2] *= g0.z, v[3] *= g0.w, v[4] *= g1.x, v[5] *= g1.y, v[6] *= g1.z, v[7] *= g1.w;
+      }
+      if (p.sigmoid_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 1.f / (1.f + expf(-v[i]));
+      }
+      *reinterpret_cast<float4*>(p.y + row) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p.y + row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (ow_first + i < p.Wo) {
+          float t = v[i];
+          if (p.residual) t += __ldg(p.residual + row + i);
+          t = activate(t, p.act);
+          if (grow) t *= __ldg(grow + i);
+          if (p.sigmoid_out) t = 1.f / (1.f + expf(-t));
+          p.y[row + i] = t;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3x3, stride S
+// CTA tile: TD x TH x 32 output voxels, NCG*TCO output channels; threads = NCG * TD*TH*4.
+template <int S, int TCO, int NCG, int TD, int TH, int CI>
+struct ConvCfg {
+  static constexpr int TW = 32;
+  static constexpr int VG = TD * TH * 4;               // voxel groups (8 columns each)
+  static constexpr int THREADS = NCG * VG;
+  static constexpr int COB = TCO * NCG;
+  static constexpr int ID = (TD - 1) * S + 3, IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
+  static constexpr int PITCH = (IW + 3) / 4 * 4;       // 36 (S=1) / 68 (S=2)
+  static constexpr int XS = CI * ID * IH * PITCH;      // floats
+  static constexpr int WS = CI * 27 * COB;
+  static constexpr size_t SMEM = (size_t)(XS + WS) * sizeof(float);
+};
+
+template <int S, int TCO, int NCG, int TD, int TH, int CI>
+__global__ void __launch_bounds__(NCG* TD* TH * 4) conv3d_k3_kernel(const ConvParams p) {
+  using C = ConvCfg<S, TCO, NCG, TD, TH, CI>;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* ws = smem + C::XS;
+  const int tid = threadIdx.x;
+  const int cg = tid / C::VG, vg = tid % C::VG;
+  const int wg = vg & 3, th = (vg >> 2) % TH, td = vg / (4 * TH);
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int thh = t % p.tiles_h;
+  const int tdd = t / p.tiles_h;
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * C::COB;
+  const int od0 = tdd * TD, oh0 = thh * TH, ow0 = tw * C::TW;
+  const int id0 = od0 * S - 1, ih0 = oh0 * S - 1, iw0 = ow0 * S - 1;  // input coordinate of xs[.][0][0][0]
+
+  float acc[TCO][8];
+#pragma unroll
+  for (int c = 0; c < TCO; ++c)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[c][v] = 0.f;
+
+  const size_t in_plane = (size_t)p.H * p.W;
+  const size_t in_vol = (size_t)p.D * in_plane;
+  for (int c0 = 0; c0 < p.Cin; c0 += CI) {
+    __syncthreads();                                   // previous chunk fully consumed
+    // ---- stage the input halo tile (zero padding = the conv's padding=1) ----
+    for (int idx = tid; idx < C::XS; idx += C::THREADS) {
+      const int wx = idx % C::PITCH;
+      int r = idx / C::PITCH;
+      const int hy = r % C::IH;
+      r /= C::IH;
+      const int dz = r % C::ID;
+      const int ci = r / C::ID;
+      const int gd = id0 + dz, gh = ih0 + hy, gw = iw0 + wx, gc = c0 + ci;
+      float v = 0.f;
+      if (wx < C::IW && gc < p.Cin && gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
+        v = __ldg(p.x + (size_t)(b * p.Cin + gc) * in_vol + (size_t)gd * in_plane + (size_t)gh * p.W + gw);
+      xs[idx] = v;
+    }
+    // ---- stage the weight slab (CI, 27, COB) ----
+    for (int idx = tid; idx < C::WS; idx += C::THREADS) {
+      const int c = idx % C::COB;
+      const int r = idx / C::COB;                      // ci*27 + tap
+      const int ci = r / 27;
+      float v = 0.f;
+      if (c0 + ci < p.Cin && co0 + c < p.Cout) v = __ldg(p.w + ((size_t)(c0 * 27 + r)) * p.Cout + co0 + c);
+      ws[idx] = v;
+    }
+    __syncthreads();
+    // ---- 192 FMAs per (ci, kd, kh) ----
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float* xr = xs + ((ci * C::ID + td * S + kd) * C::IH + th * S + kh) * C::PITCH + wg * 8 * S;
+          constexpr int NX = 7 * S + 3;                // 10 (S=1) / 17 (S=2)
+          float xv[NX + 3];
+#pragma unroll
+          for (int q = 0; q < (NX + 3) / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(xr + 4 * q);
+            xv[4 * q + 0] = t4.x, xv[4 * q + 1] = t4.y, xv[4 * q + 2] = t4.z, xv[4 * q + 3] = t4.w;
+          }
+          const float* wr = ws + (ci * 27 + (kd * 3 + kh) * 3) * C::COB + cg * TCO;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            float wv[TCO];
+            if constexpr (TCO % 4 == 0) {
+#pragma unroll
+              for (int q = 0; q < TCO / 4; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wr + kw * C::COB + 4 * q);
+                wv[4 * q + 0] = t4.x, wv[4 * q + 1] = t4.y, wv[4 * q + 2] = t4.z, wv[4 * q + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < TCO; ++c) wv[c] = wr[kw * C::COB + c];
+            }
+#pragma unroll
+            for (int c = 0; c < TCO; ++c)
+#pragma unroll
+              for (int v = 0; v < 8; ++v) acc[c][v] = fmaf(wv[c], xv[v * S + kw], acc[c][v]);
+          }
+        }
+      }
+    }
+  }
+  epilogue<TCO>(p, acc, b, co0 + cg * TCO, od0 + td, oh0 + th, ow0 + wg * 8);
+}
+
+// ------------------------------------------------------------------------------------- transposed conv, stride 2
+// Output voxel o gathers input i = m + off where m = o>>1 and, per dimension, the taps of parity p = o&1 are
+//   p=0: k=1 (off 0), k=3 (off -1, KS=4 only);   p=1: k=0 (off +1), k=2 (off 0).
+// CTA tile: 4 x 4 x 64 output voxels x 16 channels; threads are laid out so that every warp has one (pd, ph) parity
+// class and therefore executes exactly its own taps (no divergence).
+template <int KS, int CI>
+struct DeconvCfg {
+  static constexpr int TD = 4, TH = 4, TW = 64, TCO = 8, NCG = 2;
+  static constexpr int THREADS = 256, COB = 16;
+  static constexpr int ID = TD / 2 + 2, IH = TH / 2 + 2, IW = TW / 2 + 2, PITCH = 36;
+  static constexpr int XS = CI * ID * IH * PITCH;
+  static constexpr int TAPS = KS * KS * KS;
+  static constexpr int WS = CI * TAPS * COB;
+  static constexpr size_t SMEM = (size_t)(XS + WS) * sizeof(float);
+};
+
+template <int KS, int CI>
+__global__ void __launch_bounds__(256) deconv3d_kernel(const ConvParams p) {
+  using C = DeconvCfg<KS, CI>;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* ws = smem + C::XS;
+  const int tid = threadIdx.x;
+  const int cg = tid >> 7, vg = tid & 127;
+  const int cls = vg >> 5, pd = cls >> 1, ph = cls & 1;
+  const int r5 = (vg & 31) >> 3, dd = r5 >> 1, hh = r5 & 1, wg = vg & 7;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int thh = t % p.tiles_h;
+  const int tdd = t / p.tiles_h;
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * C::COB;
+  const int od0 = tdd * C::TD, oh0 = thh * C::TH, ow0 = tw * C::TW;
+  const int id0 = od0 / 2 - 1, ih0 = oh0 / 2 - 1, iw0 = ow0 / 2 - 1;
+
+  float acc[8][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[c][v] = 0.f;
+
+  const size_t in_plane = (size_t)p.H * p.W;
+  const size_t in_vol = (size_t)p.D * in_plane;
+  for (int c0 = 0; c0 < p.Cin; c0 += CI) {
+    __syncthreads();
+    for (int idx = tid; idx < C::XS; idx += C::THREADS) {
+      const int wx = idx % C::PITCH;
+      int r = idx / C::PITCH;
+      const int hy = r % C::IH;
+      r /= C::IH;
+      const int dz = r % C::ID;
+      const int ci = r / C::ID;
+      const int gd = id0 + dz, gh = ih0 + hy, gw = iw0 + wx, gc = c0 + ci;
+      float v = 0.f;
+      if (wx < C::IW && gc < p.Cin && gd >= 0 && gd < p.D && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W)
+        v = __ldg(p.x + (size_t)(b * p.Cin + gc) * in_vol + (size_t)gd * in_plane + (size_t)gh * p.W + gw);
+      xs[idx] = v;
+    }
+    for (int idx = tid; idx < C::WS; idx += C::THREADS) {
+      const int c = idx % C::COB;
+      const int r = idx / C::COB;                      // ci*TAPS + tap
+      const int ci = r / C::TAPS;
+      float v = 0.f;
+      if (c0 + ci < p.Cin && co0 + c < p.Cout) v = __ldg(p.w + ((size_t)c0 * C::TAPS + r) * p.Cout + co0 + c);
+      ws[idx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+#pragma unroll
+      for (int kd = 0; kd < KS; ++kd) {
+        if ((pd + 1 - kd) & 1) continue;               // warp-uniform
+        const int offd = (pd + 1 - kd) >> 1;           // -1, 0 or +1
+#pragma unroll
+        for (int kh = 0; kh < KS; ++kh) {
+          if ((ph + 1 - kh) & 1) continue;
+          const int offh = (ph + 1 - kh) >> 1;
+          // xs row holds input columns m0-1 .. m0+4 for this thread's m0 = ow0/2 + 4*wg
+          const float* xr = xs + ((ci * C::ID + dd + 1 + offd) * C::IH + hh + 1 + offh) * C::PITCH + wg * 4;
+          const float4 xa = *reinterpret_cast<const float4*>(xr);
+          const float2 xb = *reinterpret_cast<const float2*>(xr + 4);
+          const float xv[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
+          const float* wr = ws + ((ci * KS + kd) * KS + kh) * KS * C::COB + cg * 8;
+          float wv[KS][8];
+#pragma unroll
+          for (int kw = 0; kw < KS; ++kw) {
+            const float4 a = *reinterpret_cast<const float4*>(wr + kw * C::COB);
+            const float4 c4 = *reinterpret_cast<const float4*>(wr + kw * C::COB + 4);
+            wv[kw][0] = a.x, wv[kw][1] = a.y, wv[kw][2] = a.z, wv[kw][3] = a.w;
+            wv[kw][4] = c4.x, wv[kw][5] = c4.y, wv[kw][6] = c4.z, wv[kw][7] = c4.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              // even column 2(m0+u): k=1 <- x[m0+u] (= xv[u+1]); KS=4 also k=3 <- x[m0+u-1] (= xv[u])
+              acc[c][2 * u] = fmaf(wv[1][c], xv[u + 1], acc[c][2 * u]);
+              if constexpr (KS == 4) acc[c][2 * u] = fmaf(wv[3][c], xv[u], acc[c][2 * u]);
+              // odd column 2(m0+u)+1: k=0 <- x[m0+u+1] (= xv[u+2]), k=2 <- x[m0+u] (= xv[u+1])
+              acc[c][2 * u + 1] = fmaf(wv[0][c], xv[u + 2], acc[c][2 * u + 1]);
+              acc[c][2 * u + 1] = fmaf(wv[2][c], xv[u + 1], acc[c][2 * u + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  epilogue<8>(p, acc, b, co0 + cg * 8, od0 + 2 * dd + pd, oh0 + 2 * hh + ph, ow0 + wg * 8);
+}
+
+// --------------------------------------------------------------------------------------------------- 1x1x1 conv
+// CTA: 64 voxel-octets (512 voxels of the flattened D*H*W axis... per row of W) x 32 output channels.
+// The weight slab (<=128 input channels at a time) lives in shared memory; inputs stream from global.
+constexpr int kPwChunk = 128;
+__global__ void __launch_bounds__(256) conv3d_1x1_kernel(const ConvParams p) {
+  __shared__ __align__(16) float ws[kPwChunk * 32];
+  const int tid = threadIdx.x;
+  const int cg = tid >> 6, vq = tid & 63;
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * 32;
+  const size_t vol = (size_t)p.D * p.H * p.W;
+  // voxel octet = 8 consecutive columns of one (d,h) row
+  const int octs_per_row = (p.W + 7) / 8;
+  const size_t oct = (size_t)blockIdx.x * 64 + vq;
+  const size_t rows = (size_t)p.D * p.H;
+  const bool live = oct < rows * octs_per_row;
+  const size_t row = live ? oct / octs_per_row : 0;
+  const int ow = live ? (int)(oct % octs_per_row) * 8 : 0;
+  const size_t off = row * p.W + ow;
+  const bool vec = p.vec_ok && (ow + 7 < p.W);
+
+  float acc[8][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[c][v] = 0.f;
+
+  for (int c0 = 0; c0 < p.Cin; c0 += kPwChunk) {
+    const int nci = min(kPwChunk, p.Cin - c0);
+    __syncthreads();
+    for (int idx = tid; idx < nci * 32; idx += 256) {
+      const int c = idx & 31, ci = idx >> 5;
+      ws[idx] = (co0 + c < p.Cout) ? __ldg(p.w + (size_t)(c0 + ci) * p.Cout + co0 + c) : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll 2
+      for (int ci = 0; ci < nci; ++ci) {
+        const int gc = c0 + ci;
+        const float* src = (gc < p.Cin0) ? p.x + ((size_t)b * p.Cin0 + gc) * vol
+                                         : p.x1 + ((size_t)b * (p.Cin - p.Cin0) + (gc - p.Cin0)) * vol;
+        float xv[8];
+        if (vec) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src + off));
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(src + off + 4));
+          xv[0] = a.x, xv[1] = a.y, xv[2] = a.z, xv[3] = a.w, xv[4] = c4.x, xv[5] = c4.y, xv[6] = c4.z, xv[7] = c4.w;
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) xv[v] = (ow + v < p.W) ? __ldg(src + off + v) : 0.f;
+        }
+        const float4 wa = *reinterpret_cast<const float4*>(ws + ci * 32 + cg * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(ws + ci * 32 + cg * 8 + 4);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int v = 0; v < 8; ++v) acc[c][v] = fmaf(wv[c], xv[v], acc[c][v]);
+      }
+    }
+  }
+  if (live) {
+    const int od = (int)(row / p.H), oh = (int)(row % p.H);
+    epilogue<8>(p, acc, b, co0 + cg * 8, od, oh, ow);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------- launchers
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot reserve %zu bytes of shared memory: %s", what, bytes, cudaGetErrorString(e));
+    return OSB_ECUDA;
+  }
+  return OSB_OK;
+}
+
+template <int S, int TCO, int NCG, int TD, int TH, int CI>
+static int launch_conv_k3(ConvParams& p, cudaStream_t stream) {
+  using C = ConvCfg<S, TCO, NCG, TD, TH, CI>;
+  auto kernel = conv3d_k3_kernel<S, TCO, NCG, TD, TH, CI>;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = set_smem(kernel, C::SMEM, "conv3d_k3")) return rc;
+    configured = true;
+  }
+  p.tiles_w = (p.Wo + C::TW - 1) / C::TW;
+  p.tiles_h = (p.Ho + TH - 1) / TH;
+  p.tiles_d = (p.Do + TD - 1) / TD;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_d, (p.Cout + C::COB - 1) / C::COB, p.B);
+  OSB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_k3: grid too large");
+  kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
+  count_launch();
+  return check_launch("conv3d_k3_kernel");
+}
+
+template <int KS, int CI>
+static int launch_deconv(ConvParams& p, cudaStream_t stream) {
+  using C = DeconvCfg<KS, CI>;
+  auto kernel = deconv3d_kernel<KS, CI>;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = set_smem(kernel, C::SMEM, "deconv3d")) return rc;
+    configured = true;
+  }
+  p.tiles_w = (p.Wo + C::TW - 1) / C::TW;
+  p.tiles_h = (p.Ho + C::TH - 1) / C::TH;
+  p.tiles_d = (p.Do + C::TD - 1) / C::TD;
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_d, (p.Cout + C::COB - 1) / C::COB, p.B);
+  OSB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "deconv3d: grid too large");
+  kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
+  count_launch();
+  return check_launch("deconv3d_kernel");
+}
+
+static bool aligned16(const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_conv3d_k3_bn_act_fwd(const float* x, const float* w_packed, const float* scale, const float* shift,
+                             const float* residual, const float* gate, float* y, int B, int Cin, int Cout, int D, int H,
+                             int W, int stride, int act, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x && w_packed && y, "conv3d_k3: null pointer");
+  OSB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3: empty shape");
+  OSB_REQUIRE(stride == 1 || stride == 2, "conv3d_k3: stride %d not supported (1 or 2)", stride);
+  OSB_REQUIRE(act >= 0 && act <= 2, "conv3d_k3: unknown activation %d", act);
+  ConvParams p{};
+  p.x = x, p.w = w_packed, p.scale = scale, p.shift = shift, p.residual = residual, p.gate = gate, p.y = y;
+  p.B = B, p.Cin = Cin, p.Cin0 = Cin, p.Cout = Cout, p.D = D, p.H = H, p.W = W;
+  p.Do = (D - 1) / stride + 1, p.Ho = (H - 1) / stride + 1, p.Wo = (W - 1) / stride + 1;
+  p.act = act, p.sigmoid_out = 0;
+  p.vec_ok = (p.Wo % 4 == 0) && aligned16(y) && aligned16(residual) && aligned16(gate);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cout < 8) {  // classifier heads (32 -> 1): one channel per thread
+    return stride == 1 ? launch_conv_k3<1, 1, 1, 4, 4, 8>(p, s) : launch_conv_k3<2, 1, 1, 2, 4, 4>(p, s);
+  }
+  if (Cout % 32 != 0 && Cout % 24 == 0) {  // StereoBase widths 24/48/96/144
+    return stride == 1 ? launch_conv_k3<1, 8, 3, 4, 4, 8>(p, s) : launch_conv_k3<2, 8, 3, 2, 4, 4>(p, s);
+  }
+  return stride == 1 ? launch_conv_k3<1, 8, 4, 4, 4, 8>(p, s) : launch_conv_k3<2, 8, 4, 2, 4, 4>(p, s);
+}
+
+int osb_deconv3d_bn_act_fwd(const float* x, const float* w_packed, const float* scale, const float* shift,
+                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int kernel,
+                            int act, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x && w_packed && y, "deconv3d: null pointer");
+  OSB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "deconv3d: empty shape");
+  OSB_REQUIRE(kernel == 3 || kernel == 4, "deconv3d: kernel %d not supported (3 or 4)", kernel);
+  OSB_REQUIRE(act >= 0 && act <= 2, "deconv3d: unknown activation %d", act);
+  ConvParams p{};
+  p.x = x, p.w = w_packed, p.scale = scale, p.shift = shift, p.residual = residual, p.gate = nullptr, p.y = y;
+  p.B = B, p.Cin = Cin, p.Cin0 = Cin, p.Cout = Cout, p.D = D, p.H = H, p.W = W;
+  p.Do = 2 * D, p.Ho = 2 * H, p.Wo = 2 * W;
+  p.act = act, p.sigmoid_out = 0;
+  p.vec_ok = (p.Wo % 4 == 0) && aligned16(y) && aligned16(residual);
+  cudaStream_t s = (cudaStream_t)stream;
+  return kernel == 3 ? launch_deconv<3, 8>(p, s) : launch_deconv<4, 8>(p, s);
+}
+
+int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const float* w_packed, const float* scale,
+                              const float* shift, const float* residual, const float* gate, float* y, int B, int Cin,
+                              int Cout, int D, int H, int W, int act, int sigmoid_out, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x0 && w_packed && y, "conv3d_1x1: null pointer");
+  OSB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "conv3d_1x1: empty shape");
+  OSB_REQUIRE(Cin0 > 0 && Cin0 <= Cin && (Cin0 == Cin || x1 != nullptr), "conv3d_1x1: bad channel split %d of %d", Cin0, Cin);
+  OSB_REQUIRE(act >= 0 && act <= 2, "conv3d_1x1: unknown activation %d", act);
+  ConvParams p{};
+  p.x = x0, p.x1 = x1, p.w = w_packed, p.scale = scale, p.shift = shift, p.residual = residual, p.gate = gate, p.y = y;
+  p.B = B, p.Cin = Cin, p.Cin0 = Cin0, p.Cout = Cout, p.D = D, p.H = H, p.W = W;
+  p.Do = D, p.Ho = H, p.Wo = W;
+  p.act = act, p.sigmoid_out = sigmoid_out;
+  p.vec_ok = (W % 4 == 0) && aligned16(y) && aligned16(residual) && aligned16(gate) && aligned16(x0) && aligned16(x1);
+  const size_t octs = (size_t)D * H * ((W + 7) / 8);
+  dim3 grid((unsigned)((octs + 63) / 64), (Cout + 31) / 32, B);
+  OSB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_1x1: grid too large");
+  conv3d_1x1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("conv3d_1x1_kernel");
+}
+}

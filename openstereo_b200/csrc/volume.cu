@@ -1,0 +1,291 @@
+// Fused cost-volume constructor for sm_100a.
+//
+// Replaces the reference's Python loops of slice assignments
+//   build_gwc_volume     stereo/modeling/cost_volume/cost_volume.py:68-78
+//   build_concat_volume  stereo/modeling/cost_volume/cost_volume.py:81-92  (cat_fms, psmnet_cost_processor.py:9-50)
+//   correlation_volume   stereo/modeling/cost_volume/cost_volume.py:32-41
+//   torch.cat((gwc, concat), 1)  gwcnet_cost_processor.py:65
+// with ONE launch that writes every output row exactly once (zeros of the w<d triangle included, so no memset).
+//
+// Work decomposition.  A CTA owns one image row (b, h), one 128-column tile, one chunk of <=64 disparities and one
+// "unit" of GU output channels; warp = one output channel (a correlation group or a concat channel), lane = four
+// consecutive columns (a 16-byte quad), so every store instruction of a warp is one contiguous 512-byte row segment.
+//
+// gwc unit: the right-image rows of the unit's GU*K feature channels are staged in shared memory by ONE TMA tile load
+// (box 192 x 1 x GU*K, start column w0 - d0 - 64; the hardware zero-fills the negative / out-of-range columns, which is
+// exactly the reference's "columns w<d stay zero").  Each lane keeps a 4(d-quads) x 4(d) x 4(w) accumulator block in
+// registers: per feature channel it reads its left quad straight from global (no reuse across lanes -> no smem) and
+// five right quads from shared memory (a 20-float sliding window) and issues 64 FMAs.
+// concat unit: pure shifted copy; right rows are staged per warp in the same shared buffer.
+//
+// Roofline: HBM-bound.  Algorithmic bytes = 4*(2*B*C*H*W + B*Cout*D*H*W)  (BASELINE.md section 3).
+#include "common.cuh"
+
+namespace osb {
+
+constexpr int kTileW = 128;   // columns per CTA
+constexpr int kChunkD = 64;   // disparities per CTA
+constexpr int kRowW = kTileW + kChunkD;  // staged right-row width (192 floats)
+constexpr int kJG = 4;        // d-quads held in registers per pass (16 disparities)
+
+struct VolParams {
+  const float* ref_g;
+  const float* tgt_g;
+  const float* ref_c;
+  const float* tgt_c;
+  float* out;
+  int B, Cg, Cc, H, W, D, G, K;
+  int Ctot, oc_cat;
+  int GU, n_gwc_units, n_cat_units, w_tiles, d_chunks;
+  int mask_left, use_tma, vec_ok;
+  float inv_k;
+};
+
+__device__ __forceinline__ float4 load_quad(const float* row, int w, int W, bool vec) {
+  // row points at column 0 of a feature row; returns columns w..w+3 (zero beyond W).
+  if (vec && w + 3 < W) return __ldg(reinterpret_cast<const float4*>(row + w));
+  float4 v;
+  v.x = (w + 0 < W) ? __ldg(row + w + 0) : 0.f;
+  v.y = (w + 1 < W) ? __ldg(row + w + 1) : 0.f;
+  v.z = (w + 2 < W) ? __ldg(row + w + 2) : 0.f;
+  v.w = (w + 3 < W) ? __ldg(row + w + 3) : 0.f;
+  return v;
+}
+
+__device__ __forceinline__ void store_quad(float* row, int w, int W, bool vec, float4 v) {
+  if (vec && w + 3 < W) {
+    st_cs_f4(row + w, v);
+  } else {
+    if (w + 0 < W) __stcs(row + w + 0, v.x);
+    if (w + 1 < W) __stcs(row + w + 1, v.y);
+    if (w + 2 < W) __stcs(row + w + 2, v.z);
+    if (w + 3 < W) __stcs(row + w + 3, v.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ CUtensorMap tgt_map, const VolParams p) {
+  extern __shared__ __align__(128) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int z = blockIdx.z;
+  const int dchunk = z % p.d_chunks;
+  z /= p.d_chunks;
+  const int wt = z % p.w_tiles;
+  const int b = z / p.w_tiles;
+  const int h = blockIdx.y;
+  const int w0 = wt * kTileW, d0 = dchunk * kChunkD;
+  const int wq = w0 + 4 * lane;                       // first column of this lane's quad
+  const int nd = min(kChunkD, p.D - d0);
+  const int nquads = (nd + 3) >> 2;
+  const int col0 = w0 - d0 - kChunkD;                 // global column of staged column 0
+  const size_t HW = (size_t)p.H * p.W;
+  const bool vec = p.vec_ok != 0;
+
+  if ((int)blockIdx.x < p.n_gwc_units) {
+    // ------------------------------------------------------------------ group-wise correlation unit
+    const int g0 = blockIdx.x * p.GU;
+    const int rows = p.GU * p.K;                      // staged channel rows (box height)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)rows * kRowW);
+    if (p.use_tma) {
+      if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, (uint32_t)rows * kRowW * 4u);
+        tma_load_3d(smem, &tgt_map, bar, col0, h, b * p.Cg + g0 * p.K);
+      }
+      __syncthreads();                                // barrier init visible before anyone polls it
+      mbar_wait(bar, 0);
+    } else {
+      const int live = min(rows, p.Cg - g0 * p.K);
+      for (int idx = threadIdx.x; idx < live * kRowW; idx += blockDim.x) {
+        const int r = idx / kRowW, c = idx - r * kRowW;
+        const int gw = col0 + c;
+        float v = 0.f;
+        if (gw >= 0 && gw < p.W) v = __ldg(p.tgt_g + ((size_t)(b * p.Cg + g0 * p.K + r) * p.H + h) * p.W + gw);
+        smem[idx] = v;
+      }
+      __syncthreads();
+    }
+    const int g = g0 + warp;
+    if (g >= p.G || wq >= p.W) return;
+    const float* lrow = p.ref_g + ((size_t)(b * p.Cg + g * p.K) * p.H + h) * p.W;
+    const float* rbase = smem + (size_t)warp * p.K * kRowW;
+    float* obase = p.out + (((size_t)(b * p.Ctot + g) * p.D) * p.H + h) * p.W;   // + d*HW
+    for (int j0 = 0; j0 < nquads; j0 += kJG) {
+      float acc[kJG][4][4];
+#pragma unroll
+      for (int jj = 0; jj < kJG; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[jj][i][a] = 0.f;
+      const int win = kChunkD + 4 * (lane - j0) - 16;  // first float of the 20-float window, in [0, 172]
+#pragma unroll 2
+      for (int k = 0; k < p.K; ++k) {
+        const float4 l4 = load_quad(lrow + (size_t)k * HW, wq, p.W, vec);
+        const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+        float r[20];
+        const float4* rp = reinterpret_cast<const float4*>(rbase + (size_t)k * kRowW + win);
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+          const float4 t = rp[n];
+          r[4 * n + 0] = t.x, r[4 * n + 1] = t.y, r[4 * n + 2] = t.z, r[4 * n + 3] = t.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < kJG; ++jj)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[jj][i][a] = fmaf(l[a], r[16 - 4 * jj + a - i], acc[jj][i][a]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < kJG; ++jj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int d = d0 + 4 * (j0 + jj) + i;
+          if (d < p.D && 4 * (j0 + jj) + i < nd) {
+            float4 v;
+            v.x = (wq + 0 >= d) ? acc[jj][i][0] * p.inv_k : 0.f;
+            v.y = (wq + 1 >= d) ? acc[jj][i][1] * p.inv_k : 0.f;
+            v.z = (wq + 2 >= d) ? acc[jj][i][2] * p.inv_k : 0.f;
+            v.w = (wq + 3 >= d) ? acc[jj][i][3] * p.inv_k : 0.f;
+            store_quad(obase + (size_t)d * HW, wq, p.W, vec, v);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ concatenation unit (shifted copy)
+    const int oc = ((int)blockIdx.x - p.n_gwc_units) * p.GU + warp;
+    if (oc >= 2 * p.Cc) return;
+    const bool left = oc < p.Cc;
+    float* obase = p.out + (((size_t)(b * p.Ctot + p.oc_cat + oc) * p.D) * p.H + h) * p.W;
+    if (left) {
+      if (wq >= p.W) return;
+      const float4 v = load_quad(p.ref_c + ((size_t)(b * p.Cc + oc) * p.H + h) * p.W, wq, p.W, vec);
+      for (int dd = 0; dd < nd; ++dd) {
+        const int d = d0 + dd;
+        float4 o = v;
+        if (p.mask_left) {
+          o.x = (wq + 0 >= d) ? v.x : 0.f;
+          o.y = (wq + 1 >= d) ? v.y : 0.f;
+          o.z = (wq + 2 >= d) ? v.z : 0.f;
+          o.w = (wq + 3 >= d) ? v.w : 0.f;
+        }
+        store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
+      }
+    } else {
+      float* row = smem + (size_t)warp * kRowW;
+      const float* src = p.tgt_c + ((size_t)(b * p.Cc + (oc - p.Cc)) * p.H + h) * p.W;
+      for (int c = lane; c < kRowW; c += 32) {
+        const int gw = col0 + c;
+        row[c] = (gw >= 0 && gw < p.W) ? __ldg(src + gw) : 0.f;
+      }
+      __syncwarp();
+      if (wq >= p.W) return;
+      for (int j = 0; j < nquads; ++j) {
+        const float4 lo = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j) - 4);
+        const float4 hi = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j));
+        const float wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int d = d0 + 4 * j + i;
+          if (4 * j + i < nd) {
+            float4 o;                                  // columns w<d read the zero-filled halo
+            o.x = wv[4 - i], o.y = wv[5 - i], o.z = wv[6 - i], o.w = wv[7 - i];
+            store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
+          }
+        }
+      }
+    }
+  }
+}
+
+static int launch_volume(const float* ref_g, const float* tgt_g, const float* ref_c, const float* tgt_c, float* out,
+                         int B, int Cg, int Cc, int H, int W, int D, int G, int mask_left, cudaStream_t stream) {
+  OSB_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, "volume: empty shape B=%d H=%d W=%d D=%d", B, H, W, D);
+  OSB_REQUIRE(Cg >= 0 && Cc >= 0 && (Cg > 0 || Cc > 0), "volume: no channels");
+  int K = 0;
+  if (Cg > 0) {
+    OSB_REQUIRE(G > 0 && Cg % G == 0, "groupwise_correlation: C=%d not divisible by num_groups=%d", Cg, G);
+    K = Cg / G;
+    OSB_REQUIRE(K <= 256, "volume: %d channels per group exceeds the 256 supported", K);
+  } else {
+    G = 0;
+  }
+  VolParams p{};
+  p.ref_g = ref_g, p.tgt_g = tgt_g, p.ref_c = ref_c, p.tgt_c = tgt_c, p.out = out;
+  p.B = B, p.Cg = Cg, p.Cc = Cc, p.H = H, p.W = W, p.D = D, p.G = G, p.K = K;
+  p.Ctot = G + 2 * Cc, p.oc_cat = G;
+  int GU = 8;
+  if (Cg > 0) {
+    GU = G < 8 ? G : 8;
+    while (GU > 1 && GU * K > 128) GU >>= 1;
+  }
+  p.GU = GU;
+  p.n_gwc_units = Cg > 0 ? (G + GU - 1) / GU : 0;
+  p.n_cat_units = Cc > 0 ? (2 * Cc + GU - 1) / GU : 0;
+  p.w_tiles = (W + kTileW - 1) / kTileW;
+  p.d_chunks = (D + kChunkD - 1) / kChunkD;
+  p.mask_left = mask_left;
+  p.inv_k = K > 0 ? 1.0f / (float)K : 0.f;
+  auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_ok = (W % 4 == 0) && aligned16(ref_g) && aligned16(ref_c) && aligned16(out);
+  const int rows = Cg > 0 ? GU * K : GU;
+  size_t smem = (size_t)rows * kRowW * sizeof(float) + 16;
+  CUtensorMap map{};
+  p.use_tma = 0;
+  if (Cg > 0 && W % 4 == 0 && aligned16(tgt_g) && rows <= 256) {
+    // tensor (B*Cg, H, W) fp32; box = 192 columns x 1 row x GU*K channels
+    if (make_tensor_map_3d(&map, tgt_g, (uint64_t)W, (uint64_t)H, (uint64_t)B * Cg, (uint64_t)W * 4, (uint64_t)H * W * 4,
+                           kRowW, 1, (uint32_t)rows))
+      p.use_tma = 1;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("volume: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return OSB_ECUDA;
+    }
+    configured = smem;
+  }
+  dim3 grid(p.n_gwc_units + p.n_cat_units, H, B * p.w_tiles * p.d_chunks);
+  OSB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "volume: grid too large (H=%d, B*tiles=%u)", H, grid.z);
+  volume_kernel<<<grid, 32 * GU, smem, stream>>>(map, p);
+  count_launch();
+  return check_launch("volume_kernel");
+}
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_gwc_volume_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W, int D, int G,
+                       osb_stream_t stream) {
+  OSB_REQUIRE(ref && tgt && out, "gwc_volume: null pointer");
+  OSB_REQUIRE(C > 0, "gwc_volume: C=%d", C);
+  return osb::launch_volume(ref, tgt, nullptr, nullptr, out, B, C, 0, H, W, D, G, 1, (cudaStream_t)stream);
+}
+
+int osb_concat_volume_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W, int D,
+                          int mask_left, osb_stream_t stream) {
+  OSB_REQUIRE(ref && tgt && out, "concat_volume: null pointer");
+  OSB_REQUIRE(C > 0, "concat_volume: C=%d", C);
+  return osb::launch_volume(nullptr, nullptr, ref, tgt, out, B, 0, C, H, W, D, 0, mask_left, (cudaStream_t)stream);
+}
+
+int osb_gwc_concat_volume_fwd(const float* ref_gwc, const float* tgt_gwc, const float* ref_cat, const float* tgt_cat,
+                              float* out, int B, int Cg, int Cc, int H, int W, int D, int G, osb_stream_t stream) {
+  OSB_REQUIRE(ref_gwc && tgt_gwc && ref_cat && tgt_cat && out, "gwc_concat_volume: null pointer");
+  OSB_REQUIRE(Cg > 0 && Cc > 0, "gwc_concat_volume: Cg=%d Cc=%d", Cg, Cc);
+  return osb::launch_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, out, B, Cg, Cc, H, W, D, G, 1, (cudaStream_t)stream);
+}
+
+int osb_corr_volume_fwd(const float* left, const float* right, float* out, int B, int C, int H, int W, int D,
+                        osb_stream_t stream) {
+  OSB_REQUIRE(left && right && out, "corr_volume: null pointer");
+  OSB_REQUIRE(C > 0, "corr_volume: C=%d", C);
+  // correlation_volume == build_gwc_volume(..., num_groups=1).squeeze(1)  
+  return osb::launch_volume(left, right, nullptr, nullptr, out, B, C, 0, H, W, D, 1, 1, (cudaStream_t)stream);
+}
+}

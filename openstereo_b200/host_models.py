@@ -1,0 +1,288 @@
+"""Host-side mirrors of the reference model classes for the hot path (GwcNet, PSMNet).
+
+Same constructor arguments (a cfg object with MAX_DISP / USE_CONCAT_VOLUME / ...), same
+``forward(inputs: dict) -> {'disp_pred': ...}`` contract (docs/4.how_to_create_your_model.md:8-23)
+and the SAME state_dict keys as stereo/modeling/models/gwcnet/gwcnet.py:11-39 and
+stereo/modeling/models/psmnet/psmnet.py:10-29, so an unchanged reference checkpoint loads with
+``load_state_dict``.  They exist because the reference package itself is not importable on a
+machine without easydict/timm; where it IS importable, use
+``openstereo_b200.patch.patch(reference_model)`` instead and nothing here is needed.
+
+Division of labour: the 2D feature extractors are out of the kernel scope (SURVEY.md section 2.1
+row 12) and stay torch.nn/cuDNN; everything from the cost volume to the disparity map runs in the
+sm_100a kernels through the engines of aggregation.py.  The 3D modules below are PARAMETER
+CONTAINERS: they are never called, only read by the engines.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .aggregation import GwcAggregation, PSMAggregation
+
+
+def _cfg_get(cfgs, key, default=None):
+    if isinstance(cfgs, dict):
+        return cfgs.get(key, default)
+    return getattr(cfgs, key, default)
+
+
+# ------------------------------------------------------------------------------------------- 2D backbones (cuDNN)
+def _cb(cin, cout, k, stride, pad, dilation, bias=False):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=dilation if dilation > 1 else pad,
+                                   dilation=dilation, bias=bias), nn.BatchNorm2d(cout))
+
+
+class _ResBlock(nn.Module):
+    """conv-bn-relu, conv-bn, += identity (no trailing relu): gwcnet_backbone.py:13-35, psmnet/submodule.py:219-243."""
+
+    def __init__(self, conv1, conv2, downsample):
+        super().__init__()
+        self.conv1, self.conv2, self.downsample = conv1, conv2, downsample
+
+    def forward(self, x):
+        out = self.conv2(self.conv1(x))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        out += x
+        return out
+
+
+def _stage(make_block, make_down, inplanes, planes, blocks, stride):
+    down = make_down(inplanes, planes, stride) if (stride != 1 or inplanes != planes) else None
+    layers = [make_block(inplanes, planes, stride, down)]
+    layers += [make_block(planes, planes, 1, None) for _ in range(1, blocks)]
+    return nn.Sequential(*layers)
+
+
+class _GwcFeatureExtraction(nn.Module):
+    def __init__(self, concat_feature, concat_channels):
+        super().__init__()
+        self.concat_feature = concat_feature
+        r = lambda: nn.ReLU(inplace=True)
+        self.firstconv = nn.Sequential(_cb(3, 32, 3, 2, 1, 1), r(), _cb(32, 32, 3, 1, 1, 1), r(), _cb(32, 32, 3, 1, 1, 1), r())
+
+        def block(dil):
+            return lambda i, o, s, d: _ResBlock(nn.Sequential(_cb(i, o, 3, s, 1, dil), r()), _cb(o, o, 3, 1, 1, dil), d)
+
+        down = lambda i, o, s: nn.Sequential(nn.Conv2d(i, o, kernel_size=1, stride=s, bias=False), nn.BatchNorm2d(o))
+        self.layer1 = _stage(block(1), down, 32, 32, 3, 1)
+        self.layer2 = _stage(block(1), down, 32, 64, 16, 2)
+        self.layer3 = _stage(block(1), down, 64, 128, 3, 1)
+        self.layer4 = _stage(block(2), down, 128, 128, 3, 1)
+        if concat_feature:
+            self.lastconv = nn.Sequential(_cb(320, 128, 3, 1, 1, 1), r(),
+                                          nn.Conv2d(128, concat_channels, kernel_size=1, padding=0, stride=1, bias=False))
+
+    def forward(self, x):
+        x = self.layer1(self.firstconv(x))
+        l2 = self.layer2(x)
+        l3 = self.layer3(l2)
+        l4 = self.layer4(l3)
+        gwc = torch.cat((l2, l3, l4), dim=1)
+        out = {"gwc_feature": gwc}
+        if self.concat_feature:
+            out["concat_feature"] = self.lastconv(gwc)
+        return out
+
+
+class _GwcBackbone(nn.Module):
+    def __init__(self, use_concat_volume, concat_channels):
+        super().__init__()
+        self.feature_extraction = _GwcFeatureExtraction(use_concat_volume, concat_channels)
+
+    def forward(self, inputs):
+        # left and right share weights: one batched pass (B*2) instead of two (gwcnet_backbone.py:101-107)
+        both = self.feature_extraction(torch.cat((inputs["left"], inputs["right"]), 0))
+        b = inputs["left"].shape[0]
+        return {"ref_feature": {k: v[:b] for k, v in both.items()}, "tgt_feature": {k: v[b:] for k, v in both.items()}}
+
+
+class _PsmBackbone(nn.Module):
+    def __init__(self):
+        super().__init__()
+        cbr = lambda i, o, k, s, p, d: nn.Sequential(*_cb(i, o, k, s, p, d), nn.ReLU(inplace=True))
+        self.firstconv = nn.Sequential(cbr(3, 32, 3, 2, 1, 1), cbr(32, 32, 3, 1, 1, 1), cbr(32, 32, 3, 1, 1, 1))
+
+        def block(pad, dil):
+            return lambda i, o, s, d: _ResBlock(cbr(i, o, 3, s, pad, dil), _cb(o, o, 3, 1, pad, dil), d)
+
+        down = lambda i, o, s: _cb(i, o, 1, s, 0, 1, bias=True)          # conv_bn default bias=True (psmnet_backbone.py:68-71)
+        self.layer1 = _stage(block(1, 1), down, 32, 32, 3, 1)
+        self.layer2 = _stage(block(1, 1), down, 32, 64, 16, 2)
+        self.layer3 = _stage(block(1, 1), down, 64, 128, 3, 1)
+        self.layer4 = _stage(block(2, 2), down, 128, 128, 3, 1)
+        for i, k in zip((1, 2, 3, 4), (64, 32, 16, 8)):
+            setattr(self, "branch%d" % i, nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)), cbr(128, 32, 1, 1, 0, 1)))
+        self.lastconv = nn.Sequential(cbr(320, 128, 3, 1, 1, 1),
+                                      nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, dilation=1, bias=False))
+
+    def _forward(self, x):
+        o2 = self.layer1(self.firstconv(x))
+        o4_0 = self.layer2(o2)
+        o8 = self.layer4(self.layer3(o4_0))
+        size = (o8.size()[2], o8.size()[3])
+        up = [F.interpolate(getattr(self, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
+        return self.lastconv(torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1))
+
+    def forward(self, inputs):
+        both = self._forward(torch.cat((inputs["left"], inputs["right"]), 0))
+        b = inputs["left"].shape[0]
+        return {"ref_feature": both[:b], "tgt_feature": both[b:]}
+
+
+# ------------------------------------------------------------------------------ 3D parameter containers (never called)
+def _cb3(cin, cout, k, s, p):
+    return nn.Sequential(nn.Conv3d(cin, cout, kernel_size=k, stride=s, padding=p, bias=False), nn.BatchNorm3d(cout))
+
+
+def _db3(cin, cout):
+    return nn.Sequential(nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False), nn.BatchNorm3d(cout))
+
+
+class _GwcHourglassParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        r = lambda: nn.ReLU(inplace=True)
+        self.conv1 = nn.Sequential(_cb3(c, 2 * c, 3, 2, 1), r())
+        self.conv2 = nn.Sequential(_cb3(2 * c, 2 * c, 3, 1, 1), r())
+        self.conv3 = nn.Sequential(_cb3(2 * c, 4 * c, 3, 2, 1), r())
+        self.conv4 = nn.Sequential(_cb3(4 * c, 4 * c, 3, 1, 1), r())
+        self.conv5, self.conv6 = _db3(4 * c, 2 * c), _db3(2 * c, c)
+        self.redir1, self.redir2 = _cb3(c, c, 1, 1, 0), _cb3(2 * c, 2 * c, 1, 1, 0)
+
+
+class GwcVolumeCostProcessor(nn.Module):
+    """gwcnet_cost_processor.py:5-68 -- both volumes and the concat in one kernel launch."""
+
+    def __init__(self, maxdisp=192, downsample=4, num_groups=40, use_concat_volume=True, *args, **kwargs):
+        super().__init__()
+        self.maxdisp, self.downsample, self.num_groups, self.use_concat_volume = maxdisp, downsample, num_groups, use_concat_volume
+
+    def forward(self, inputs):
+        lf, rf = inputs["ref_feature"], inputs["tgt_feature"]
+        d = self.maxdisp // self.downsample
+        if self.use_concat_volume:
+            vol = ops.gwc_concat_volume(lf["gwc_feature"], rf["gwc_feature"], lf["concat_feature"], rf["concat_feature"],
+                                        d, self.num_groups)
+        else:
+            vol = ops.build_gwc_volume(lf["gwc_feature"], rf["gwc_feature"], d, self.num_groups)
+        return {"cost_volume": vol}
+
+
+class GwcDispProcessor(nn.Module):
+    """gwcnet_disp_processor.py:29-140 (inference branch); parameters under the reference's names."""
+
+    def __init__(self, maxdisp=192, downsample=4, num_groups=40, use_concat_volume=True, concat_channels=12, *args, **kwargs):
+        super().__init__()
+        self.maxdisp = maxdisp
+        cin = num_groups + (2 * concat_channels if use_concat_volume else 0)
+        r = lambda: nn.ReLU(inplace=True)
+        self.dres0 = nn.Sequential(_cb3(cin, 32, 3, 1, 1), r(), _cb3(32, 32, 3, 1, 1), r())
+        self.dres1 = nn.Sequential(_cb3(32, 32, 3, 1, 1), r(), _cb3(32, 32, 3, 1, 1))
+        self.dres2, self.dres3, self.dres4 = _GwcHourglassParams(32), _GwcHourglassParams(32), _GwcHourglassParams(32)
+        for i in range(4):
+            setattr(self, "classif%d" % i, nn.Sequential(_cb3(32, 32, 3, 1, 1), r(),
+                                                         nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False)))
+        self._engine = None
+
+    def forward(self, inputs):
+        if self.training:
+            raise RuntimeError("openstereo_b200.GwcDispProcessor implements the inference branch only (model.eval())")
+        if self._engine is None:
+            self._engine = GwcAggregation(self)
+        h, w = inputs["left"].shape[2:]
+        return {"inference_disp": {"disp_est": self._engine(inputs["cost_volume"], h, w)}}
+
+
+class GwcNet(nn.Module):
+    def __init__(self, cfgs):
+        super().__init__()
+        self.maxdisp = _cfg_get(cfgs, "MAX_DISP", 192)
+        use_concat, cc = _cfg_get(cfgs, "USE_CONCAT_VOLUME", True), _cfg_get(cfgs, "CONCAT_CHANNELS", 12)
+        ds, g = _cfg_get(cfgs, "DOWNSAMPLE", 4), _cfg_get(cfgs, "NUM_GROUPS", 40)
+        self.Backbone = _GwcBackbone(use_concat, cc if use_concat else 0)
+        self.CostProcessor = GwcVolumeCostProcessor(self.maxdisp, ds, g, use_concat)
+        self.DispProcessor = GwcDispProcessor(self.maxdisp, ds, g, use_concat, cc)
+
+    def forward(self, inputs):
+        inputs.update(self.Backbone(inputs))                      # the reference mutates the dict too (gwcnet.py:30,32)
+        inputs.update(self.CostProcessor(inputs))
+        return {"disp_pred": self.DispProcessor(inputs)["inference_disp"]["disp_est"]}
+
+
+# ---- PSMNet
+def _cbr3(cin, cout, k=3, s=1, p=1):
+    return nn.Sequential(nn.Conv3d(cin, cout, kernel_size=k, stride=s, padding=p, dilation=1, bias=False),
+                         nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+
+class _PsmHourglassParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv1, self.conv2 = _cbr3(c, 2 * c, 3, 2, 1), _cb3(2 * c, 2 * c, 3, 1, 1)
+        self.conv3, self.conv4 = _cbr3(2 * c, 2 * c, 3, 2, 1), _cbr3(2 * c, 2 * c, 3, 1, 1)
+        self.conv5, self.conv6 = _db3(2 * c, 2 * c), _db3(2 * c, c)
+
+
+class _PsmAggregatorParams(nn.Module):
+    def __init__(self, max_disp, in_planes=64):
+        super().__init__()
+        self.max_disp = max_disp
+        self.dres0 = nn.Sequential(_cbr3(in_planes, 32), _cbr3(32, 32))
+        self.dres1 = nn.Sequential(_cbr3(32, 32), _cb3(32, 32, 3, 1, 1))
+        self.dres2, self.dres3, self.dres4 = _PsmHourglassParams(32), _PsmHourglassParams(32), _PsmHourglassParams(32)
+        for i in (1, 2, 3):
+            setattr(self, "classif%d" % i, nn.Sequential(_cbr3(32, 32), nn.Conv3d(32, 1, kernel_size=3, stride=1, padding=1, bias=False)))
+
+
+class PSMCostProcessor(nn.Module):
+    """psmnet_cost_processor.py:224-256.  Returns the three DISPARITY maps directly (the fused tail never
+    materialises the (B,192,H,W) costs), under the keys disp1..3."""
+
+    def __init__(self, max_disp=192, in_planes=64):
+        super().__init__()
+        self.max_disp = max_disp
+        self.aggregator = _PsmAggregatorParams(max_disp, in_planes)
+        self._engine = None
+
+    def forward(self, inputs):
+        if self.training:
+            raise RuntimeError("openstereo_b200.PSMCostProcessor implements inference only (model.eval())")
+        if self._engine is None:
+            self._engine = PSMAggregation(self.aggregator)
+        raw = ops.cat_fms(inputs["ref_feature"], inputs["tgt_feature"], max_disp=int(self.max_disp // 4))
+        d1, d2, d3 = self._engine(raw)
+        return {"disp1": d1, "disp2": d2, "disp3": d3}
+
+
+class _PsmSoftArgminParams(nn.Module):
+    def __init__(self, max_disp):
+        super().__init__()
+        self.disp_regression = nn.Conv3d(1, 1, (max_disp, 1, 1), 1, 0, bias=False)     # frozen linspace weight, kept for the checkpoint
+        self.disp_regression.weight.data = torch.linspace(0, max_disp - 1, max_disp).view(1, 1, max_disp, 1, 1)
+        self.disp_regression.weight.requires_grad = False
+
+
+class PSMDispProcessor(nn.Module):
+    def __init__(self, max_disp=192):
+        super().__init__()
+        self.disp_processor = _PsmSoftArgminParams(max_disp)
+
+    def forward(self, inputs):
+        return [inputs["disp1"], inputs["disp2"], inputs["disp3"]]
+
+
+class PSMNet(nn.Module):
+    def __init__(self, cfgs):
+        super().__init__()
+        self.maxdisp = _cfg_get(cfgs, "MAX_DISP", 192)
+        self.Backbone = _PsmBackbone()
+        self.CostProcessor = PSMCostProcessor(max_disp=self.maxdisp)
+        self.DispProcessor = PSMDispProcessor(max_disp=self.maxdisp)
+
+    def forward(self, inputs):
+        inputs.update(self.Backbone(inputs))
+        inputs.update(self.CostProcessor(inputs))
+        disps = self.DispProcessor(inputs)
+        return {"disp_pred": disps[-1], "train_preds": disps}

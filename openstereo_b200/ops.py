@@ -1,0 +1,257 @@
+"""Reference-facing operators: same names, argument meaning and error behaviour as the OpenStereo
+functions they replace, executed by the sm_100a kernels in libopenstereo_b200.so.
+
+PyTorch is plumbing here: it owns device memory (tensor.data_ptr()) and the stream
+(torch.cuda.current_stream()).  All arithmetic happens in the hand-written kernels.  There is no
+CPU path: a non-CUDA tensor raises, exactly like the reference's own native ops
+(stereo/modeling/models/nmrf/ops/src/ms_deform_attn.h:29-38 -> "Not implemented on the CPU").
+"""
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# Optional live timing: CUDA events recorded on the launching stream around every entry-point call.
+_PROFILE = None
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {entry point name: [(start_event, stop_event), ...]}; call torch.cuda.synchronize() before reading."""
+    global _PROFILE
+    out, _PROFILE = _PROFILE, None
+    return out or {}
+
+
+def _call(name, *args):
+    if _PROFILE is None:
+        return _lib.call(name, *args)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _lib.call(name, *args)
+    stop.record()
+    _PROFILE.setdefault(name, []).append((start, stop))
+
+
+def _prep(t, name):
+    """-> (contiguous fp32 CUDA tensor, original dtype).  Half/bf16 inputs (StereoBase under autocast,
+    cfgs/stereobase/stereobase_sceneflow.yaml:50) are up-converted on load; outputs are cast back."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s: not implemented on the CPU (openstereo_b200 has no CPU fallback)" % name)
+    if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError("%s: unsupported dtype %s" % (name, t.dtype))
+    return t.detach().float().contiguous(), t.dtype
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- cost volumes
+def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
+    """stereo/modeling/cost_volume/cost_volume.py:68-78 -> (B, num_groups, maxdisp, H, W)."""
+    ref, dt = _prep(refimg_fea, "refimg_fea")
+    tgt, _ = _prep(targetimg_fea, "targetimg_fea")
+    assert ref.dim() == 4 and ref.shape == tgt.shape
+    b, c, h, w = ref.shape
+    assert c % num_groups == 0                       # cost_volume.py:61
+    out = torch.empty((b, num_groups, maxdisp, h, w), dtype=torch.float32, device=ref.device)
+    if out.numel():
+        _call("osb_gwc_volume_fwd", ref.data_ptr(), tgt.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp,
+                  num_groups, _stream())
+    return out.to(dt)
+
+
+def build_concat_volume(refimg_fea, targetimg_fea, maxdisp, mask_left=True):
+    """cost_volume.py:81-92 -> (B, 2C, maxdisp, H, W); mask_left=False is igev/submodule.py:216-227."""
+    ref, dt = _prep(refimg_fea, "refimg_fea")
+    tgt, _ = _prep(targetimg_fea, "targetimg_fea")
+    assert ref.dim() == 4 and ref.shape == tgt.shape
+    b, c, h, w = ref.shape
+    out = torch.empty((b, 2 * c, maxdisp, h, w), dtype=torch.float32, device=ref.device)
+    if out.numel():
+        _call("osb_concat_volume_fwd", ref.data_ptr(), tgt.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp,
+                  1 if mask_left else 0, _stream())
+    return out.to(dt)
+
+
+def cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1):
+    """psmnet/psmnet_cost_processor.py:9-50.  PSMNet only ever calls it with start_disp=0, dilation=1
+    (:227-232), where it equals build_concat_volume; other samplings are not on the hot path."""
+    if start_disp != 0 or dilation != 1:
+        raise NotImplementedError("cat_fms: only start_disp=0, dilation=1 (the PSMNet configuration) is accelerated")
+    return build_concat_volume(reference_fm, target_fm, max_disp)
+
+
+def correlation_volume(left_feature, right_feature, max_disp):
+    """cost_volume.py:32-41 -> (B, max_disp, H, W)."""
+    l, dt = _prep(left_feature, "left_feature")
+    r, _ = _prep(right_feature, "right_feature")
+    assert l.dim() == 4 and l.shape == r.shape
+    b, c, h, w = l.shape
+    out = torch.empty((b, max_disp, h, w), dtype=torch.float32, device=l.device)
+    if out.numel():
+        _call("osb_corr_volume_fwd", l.data_ptr(), r.data_ptr(), out.data_ptr(), b, c, h, w, max_disp, _stream())
+    return out.to(dt)
+
+
+def gwc_concat_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, maxdisp, num_groups):
+    """GwcVolumeCostProcessor.forward (gwcnet_cost_processor.py:55-68): both volumes and the
+    torch.cat in one launch -> (B, G + 2*Cc, maxdisp, H, W)."""
+    rg, dt = _prep(ref_gwc, "ref_gwc")
+    tg, _ = _prep(tgt_gwc, "tgt_gwc")
+    rc, _ = _prep(ref_cat, "ref_cat")
+    tc, _ = _prep(tgt_cat, "tgt_cat")
+    assert rg.shape == tg.shape and rc.shape == tc.shape and rg.shape[0] == rc.shape[0] and rg.shape[2:] == rc.shape[2:]
+    b, cg, h, w = rg.shape
+    cc = rc.shape[1]
+    assert cg % num_groups == 0
+    out = torch.empty((b, num_groups + 2 * cc, maxdisp, h, w), dtype=torch.float32, device=rg.device)
+    if out.numel():
+        _call("osb_gwc_concat_volume_fwd", rg.data_ptr(), tg.data_ptr(), rc.data_ptr(), tc.data_ptr(),
+                  out.data_ptr(), b, cg, cc, h, w, maxdisp, num_groups, _stream())
+    return out.to(dt)
+
+
+# --------------------------------------------------------------------------- soft-argmin tails
+def softargmin(cost, maxdisp, keepdim=True, alpha=1.0, start=0.0, step=1.0, normalize=True):
+    """disparity_regression(F.softmax(cost, 1), maxdisp) in one pass (stereobase_gru.py:163-164)."""
+    c, dt = _prep(cost, "cost")
+    assert len(c.shape) == 4                          # disp_regression.py:9
+    b, d, h, w = c.shape
+    assert d == maxdisp
+    out = torch.empty((b, h, w), dtype=torch.float32, device=c.device)
+    if out.numel():
+        _call("osb_softargmin_fwd", c.data_ptr(), out.data_ptr(), b, d, h, w, float(alpha), float(start),
+                  float(step), 1 if normalize else 0, _stream())
+    out = out.to(dt)
+    return out.unsqueeze(1) if keepdim else out
+
+
+def disparity_regression(x, maxdisp, keepdim=True):
+    """disp_pred/disp_regression.py:8-12 (keepdim=True) / gwcnet_disp_processor.py:22-26 (False):
+    sum_d x[:, d] * d on an already-normalised x."""
+    return softargmin(x, maxdisp, keepdim=keepdim, normalize=False)
+
+
+def faster_soft_argmin(cost_volume, max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True):
+    """FasterSoftArgmin.forward, psmnet/psmnet_disp_processor.py:51-74 -> (B, H, W)."""
+    if cost_volume.dim() != 4:
+        raise ValueError('expected 4D input (got {}D input)'.format(cost_volume.dim()))
+    n = (max_disp + dilation - 1) // dilation
+    end = start_disp + max_disp - 1
+    step = (end - start_disp) / (n - 1) if n > 1 else 0.0       # torch.linspace(start, end, n)
+    return softargmin(cost_volume, n, keepdim=False, alpha=alpha, start=start_disp, step=step, normalize=normalize)
+
+
+def upsample_softargmin(cost, maxdisp, out_h, out_w, align_corners=False):
+    """F.interpolate(cost, [maxdisp, H, W], 'trilinear') -> squeeze -> softmax -> regression, fused
+    (gwcnet_disp_processor.py:129-133; psmnet_cost_processor.py:203-214 with align_corners=True).
+    cost: (B, 1, D', H', W') -> (B, H, W)."""
+    c, dt = _prep(cost, "cost")
+    assert c.dim() == 5 and c.shape[1] == 1
+    b, _, dl, hl, wl = c.shape
+    out = torch.empty((b, out_h, out_w), dtype=torch.float32, device=c.device)
+    if out.numel():
+        _call("osb_upsample_softargmin_fwd", c.data_ptr(), out.data_ptr(), b, dl, hl, wl, maxdisp, out_h, out_w,
+                  1 if align_corners else 0, _stream())
+    return out.to(dt)
+
+
+def epe_partial(disp_pred, disp_gt, maxdisp):
+    """Per-image {sum |pred-gt| over 0<gt<maxdisp, #valid} -> (B, 2) fp32
+    (metric_per_image.py:32-41 with the mask of trainer_template.py:288)."""
+    p, _ = _prep(disp_pred, "disp_pred")
+    g, _ = _prep(disp_gt, "disp_gt")
+    assert p.shape == g.shape and p.dim() == 3
+    b = p.shape[0]
+    out = torch.empty((b, 2), dtype=torch.float32, device=p.device)
+    _call("osb_epe_partial_fwd", p.data_ptr(), g.data_ptr(), out.data_ptr(), b, p.shape[1] * p.shape[2],
+              float(maxdisp), _stream())
+    return out
+
+
+def epe_per_image(disp_pred, disp_gt, maxdisp):
+    part = epe_partial(disp_pred, disp_gt, maxdisp)
+    return torch.where(part[:, 1] > 0, part[:, 0] / part[:, 1], torch.zeros_like(part[:, 0]))
+
+
+# --------------------------------------------------------------------------- 3D aggregation primitives
+def pack_conv_weight(weight):
+    """(Cout, Cin, k, k, k) Conv3d parameter -> (Cin, k^3, Cout) contiguous fp32."""
+    co, ci = weight.shape[:2]
+    return weight.detach().float().permute(1, 2, 3, 4, 0).reshape(ci, -1, co).contiguous()
+
+
+def pack_deconv_weight(weight):
+    """(Cin, Cout, k, k, k) ConvTranspose3d parameter -> (Cin, k^3, Cout) contiguous fp32."""
+    ci, co = weight.shape[:2]
+    return weight.detach().float().permute(0, 2, 3, 4, 1).reshape(ci, -1, co).contiguous()
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm -> (scale, shift) with y = x*scale + shift."""
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps))
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def conv3d_k3(x, w_packed, scale=None, shift=None, residual=None, gate=None, stride=1, act=ACT_NONE):
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
+    b, cin, d, h, w = x.shape
+    assert w_packed.shape[0] == cin and w_packed.shape[1] == 27
+    cout = w_packed.shape[2]
+    do, ho, wo = (d - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((b, cout, do, ho, wo), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+    if gate is not None:
+        assert gate.shape == (b, cout, ho, wo) and gate.is_contiguous()
+    _call("osb_conv3d_k3_bn_act_fwd", x.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+              _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, stride, act, _stream())
+    return y
+
+
+def deconv3d(x, w_packed, scale=None, shift=None, residual=None, kernel=3, act=ACT_NONE):
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
+    b, cin, d, h, w = x.shape
+    assert w_packed.shape[0] == cin and w_packed.shape[1] == kernel ** 3
+    cout = w_packed.shape[2]
+    y = torch.empty((b, cout, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+    _call("osb_deconv3d_bn_act_fwd", x.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+              y.data_ptr(), b, cin, cout, d, h, w, kernel, act, _stream())
+    return y
+
+
+def conv3d_1x1(x0, w_packed, scale=None, shift=None, residual=None, gate=None, act=ACT_NONE, x1=None,
+               sigmoid_out=False):
+    """1x1x1 conv over the channel concat of x0 (and x1).  4-D inputs are treated as D=1 volumes."""
+    squeeze = x0.dim() == 4
+    if squeeze:
+        x0 = x0.unsqueeze(2)
+        x1 = None if x1 is None else x1.unsqueeze(2)
+    assert x0.is_cuda and x0.dtype == torch.float32 and x0.is_contiguous()
+    b, c0, d, h, w = x0.shape
+    cin = c0 + (0 if x1 is None else x1.shape[1])
+    if x1 is not None:
+        assert x1.is_contiguous() and x1.shape[0] == b and x1.shape[2:] == x0.shape[2:]
+    assert w_packed.shape[0] == cin
+    cout = w_packed.shape[-1]
+    y = torch.empty((b, cout, d, h, w), dtype=torch.float32, device=x0.device)
+    _call("osb_conv3d_1x1_bn_act_fwd", x0.data_ptr(), _ptr(x1), c0, w_packed.data_ptr(), _ptr(scale), _ptr(shift),
+              _ptr(residual), _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, act, 1 if sigmoid_out else 0, _stream())
+    return y.squeeze(2) if squeeze else y

@@ -1,0 +1,256 @@
+"""GPU: op-level parity of the CUDA kernels (through the C ABI) against the CPU oracle and the committed golden
+vectors.  Tolerances: volumes <= 1e-6 abs (products / means of <= 24 fp32 terms; zeros of the w<d triangle are exact);
+soft-argmin <= 1e-4 px on small ranges and, for 192-bin expectations whose value is ~100 px (fp32 ulp 7.6e-6, the
+reference's own softmax->mul->sum chain carries the same noise: FasterSoftArgmin vs disparity_regression differ by
+4.6e-5), max <= 5e-4 px with mean <= 5e-5 px -- both far inside the 1e-3 px EPE bar;
+conv primitives <= 1e-5 relative to the output scale (fp32 accumulation order differs)."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cost_volume as ocv      # noqa: E402
+from oracle import regression as oreg      # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__
+    __graft_entry__.build()
+    from openstereo_b200 import ops as _ops
+    return _ops
+
+
+def dev(t):
+    return t.cuda()
+
+
+def rnd(seed, *shape, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def assert_close(got, want, atol, what=""):
+    got = got.detach().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs().max().item() if want.numel() else 0.0
+    assert err <= atol, "%s: max abs err %g > %g" % (what, err, atol)
+
+
+def assert_zero_triangle(vol, d_axis):
+    """Columns w < d must be exactly zero (the reference never writes them after new_zeros)."""
+    v = vol.detach().cpu().movedim(d_axis, 0)
+    for d in range(v.shape[0]):
+        assert (v[d][..., :min(d, v.shape[-1])] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ volumes
+@pytest.mark.parametrize("name", ["gwc_small", "gwc_d_gt_w", "gwc_k12", "gwc_k8_w128"])
+def test_gwc_volume_golden(ops, name):
+    g = load_golden(name)
+    out = ops.build_gwc_volume(dev(g["left"]), dev(g["right"]), g["maxdisp"], g["groups"])
+    assert out.is_contiguous() and out.dtype == torch.float32
+    assert_close(out, g["out"], 1e-6, name)
+    assert_zero_triangle(out, 2)
+
+
+@pytest.mark.parametrize("name", ["concat_small", "concat_d_gt_w", "concat_c12_w128"])
+def test_concat_volume_golden(ops, name):
+    g = load_golden(name)
+    out = ops.build_concat_volume(dev(g["left"]), dev(g["right"]), g["maxdisp"])
+    assert torch.equal(out.cpu(), g["out"])                       # pure copy: bit exact
+    assert torch.equal(ops.cat_fms(dev(g["left"]), dev(g["right"]), max_disp=g["maxdisp"]).cpu(), g["out"])
+    out = ops.build_concat_volume(dev(g["left"]), dev(g["right"]), g["maxdisp"], mask_left=False)
+    assert torch.equal(out.cpu(), g["out_unmasked"])
+
+
+def test_corr_and_fused_golden(ops):
+    g = load_golden("corr_small")
+    assert_close(ops.correlation_volume(dev(g["left"]), dev(g["right"]), g["maxdisp"]), g["out"], 1e-6, "corr")
+    g = load_golden("gwc_concat_fused")
+    out = ops.gwc_concat_volume(dev(g["lg"]), dev(g["rg"]), dev(g["lc"]), dev(g["rc"]), g["maxdisp"], g["groups"])
+    assert_close(out, g["out"], 1e-6, "fused")
+    assert torch.equal(out[:, g["groups"]:].cpu(), g["out"][:, g["groups"]:])   # concat half is a bit-exact copy
+
+
+@pytest.mark.parametrize("b,c,h,w,d,g", [
+    (2, 320, 3, 128, 48, 40),     # GwcNet shape (config 2), few rows
+    (1, 96, 2, 160, 48, 8),       # IGEV / StereoBase K=12, two column tiles
+    (1, 16, 2, 130, 70, 4),       # W % 4 != 0 (no TMA), two disparity chunks
+    (1, 24, 3, 184, 48, 1),       # LightStereo correlation (G=1, K=24)
+    (1, 8, 1, 5, 3, 8),           # K = 1
+    (3, 12, 2, 36, 9, 3),
+])
+def test_gwc_volume_vs_oracle(ops, b, c, h, w, d, g):
+    l, r = rnd(1, b, c, h, w), rnd(2, b, c, h, w)
+    out = ops.build_gwc_volume(dev(l), dev(r), d, g)
+    assert_close(out, ocv.build_gwc_volume(l, r, d, g), 1e-6, "gwc %s" % ((b, c, h, w, d, g),))
+    assert_zero_triangle(out, 2)
+
+
+@pytest.mark.parametrize("b,c,h,w,d", [(2, 12, 3, 128, 48), (1, 32, 2, 128, 48), (1, 5, 2, 37, 70), (1, 3, 1, 260, 9)])
+def test_concat_volume_vs_oracle(ops, b, c, h, w, d):
+    l, r = rnd(3, b, c, h, w), rnd(4, b, c, h, w)
+    assert torch.equal(ops.build_concat_volume(dev(l), dev(r), d).cpu(), ocv.build_concat_volume(l, r, d))
+
+
+def test_fused_volume_gwcnet_shape(ops):
+    lg, rg, lc, rc = rnd(5, 1, 320, 2, 128), rnd(6, 1, 320, 2, 128), rnd(7, 1, 12, 2, 128), rnd(8, 1, 12, 2, 128)
+    out = ops.gwc_concat_volume(dev(lg), dev(rg), dev(lc), dev(rc), 48, 40)
+    assert out.shape == (1, 64, 48, 2, 128)
+    assert_close(out, ocv.gwc_concat_volume(lg, rg, lc, rc, 48, 40), 1e-6, "fused gwcnet")
+
+
+def test_volume_properties_full_size(ops):
+    """Config-2 size (B=8, C=320, G=40, 64x128, D'=48): size-independent properties instead of a CPU oracle run.
+    (1) linearity in the left feature; (2) the d=0 slice equals the plain group mean of l*r; (3) zero triangle;
+    (4) shifting the right image by s columns shifts the disparity axis by s."""
+    torch.manual_seed(0)
+    l = torch.randn(8, 320, 64, 128, device="cuda")
+    r = torch.randn(8, 320, 64, 128, device="cuda")
+    v1 = ops.build_gwc_volume(l, r, 48, 40)
+    v2 = ops.build_gwc_volume(2.0 * l, r, 48, 40)
+    assert torch.equal(v2, 2.0 * v1)                              # scaling by 2 is exact in fp32
+    d0 = (l * r).view(8, 40, 8, 64, 128).mean(2)
+    assert (v1[:, :, 0] - d0).abs().max().item() <= 1e-6
+    assert_zero_triangle(v1[:1], 2)
+    s = 5
+    r_shift = torch.zeros_like(r)
+    r_shift[..., s:] = r[..., :-s]                                # r_shift[w] = r[w-s]
+    v3 = ops.build_gwc_volume(l, r_shift, 48, 40)                 # v3[d] pairs l[w] with r[w-d-s] = v1[d+s] where defined
+    assert (v3[:, :, :48 - s, :, 48:] - v1[:, :, s:, :, 48:]).abs().max().item() <= 1e-6
+
+
+def test_half_inputs_roundtrip(ops):
+    """Under autocast StereoBase feeds fp16 features (stereobase_sceneflow.yaml:50); output dtype = input dtype."""
+    l, r = rnd(9, 1, 16, 2, 32).half(), rnd(10, 1, 16, 2, 32).half()
+    out = ops.build_gwc_volume(dev(l), dev(r), 8, 4)
+    assert out.dtype == torch.float16
+    ref = ocv.build_gwc_volume(l.float(), r.float(), 8, 4)
+    assert (out.float().cpu() - ref).abs().max().item() <= 2e-3
+
+
+def test_reference_assertions(ops):
+    x = torch.randn(1, 10, 2, 8, device="cuda")
+    with pytest.raises(AssertionError):
+        ops.build_gwc_volume(x, x, 4, 3)                          # cost_volume.py:61: C % num_groups
+    with pytest.raises(AssertionError):
+        ops.disparity_regression(torch.randn(1, 4, 4, device="cuda"), 4)   # disp_regression.py:9
+
+
+# ------------------------------------------------------------------------------------------------ soft-argmin
+def test_softargmin_golden(ops):
+    g = load_golden("softargmin_small")
+    assert_close(ops.softargmin(dev(g["cost"]), g["maxdisp"]), g["out_keepdim"], 1e-4, "softargmin")
+    assert_close(ops.disparity_regression(dev(g["prob"]), g["maxdisp"]), g["out_keepdim"], 1e-4, "regression keepdim")
+    assert_close(ops.disparity_regression(dev(g["prob"]), g["maxdisp"], keepdim=False), g["out_flat"], 1e-4, "regression")
+    g = load_golden("faster_softargmin")
+    assert_close(ops.faster_soft_argmin(dev(g["cost"]), g["maxdisp"]), g["out"], 1e-4, "faster")
+
+
+def test_upsample_softargmin_golden(ops):
+    g = load_golden("upsample_softargmin")
+    got = ops.upsample_softargmin(dev(g["cost"]), g["maxdisp"], g["out_h"], g["out_w"], align_corners=False)
+    assert_close(got, g["out_gwc"], 1e-4, "gwc tail")
+    got = ops.upsample_softargmin(dev(g["cost"]), g["maxdisp"], g["out_h"], g["out_w"], align_corners=True)
+    assert_close(got, g["out_psm"], 1e-4, "psm tail")
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_upsample_softargmin_vs_oracle(ops, align):
+    cost = rnd(11, 2, 1, 48, 16, 32, scale=4.0)
+    got = ops.upsample_softargmin(dev(cost), 192, 64, 128, align_corners=align)
+    want = oreg.upsample_softargmin(cost, 192, 64, 128, align_corners=align, psm_tail=align)
+    assert_close(got, want, 5e-4, "upsample align=%s" % align)
+    assert (got.cpu() - want).abs().mean().item() <= 5e-5
+    assert want.std() > 5.0
+
+
+def test_softargmin_shapes(ops):
+    for shape, scale in [((2, 48, 16, 32), 3.0), ((1, 192, 8, 40), 6.0), ((1, 5, 3, 7), 30.0)]:
+        cost = rnd(12, *shape, scale=scale)
+        assert_close(ops.softargmin(dev(cost), shape[1]), oreg.softargmin(cost, shape[1]), 5e-4 if shape[1] > 100 else 1e-4, str(shape))
+    cost = rnd(13, 1, 24, 4, 9)
+    got = ops.faster_soft_argmin(dev(cost), 24, alpha=2.5)
+    assert_close(got, oreg.faster_soft_argmin(cost, 24, alpha=2.5), 1e-4, "alpha")
+
+
+def test_softargmin_properties_full_size(ops):
+    """Config-2 size: a one-hot-like cost volume regresses to the argmax; a constant shift of the logits changes nothing."""
+    b, d, h, w = 2, 192, 256, 512
+    idx = torch.randint(0, d, (b, 1, h, w), device="cuda")
+    cost = torch.full((b, d, h, w), -40.0, device="cuda").scatter_(1, idx, 40.0)
+    out = ops.softargmin(cost, d, keepdim=False)
+    assert (out - idx[:, 0].float()).abs().max().item() <= 1e-4
+    out2 = ops.softargmin(cost + 7.0, d, keepdim=False)
+    assert (out - out2).abs().max().item() <= 1e-4
+
+
+def test_epe_partial(ops):
+    g = load_golden("epe_per_image")
+    got = ops.epe_per_image(dev(g["pred"]), dev(g["gt"]), 192)
+    assert_close(got, g["out"], 1e-4, "epe")
+    assert got[2].item() == 0.0                                   # image without valid pixels
+
+
+# ------------------------------------------------------------------------------------------------ conv primitives
+def rel_close(got, want, rtol, what):
+    got = got.detach().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = want.abs().max().item() + 1e-12
+    err = (got - want).abs().max().item() / scale
+    assert err <= rtol, "%s: rel err %g > %g" % (what, err, rtol)
+
+
+@pytest.mark.parametrize("cin,cout,d,h,w,stride", [
+    (8, 32, 8, 8, 32, 1), (32, 32, 5, 7, 19, 1), (12, 24, 6, 6, 40, 1), (16, 1, 4, 9, 33, 1),
+    (8, 64, 8, 8, 32, 2), (16, 48, 7, 9, 21, 2), (32, 1, 6, 6, 16, 2), (20, 40, 3, 4, 12, 1),
+])
+def test_conv3d_k3(ops, cin, cout, d, h, w, stride):
+    import torch.nn.functional as F
+    x, wt = rnd(20, 2, cin, d, h, w), rnd(21, cout, cin, 3, 3, 3, scale=0.2)
+    sc, sh = torch.rand(cout, generator=torch.Generator().manual_seed(22)) + 0.5, rnd(23, cout, scale=0.1)
+    want = F.conv3d(x, wt, stride=stride, padding=1)
+    res = rnd(24, *want.shape)
+    got = ops.conv3d_k3(dev(x), ops.pack_conv_weight(dev(wt)), stride=stride)
+    rel_close(got, want, 1e-5, "plain")
+    got = ops.conv3d_k3(dev(x), ops.pack_conv_weight(dev(wt)), dev(sc), dev(sh), dev(res), None, stride, ops.ACT_RELU)
+    want2 = F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res)
+    rel_close(got, want2, 1e-5, "bn+res+relu")
+    gate = torch.sigmoid(rnd(25, 2, cout, want.shape[3], want.shape[4]))
+    got = ops.conv3d_k3(dev(x), ops.pack_conv_weight(dev(wt)), dev(sc), dev(sh), None, dev(gate), stride, ops.ACT_LEAKY)
+    want3 = F.leaky_relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)) * gate.unsqueeze(2)
+    rel_close(got, want3, 1e-5, "bn+leaky+gate")
+
+
+@pytest.mark.parametrize("cin,cout,d,h,w,k", [(16, 16, 4, 4, 32, 3), (24, 8, 3, 5, 9, 3), (12, 24, 2, 3, 40, 4),
+                                              (8, 16, 4, 4, 32, 4), (128, 64, 3, 4, 8, 3)])
+def test_deconv3d(ops, cin, cout, d, h, w, k):
+    import torch.nn.functional as F
+    x, wt = rnd(30, 2, cin, d, h, w), rnd(31, cin, cout, k, k, k, scale=0.2)
+    want = F.conv_transpose3d(x, wt, stride=2, padding=1, output_padding=1 if k == 3 else 0)
+    assert want.shape[2:] == (2 * d, 2 * h, 2 * w)
+    got = ops.deconv3d(dev(x), ops.pack_deconv_weight(dev(wt)), kernel=k)
+    rel_close(got, want, 1e-5, "deconv k%d" % k)
+    sc, sh, res = torch.rand(cout) + 0.5, rnd(33, cout, scale=0.1), rnd(34, *want.shape)
+    got = ops.deconv3d(dev(x), ops.pack_deconv_weight(dev(wt)), dev(sc), dev(sh), dev(res), k, ops.ACT_RELU)
+    rel_close(got, F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res), 1e-5, "deconv fused")
+
+
+def test_conv3d_1x1(ops):
+    import torch.nn.functional as F
+    x0, x1 = rnd(40, 2, 24, 3, 5, 16), rnd(41, 2, 40, 3, 5, 16)
+    wt = rnd(42, 48, 64, 1, 1, 1, scale=0.2)
+    want = F.conv3d(torch.cat((x0, x1), 1), wt)
+    got = ops.conv3d_1x1(dev(x0), dev(wt.view(48, 64).t().contiguous()), x1=dev(x1))
+    rel_close(got, want, 1e-5, "1x1 two slabs")
+    x = rnd(43, 1, 200, 2, 3, 7)                                   # Cin > one weight slab, W % 4 != 0
+    wt = rnd(44, 20, 200, 1, 1, 1, scale=0.1)
+    sh = rnd(45, 20)
+    got = ops.conv3d_1x1(dev(x), dev(wt.view(20, 200).t().contiguous()), None, dev(sh), sigmoid_out=True)
+    rel_close(got, torch.sigmoid(F.conv3d(x, wt, bias=sh)), 1e-5, "1x1 sigmoid")
+    f = rnd(46, 2, 16, 6, 10)                                      # 2-D feature map (FeatureAtt)
+    wt = rnd(47, 8, 16, 1, 1, scale=0.3)
+    got = ops.conv3d_1x1(dev(f), dev(wt.view(8, 16).t().contiguous()), act=ops.ACT_LEAKY)
+    rel_close(got, F.leaky_relu(F.conv2d(f, wt)), 1e-5, "1x1 2d")

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Per-kernel timing at the BASELINE config-2 shapes (GwcNet, B=8, 256x512, D=192) with CUDA events.
+
+    python tools/kbench.py [--batch 8] [--iters 20] [--only volume,softargmin,conv]
+
+Prints one JSON line per kernel: duration, algorithmic bytes / flops and the achieved
+HBM GB/s or fp32 TFLOP/s.  An L2 flush (a 256 MB write) runs between timed launches.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from openstereo_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        fn()
+        stop.record()
+        stop.synchronize()
+        times.append(start.elapsed_time(stop))
+    times.sort()
+    return times[len(times) // 2], times[0]
+
+
+def report(name, ms, best, bytes_=None, flops=None, **extra):
+    line = {"kernel": name, "ms_median": round(ms, 4), "ms_best": round(best, 4)}
+    if bytes_:
+        line["alg_bytes"] = bytes_
+        line["GBps"] = round(bytes_ / ms / 1e6, 1)
+    if flops:
+        line["flops"] = flops
+        line["TFLOPs"] = round(flops / ms / 1e9, 2)
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="volume,softargmin,conv")
+    a = ap.parse_args()
+    only = set(a.only.split(","))
+    B = a.batch
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    H, W, D = 64, 128, 48
+    if "volume" in only:
+        lg, rg = torch.randn(B, 320, H, W, device=dev), torch.randn(B, 320, H, W, device=dev)
+        lc, rc = torch.randn(B, 12, H, W, device=dev), torch.randn(B, 12, H, W, device=dev)
+        ms, best = timeit(lambda: ops.build_gwc_volume(lg, rg, D, 40), a.iters, flush)
+        report("gwc_volume", ms, best, 4 * (2 * B * 320 * H * W + B * 40 * D * H * W))
+        ms, best = timeit(lambda: ops.build_concat_volume(lc, rc, D), a.iters, flush)
+        report("concat_volume", ms, best, 4 * (2 * B * 12 * H * W + B * 24 * D * H * W))
+        ms, best = timeit(lambda: ops.gwc_concat_volume(lg, rg, lc, rc, D, 40), a.iters, flush)
+        report("gwc_concat_fused", ms, best, 4 * (2 * B * 332 * H * W + B * 64 * D * H * W))
+        l, r = torch.randn(16, 24, 80, 184, device=dev), torch.randn(16, 24, 80, 184, device=dev)
+        ms, best = timeit(lambda: ops.correlation_volume(l, r, 48), a.iters, flush)
+        report("corr_volume_c4", ms, best, 4 * (2 * 16 * 24 * 80 * 184 + 16 * 48 * 80 * 184))
+        l, r = torch.randn(8, 96, 120, 160, device=dev), torch.randn(8, 96, 120, 160, device=dev)
+        ms, best = timeit(lambda: ops.build_gwc_volume(l, r, 48, 8), a.iters, flush)
+        report("gwc_volume_c5_igev", ms, best, 4 * (2 * 8 * 96 * 120 * 160 + 8 * 8 * 48 * 120 * 160))
+        del lg, rg, lc, rc, l, r
+    if "softargmin" in only:
+        cost = torch.randn(B, 1, D, H, W, device=dev) * 4
+        ms, best = timeit(lambda: ops.upsample_softargmin(cost, 192, 256, 512), a.iters, flush)
+        report("upsample_softargmin", ms, best, 4 * (B * D * H * W + B * 256 * 512), exps=B * 256 * 512 * 240)
+        full = torch.randn(B, 192, 256, 512, device=dev)
+        ms, best = timeit(lambda: ops.softargmin(full, 192), a.iters, flush)
+        report("softargmin_fullres", ms, best, 4 * (B * 192 * 256 * 512 + B * 256 * 512))
+        del full, cost
+    if "conv" in only:
+        def conv_case(name, cin, cout, d, h, w, stride):
+            x = torch.randn(B, cin, d, h, w, device=dev)
+            wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.05)
+            sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1
+            ms, best = timeit(lambda: ops.conv3d_k3(x, wp, sc, sh, None, None, stride, ops.ACT_RELU), a.iters, flush)
+            do, ho, wo = (d - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
+            report(name, ms, best, flops=2 * B * cout * cin * 27 * do * ho * wo)
+
+        conv_case("conv3d_64to32_full", 64, 32, 48, 64, 128, 1)
+        conv_case("conv3d_32to32_full", 32, 32, 48, 64, 128, 1)
+        conv_case("conv3d_32to64_s2", 32, 64, 48, 64, 128, 2)
+        conv_case("conv3d_64to64_half", 64, 64, 24, 32, 64, 1)
+        conv_case("conv3d_64to128_s2", 64, 128, 24, 32, 64, 2)
+        conv_case("conv3d_128to128_quarter", 128, 128, 12, 16, 32, 1)
+        conv_case("conv3d_32to1_full", 32, 1, 48, 64, 128, 1)
+        for name, cin, cout, d, h, w in [("deconv3d_128to64", 128, 64, 12, 16, 32), ("deconv3d_64to32", 64, 32, 24, 32, 64)]:
+            x = torch.randn(B, cin, d, h, w, device=dev)
+            wp = ops.pack_deconv_weight(torch.randn(cin, cout, 3, 3, 3, device=dev) * 0.05)
+            ms, best = timeit(lambda: ops.deconv3d(x, wp, None, None, None, 3, ops.ACT_RELU), a.iters, flush)
+            report(name, ms, best, flops=2 * B * cout * cin * 27 * d * h * w)
+        x = torch.randn(B, 32, 48, 64, 128, device=dev)
+        wp = (torch.randn(32, 32, device=dev) * 0.1).contiguous()
+        ms, best = timeit(lambda: ops.conv3d_1x1(x, wp), a.iters, flush)
+        report("conv1x1_32to32_full", ms, best, bytes_=4 * 2 * B * 32 * 48 * 64 * 128)
+
+
+if __name__ == "__main__":
+    main()
