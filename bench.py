@@ -128,6 +128,25 @@ class ClockSampler:
         return out
 
 
+def usable_cores():
+    """Host threads this process may really use: min(affinity mask, cgroup CPU quota) -- os.cpu_count() alone
+    oversubscribes a quota-limited container and makes the CPU arm look far slower than it is."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,7 +191,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model = oracle_model()
     pairs = 1                                                       # bounded sample: one pair of the B=8 batch per step
@@ -231,13 +250,10 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()               # the caller reads the metric every step
             return part
 
+    from openstereo_b200.distributed import gather_epe_partials
+
     def gather(part):
-        if world == 1:
-            return part
-        import torch.distributed as dist
-        out = [torch.empty_like(part) for _ in range(world)]
-        dist.all_gather(out, part)                                  # the single collective of the path
-        return torch.cat(out, 0)
+        return gather_epe_partials(part)[0]                         # the single collective of the path (NCCL all_gather)
 
     def timed(step_fn, steps, profile):
         barrier(world)
@@ -323,7 +339,7 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         torch.set_num_threads(cores)
         cm = oracle_model()
         n = 4

@@ -24,8 +24,8 @@ SIGNATURES = {
     "osb_upsample_softargmin_fwd": [_f32p, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _s],
     "osb_epe_partial_fwd": [_f32p, _f32p, _f32p, _i, _i, _f, _s],
     "osb_conv3d_k3_bn_act_fwd": [_f32p] * 7 + [_i] * 8 + [_s],
-    "osb_deconv3d_bn_act_fwd": [_f32p] * 6 + [_i] * 7 + [_s],
-    "osb_conv3d_1x1_bn_act_fwd": [_f32p, _f32p, _i] + [_f32p] * 6 + [_i] * 7 + [_s],
+    "osb_deconv3d_bn_act_fwd": [_f32p] * 6 + [_i] * 8 + [_s],
+    "osb_conv3d_1x1_bn_act_fwd": [_f32p, _f32p, _i] + [_f32p] * 6 + [_i] * 8 + [_s],
 }
 
 
@@ -59,6 +59,8 @@ _ERRORS = {1: ValueError, 2: RuntimeError, 3: NotImplementedError}
 
 def call(name, *args):
     """Invoke an entry point; translate OSB_E* into the exception class the reference would raise."""
+    if len(args) != len(SIGNATURES[name]):          # ctypes would silently pass extra args as 32-bit ints
+        raise TypeError("%s takes %d arguments (%d given)" % (name, len(SIGNATURES[name]), len(args)))
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = (lib.osb_last_error() or b"").decode("utf-8", "replace")

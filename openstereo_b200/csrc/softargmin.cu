@@ -78,11 +78,29 @@ __host__ inline Axis make_axis(int in, int out, int align) {
 }
 
 // cost (B,Dl,Hl,Wl) low-res logits -> out (B,H,W).  aten nests the interpolation W innermost, D outermost, so the
-// per-pixel bilinear value t(i) of coarse slice i is computed once and the fine samples are lerps between t(i0), t(i1).
-// A lerp never exceeds max(t(i0), t(i1)), so the running maximum is updated once per coarse interval.
-__global__ void __launch_bounds__(256) upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ out,
+// per-pixel bilinear value t(c) of coarse slice c is computed once and the fine samples whose lower neighbour is c are
+// lerps between t(c) and t(c+1).  A lerp never exceeds max(t(c), t(c+1)), so the running maximum is updated once per
+// coarse interval (one extra exp per interval instead of one per sample).  The fine->coarse map depends on d only; it
+// is tabulated once per CTA in shared memory (lambda per fine sample, first fine sample per coarse interval).
+// Logits are pre-scaled by log2(e) so every exponential is a single MUFU.EX2.
+__global__ void __launch_bounds__(128) upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ out,
                                                                   int Dl, int Hl, int Wl, int D, int H, int W, Axis ad,
                                                                   Axis ah, Axis aw) {
+  extern __shared__ float s_tab[];
+  float* s_lam = s_tab;                                  // [D]   weight of the upper neighbour
+  int* s_first = reinterpret_cast<int*>(s_tab + D);      // [Dl+1] first fine sample of coarse interval c
+  for (int c = threadIdx.x; c <= Dl; c += blockDim.x) s_first[c] = D;
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    int i0, i1, p0 = -1, p1;
+    float l1, pl;
+    ad.locate(d, i0, i1, l1);
+    if (d > 0) ad.locate(d - 1, p0, p1, pl);
+    s_lam[d] = l1;
+    for (int c = p0 + 1; c <= i0; ++c) s_first[c] = d;   // i0 is non-decreasing in d
+  }
+  __syncthreads();
+
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -91,37 +109,44 @@ __global__ void __launch_bounds__(256) upsample_softargmin_kernel(const float* _
   float ly, lx;
   ah.locate(y, y0, y1, ly);
   aw.locate(x, x0, x1, lx);
-  const float hy = 1.f - ly, hx = 1.f - lx;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float hy = (1.f - ly) * kLog2e, hx = 1.f - lx;
+  ly *= kLog2e;
   const size_t slice = (size_t)Hl * Wl;
   const float* base = cost + (size_t)b * Dl * slice;
   const float* p00 = base + (size_t)y0 * Wl + x0;
   const float* p01 = base + (size_t)y0 * Wl + x1;
   const float* p10 = base + (size_t)y1 * Wl + x0;
   const float* p11 = base + (size_t)y1 * Wl + x1;
-  auto bilinear = [&](int i) {
-    const size_t o = (size_t)i * slice;
-    return hy * (hx * __ldg(p00 + o) + lx * __ldg(p01 + o)) + ly * (hx * __ldg(p10 + o) + lx * __ldg(p11 + o));
-  };
+  // raw corner values of one coarse slice; combined later so the loads have a whole interval to land
+  float a0 = __ldg(p00), a1 = __ldg(p01), a2 = __ldg(p10), a3 = __ldg(p11);
+  float t0 = hy * (hx * a0 + lx * a1) + ly * (hx * a2 + lx * a3);
+  if (Dl > 1) {
+    a0 = __ldg(p00 + slice), a1 = __ldg(p01 + slice), a2 = __ldg(p10 + slice), a3 = __ldg(p11 + slice);
+  }
   float m = -INFINITY, s = 0.f, t = 0.f;
-  int c0 = -1, c1 = -1;
-  float t0 = 0.f, t1 = 0.f;
-  for (int d = 0; d < D; ++d) {
-    int i0, i1;
-    float l1;
-    ad.locate(d, i0, i1, l1);
-    if (i0 != c0 || i1 != c1) {                        // entered a new coarse interval (uniform per warp: depends on d only)
-      t0 = (i0 == c1) ? t1 : bilinear(i0);
-      t1 = (i1 == i0) ? t0 : bilinear(i1);
-      c0 = i0, c1 = i1;
+  for (int c = 0; c < Dl; ++c) {
+    const float t1 = (c + 1 < Dl) ? hy * (hx * a0 + lx * a1) + ly * (hx * a2 + lx * a3) : t0;
+    if (c + 2 < Dl) {                                    // prefetch slice c+2
+      const size_t o = (size_t)(c + 2) * slice;
+      a0 = __ldg(p00 + o), a1 = __ldg(p01 + o), a2 = __ldg(p10 + o), a3 = __ldg(p11 + o);
+    }
+    const int dbeg = s_first[c], dend = s_first[c + 1];
+    if (dbeg < dend) {
       const float nm = fmaxf(m, fmaxf(t0, t1));
-      const float sc = expf(m - nm);
+      const float sc = exp2f(m - nm);                    // exp2(-inf) = 0 on the first interval
       s *= sc, t *= sc;
       m = nm;
+      const float dt = t1 - t0, tm = t0 - m;
+      float fd = (float)dbeg;
+      for (int d = dbeg; d < dend; ++d) {
+        const float e = exp2f(fmaf(s_lam[d], dt, tm));   // (1-l)*t0 + l*t1 - m
+        s += e;
+        t = fmaf(e, fd, t);
+        fd += 1.f;
+      }
     }
-    const float v = (1.f - l1) * t0 + l1 * t1;
-    const float e = expf(v - m);
-    s += e;
-    t = fmaf(e, (float)d, t);
+    t0 = t1;
   }
   out[((size_t)b * H + y) * W + x] = t / s;
 }
@@ -178,7 +203,8 @@ int osb_upsample_softargmin_fwd(const float* cost, float* out, int B, int Dl, in
   OSB_REQUIRE(B > 0 && Dl > 0 && Hl > 0 && Wl > 0 && D > 0 && H > 0 && W > 0, "upsample_softargmin: empty shape");
   OSB_REQUIRE(H <= 65535 && B <= 65535, "upsample_softargmin: grid too large");
   dim3 grid((W + 127) / 128, H, B);
-  osb::upsample_softargmin_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+  OSB_REQUIRE((size_t)(D + Dl + 1) * 4 <= 48 * 1024, "upsample_softargmin: D=%d too large for the shared tables", D);
+  osb::upsample_softargmin_kernel<<<grid, 128, (size_t)(D + Dl + 1) * 4, (cudaStream_t)stream>>>(
       cost, out, Dl, Hl, Wl, D, H, W, osb::make_axis(Dl, D, align_corners), osb::make_axis(Hl, H, align_corners),
       osb::make_axis(Wl, W, align_corners));
   osb::count_launch();

@@ -7,8 +7,10 @@
 //   torch.cat((gwc, concat), 1)  gwcnet_cost_processor.py:65
 // with ONE launch that writes every output row exactly once (zeros of the w<d triangle included, so no memset).
 //
-// Work decomposition.  A CTA owns one image row (b, h), one 128-column tile, one chunk of <=64 disparities and one
-// "unit" of GU output channels; warp = one output channel (a correlation group or a concat channel), lane = four
+// Work decomposition.  A work item is one image row (b, h), one 128-column tile, one chunk of <=64 disparities and one
+// "unit" of GU output channels; the kernel is persistent (2 CTAs per SM, grid = a multiple of the SM count) and each CTA
+// walks the item list through a two-stage shared-memory ring, so the TMA load of the next item overlaps the FMAs and
+// stores of the current one.  Within an item warp = one output channel (a correlation group or a concat channel), lane = four
 // consecutive columns (a 16-byte quad), so every store instruction of a warp is one contiguous 512-byte row segment.
 //
 // gwc unit: the right-image rows of the unit's GU*K feature channels are staged in shared memory by ONE TMA tile load
@@ -63,141 +65,209 @@ __device__ __forceinline__ void store_quad(float* row, int w, int W, bool vec, f
   }
 }
 
-__global__ void __launch_bounds__(256) volume_kernel(const __grid_constant__ CUtensorMap tgt_map, const VolParams p) {
+struct Item {
+  int unit, h, b, w0, d0;
+};
+__device__ __forceinline__ Item decode_item(const VolParams& p, int it) {
+  Item i;
+  const int units = p.n_gwc_units + p.n_cat_units;
+  i.unit = it % units;
+  it /= units;
+  i.h = it % p.H;
+  it /= p.H;
+  i.d0 = (it % p.d_chunks) * kChunkD;
+  it /= p.d_chunks;
+  i.w0 = (it % p.w_tiles) * kTileW;
+  i.b = it / p.w_tiles;
+  return i;
+}
+
+// Persistent kernel: gridDim.x = resident CTAs (2 per SM); each CTA walks the item list with a 2-stage shared-memory
+// ring.  While the warps compute item i out of buffer s, the TMA engine is already filling buffer s^1 for item i+grid.
+__global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ CUtensorMap tgt_map, const VolParams p,
+                                                        const int total_items) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int z = blockIdx.z;
-  const int dchunk = z % p.d_chunks;
-  z /= p.d_chunks;
-  const int wt = z % p.w_tiles;
-  const int b = z / p.w_tiles;
-  const int h = blockIdx.y;
-  const int w0 = wt * kTileW, d0 = dchunk * kChunkD;
-  const int wq = w0 + 4 * lane;                       // first column of this lane's quad
-  const int nd = min(kChunkD, p.D - d0);
-  const int nquads = (nd + 3) >> 2;
-  const int col0 = w0 - d0 - kChunkD;                 // global column of staged column 0
+  const int rows = p.n_gwc_units > 0 ? p.GU * p.K : p.GU;          // staged channel rows per buffer
+  const size_t buf_floats = (size_t)rows * kRowW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * buf_floats);
   const size_t HW = (size_t)p.H * p.W;
   const bool vec = p.vec_ok != 0;
+  const uint32_t tx_bytes = (uint32_t)rows * kRowW * 4u;
 
-  if ((int)blockIdx.x < p.n_gwc_units) {
-    // ------------------------------------------------------------------ group-wise correlation unit
-    const int g0 = blockIdx.x * p.GU;
-    const int rows = p.GU * p.K;                      // staged channel rows (box height)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)rows * kRowW);
-    if (p.use_tma) {
-      if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_arrive_expect_tx(bar, (uint32_t)rows * kRowW * 4u);
-        tma_load_3d(smem, &tgt_map, bar, col0, h, b * p.Cg + g0 * p.K);
-      }
-      __syncthreads();                                // barrier init visible before anyone polls it
-      mbar_wait(bar, 0);
-    } else {
-      const int live = min(rows, p.Cg - g0 * p.K);
-      for (int idx = threadIdx.x; idx < live * kRowW; idx += blockDim.x) {
-        const int r = idx / kRowW, c = idx - r * kRowW;
-        const int gw = col0 + c;
-        float v = 0.f;
-        if (gw >= 0 && gw < p.W) v = __ldg(p.tgt_g + ((size_t)(b * p.Cg + g0 * p.K + r) * p.H + h) * p.W + gw);
-        smem[idx] = v;
-      }
-      __syncthreads();
+  if (p.use_tma && threadIdx.x == 0) {
+    tma_prefetch_desc(&tgt_map);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue_tma = [&](int it, int stage) {                         // thread 0 only
+    const Item n = decode_item(p, it);
+    if (n.unit < p.n_gwc_units) {
+      fence_proxy_async();                                          // generic-proxy accesses of this buffer are done
+      mbar_arrive_expect_tx(&bars[stage], tx_bytes);
+      tma_load_3d(smem + stage * buf_floats, &tgt_map, &bars[stage], n.w0 - n.d0 - kChunkD, n.h,
+                  n.b * p.Cg + n.unit * p.GU * p.K);
     }
-    const int g = g0 + warp;
-    if (g >= p.G || wq >= p.W) return;
-    const float* lrow = p.ref_g + ((size_t)(b * p.Cg + g * p.K) * p.H + h) * p.W;
-    const float* rbase = smem + (size_t)warp * p.K * kRowW;
-    float* obase = p.out + (((size_t)(b * p.Ctot + g) * p.D) * p.H + h) * p.W;   // + d*HW
-    for (int j0 = 0; j0 < nquads; j0 += kJG) {
-      float acc[kJG][4][4];
-#pragma unroll
-      for (int jj = 0; jj < kJG; ++jj)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int a = 0; a < 4; ++a) acc[jj][i][a] = 0.f;
-      const int win = kChunkD + 4 * (lane - j0) - 16;  // first float of the 20-float window, in [0, 172]
-#pragma unroll 2
-      for (int k = 0; k < p.K; ++k) {
-        const float4 l4 = load_quad(lrow + (size_t)k * HW, wq, p.W, vec);
-        const float l[4] = {l4.x, l4.y, l4.z, l4.w};
-        float r[20];
-        const float4* rp = reinterpret_cast<const float4*>(rbase + (size_t)k * kRowW + win);
-#pragma unroll
-        for (int n = 0; n < 5; ++n) {
-          const float4 t = rp[n];
-          r[4 * n + 0] = t.x, r[4 * n + 1] = t.y, r[4 * n + 2] = t.z, r[4 * n + 3] = t.w;
+  };
+
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  if (p.use_tma && threadIdx.x == 0 && (int)blockIdx.x < total_items) issue_tma(blockIdx.x, 0);
+
+  for (int it = blockIdx.x; it < total_items; it += gridDim.x, stage ^= 1) {
+    const Item cur = decode_item(p, it);
+    const int nxt = it + gridDim.x;
+    if (p.use_tma && threadIdx.x == 0 && nxt < total_items) issue_tma(nxt, stage ^ 1);
+    float* buf = smem + stage * buf_floats;
+    const int h = cur.h, b = cur.b, w0 = cur.w0, d0 = cur.d0;
+    const int wq = w0 + 4 * lane;                                   // first column of this lane's quad
+    const int nd = min(kChunkD, p.D - d0);
+    const int nquads = (nd + 3) >> 2;
+    const int col0 = w0 - d0 - kChunkD;                             // global column of staged column 0
+
+    if (cur.unit < p.n_gwc_units) {
+      // ---------------------------------------------------------------- group-wise correlation unit
+      const int g0 = cur.unit * p.GU;
+      if (p.use_tma) {
+        if (stage == 0) {
+          mbar_wait(&bars[0], phase0);
+          phase0 ^= 1;
+        } else {
+          mbar_wait(&bars[1], phase1);
+          phase1 ^= 1;
         }
-#pragma unroll
-        for (int jj = 0; jj < kJG; ++jj)
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) acc[jj][i][a] = fmaf(l[a], r[16 - 4 * jj + a - i], acc[jj][i][a]);
+      } else {
+        const int live = min(rows, p.Cg - g0 * p.K);
+        for (int idx = threadIdx.x; idx < live * kRowW; idx += blockDim.x) {
+          const int r = idx / kRowW, c = idx - r * kRowW;
+          const int gw = col0 + c;
+          float v = 0.f;
+          if (gw >= 0 && gw < p.W) v = __ldg(p.tgt_g + ((size_t)(b * p.Cg + g0 * p.K + r) * p.H + h) * p.W + gw);
+          buf[idx] = v;
+        }
+        __syncthreads();
       }
+      const int g = g0 + warp;
+      if (g < p.G && wq < p.W) {
+        const float* lrow = p.ref_g + ((size_t)(b * p.Cg + g * p.K) * p.H + h) * p.W;
+        const float* rbase = buf + (size_t)warp * p.K * kRowW;
+        float* obase = p.out + (((size_t)(b * p.Ctot + g) * p.D) * p.H + h) * p.W;   // + d*HW
+        for (int j0 = 0; j0 < nquads; j0 += kJG) {
+          float acc[kJG][4][4];
 #pragma unroll
-      for (int jj = 0; jj < kJG; ++jj) {
+          for (int jj = 0; jj < kJG; ++jj)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int d = d0 + 4 * (j0 + jj) + i;
-          if (d < p.D && 4 * (j0 + jj) + i < nd) {
-            float4 v;
-            v.x = (wq + 0 >= d) ? acc[jj][i][0] * p.inv_k : 0.f;
-            v.y = (wq + 1 >= d) ? acc[jj][i][1] * p.inv_k : 0.f;
-            v.z = (wq + 2 >= d) ? acc[jj][i][2] * p.inv_k : 0.f;
-            v.w = (wq + 3 >= d) ? acc[jj][i][3] * p.inv_k : 0.f;
-            store_quad(obase + (size_t)d * HW, wq, p.W, vec, v);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int a = 0; a < 4; ++a) acc[jj][i][a] = 0.f;
+          const int win = kChunkD + 4 * (lane - j0) - 16;           // first float of the 20-float window, in [0, 172]
+          for (int k0 = 0; k0 < p.K; k0 += 4) {
+            float4 lq[4];                                           // four independent global loads in flight
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              lq[kk] = (k0 + kk < p.K) ? load_quad(lrow + (size_t)(k0 + kk) * HW, wq, p.W, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (k0 + kk < p.K) {
+                const float l[4] = {lq[kk].x, lq[kk].y, lq[kk].z, lq[kk].w};
+                float r[20];
+                const float4* rp = reinterpret_cast<const float4*>(rbase + (size_t)(k0 + kk) * kRowW + win);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                  const float4 t = rp[n];
+                  r[4 * n + 0] = t.x, r[4 * n + 1] = t.y, r[4 * n + 2] = t.z, r[4 * n + 3] = t.w;
+                }
+#pragma unroll
+                for (int jj = 0; jj < kJG; ++jj)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) acc[jj][i][a] = fmaf(l[a], r[16 - 4 * jj + a - i], acc[jj][i][a]);
+              }
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < kJG; ++jj) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int d = d0 + 4 * (j0 + jj) + i;
+              if (4 * (j0 + jj) + i < nd) {
+                float4 v;
+                v.x = (wq + 0 >= d) ? acc[jj][i][0] * p.inv_k : 0.f;
+                v.y = (wq + 1 >= d) ? acc[jj][i][1] * p.inv_k : 0.f;
+                v.z = (wq + 2 >= d) ? acc[jj][i][2] * p.inv_k : 0.f;
+                v.w = (wq + 3 >= d) ? acc[jj][i][3] * p.inv_k : 0.f;
+                store_quad(obase + (size_t)d * HW, wq, p.W, vec, v);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // ---------------------------------------------------------------- concatenation unit (shifted copy)
+      const int oc = (cur.unit - p.n_gwc_units) * p.GU + warp;
+      if (oc < 2 * p.Cc) {
+        const bool left = oc < p.Cc;
+        float* obase = p.out + (((size_t)(b * p.Ctot + p.oc_cat + oc) * p.D) * p.H + h) * p.W;
+        if (left) {
+          if (wq < p.W) {
+            const float4 v = load_quad(p.ref_c + ((size_t)(b * p.Cc + oc) * p.H + h) * p.W, wq, p.W, vec);
+            for (int dd = 0; dd < nd; ++dd) {
+              const int d = d0 + dd;
+              float4 o = v;
+              if (p.mask_left) {
+                o.x = (wq + 0 >= d) ? v.x : 0.f;
+                o.y = (wq + 1 >= d) ? v.y : 0.f;
+                o.z = (wq + 2 >= d) ? v.z : 0.f;
+                o.w = (wq + 3 >= d) ? v.w : 0.f;
+              }
+              store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
+            }
+          }
+        } else {
+          float* row = buf + (size_t)warp * kRowW;
+          const float* src = p.tgt_c + ((size_t)(b * p.Cc + (oc - p.Cc)) * p.H + h) * p.W;
+          for (int c = lane; c < kRowW; c += 32) {
+            const int gw = col0 + c;
+            row[c] = (gw >= 0 && gw < p.W) ? __ldg(src + gw) : 0.f;
+          }
+          __syncwarp();
+          if (wq < p.W) {
+            for (int j = 0; j < nquads; ++j) {
+              const float4 lo = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j) - 4);
+              const float4 hi = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j));
+              const float wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int d = d0 + 4 * j + i;
+                if (4 * j + i < nd) {
+                  float4 o;                                         // columns w<d read the zero-filled halo
+                  o.x = wv[4 - i], o.y = wv[5 - i], o.z = wv[6 - i], o.w = wv[7 - i];
+                  store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
+                }
+              }
+            }
           }
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ concatenation unit (shifted copy)
-    const int oc = ((int)blockIdx.x - p.n_gwc_units) * p.GU + warp;
-    if (oc >= 2 * p.Cc) return;
-    const bool left = oc < p.Cc;
-    float* obase = p.out + (((size_t)(b * p.Ctot + p.oc_cat + oc) * p.D) * p.H + h) * p.W;
-    if (left) {
-      if (wq >= p.W) return;
-      const float4 v = load_quad(p.ref_c + ((size_t)(b * p.Cc + oc) * p.H + h) * p.W, wq, p.W, vec);
-      for (int dd = 0; dd < nd; ++dd) {
-        const int d = d0 + dd;
-        float4 o = v;
-        if (p.mask_left) {
-          o.x = (wq + 0 >= d) ? v.x : 0.f;
-          o.y = (wq + 1 >= d) ? v.y : 0.f;
-          o.z = (wq + 2 >= d) ? v.z : 0.f;
-          o.w = (wq + 3 >= d) ? v.w : 0.f;
-        }
-        store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
-      }
-    } else {
-      float* row = smem + (size_t)warp * kRowW;
-      const float* src = p.tgt_c + ((size_t)(b * p.Cc + (oc - p.Cc)) * p.H + h) * p.W;
-      for (int c = lane; c < kRowW; c += 32) {
-        const int gw = col0 + c;
-        row[c] = (gw >= 0 && gw < p.W) ? __ldg(src + gw) : 0.f;
-      }
-      __syncwarp();
-      if (wq >= p.W) return;
-      for (int j = 0; j < nquads; ++j) {
-        const float4 lo = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j) - 4);
-        const float4 hi = *reinterpret_cast<const float4*>(row + kChunkD + 4 * (lane - j));
-        const float wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int d = d0 + 4 * j + i;
-          if (4 * j + i < nd) {
-            float4 o;                                  // columns w<d read the zero-filled halo
-            o.x = wv[4 - i], o.y = wv[5 - i], o.z = wv[6 - i], o.w = wv[7 - i];
-            store_quad(obase + (size_t)d * HW, wq, p.W, vec, o);
-          }
-        }
-      }
+    __syncthreads();                                                // buffer `stage` may be refilled from now on
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = 148;
     }
   }
+  return n;
 }
 
 static int launch_volume(const float* ref_g, const float* tgt_g, const float* ref_c, const float* tgt_c, float* out,
@@ -208,7 +278,7 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   if (Cg > 0) {
     OSB_REQUIRE(G > 0 && Cg % G == 0, "groupwise_correlation: C=%d not divisible by num_groups=%d", Cg, G);
     K = Cg / G;
-    OSB_REQUIRE(K <= 256, "volume: %d channels per group exceeds the 256 supported", K);
+    OSB_REQUIRE(K <= 144, "volume: %d channels per group exceeds the 144 supported (two-stage 192-float rows in 227 KB)", K);
   } else {
     G = 0;
   }
@@ -231,7 +301,7 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = (W % 4 == 0) && aligned16(ref_g) && aligned16(ref_c) && aligned16(out);
   const int rows = Cg > 0 ? GU * K : GU;
-  size_t smem = (size_t)rows * kRowW * sizeof(float) + 16;
+  size_t smem = 2 * (size_t)rows * kRowW * sizeof(float) + 16;    // two-stage ring + two mbarriers
   CUtensorMap map{};
   p.use_tma = 0;
   if (Cg > 0 && W % 4 == 0 && aligned16(tgt_g) && rows <= 256) {
@@ -249,9 +319,18 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
     }
     configured = smem;
   }
-  dim3 grid(p.n_gwc_units + p.n_cat_units, H, B * p.w_tiles * p.d_chunks);
-  OSB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "volume: grid too large (H=%d, B*tiles=%u)", H, grid.z);
-  volume_kernel<<<grid, 32 * GU, smem, stream>>>(map, p);
+  const long long total = (long long)(p.n_gwc_units + p.n_cat_units) * H * B * p.w_tiles * p.d_chunks;
+  OSB_REQUIRE(total < (1ll << 31), "volume: too many work items (%lld)", total);
+  int per_sm = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, volume_kernel, 32 * GU, smem);
+  if (oe != cudaSuccess || per_sm < 1) {
+    set_error("volume: occupancy query failed (%s), smem=%zu", cudaGetErrorString(oe), smem);
+    (void)cudaGetLastError();
+    return OSB_ECUDA;
+  }
+  long long grid = (long long)sm_count() * per_sm;                // persistent: every CTA resident, multiple of the SM count
+  if (grid > total) grid = total;
+  volume_kernel<<<(unsigned)grid, 32 * GU, smem, stream>>>(map, p, (int)total);
   count_launch();
   return check_launch("volume_kernel");
 }

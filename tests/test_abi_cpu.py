@@ -35,6 +35,24 @@ def test_header_symbols_exported(native):
         assert name in names
 
 
+def test_binding_signatures_match_header(native):
+    """Arity and C types of every ctypes binding are checked against the prototypes in the header."""
+    text = open(os.path.join(ROOT, "include", "openstereo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    kinds = {"const float*": ctypes.c_void_p, "float*": ctypes.c_void_p, "int": ctypes.c_int, "float": ctypes.c_float,
+             "osb_stream_t": ctypes.c_void_p}
+    for name, argtypes in native.SIGNATURES.items():
+        m = re.search(r"int\s+%s\s*\(([^)]*)\)" % name, text)
+        assert m, name
+        params = [p.strip() for p in m.group(1).replace("\n", " ").split(",")]
+        want = []
+        for p in params:
+            ctype = p.rsplit(" ", 1)[0].strip()
+            assert ctype in kinds, (name, p)
+            want.append(kinds[ctype])
+        assert want == list(argtypes), "%s: header %d params vs binding %d" % (name, len(want), len(argtypes))
+
+
 def test_version_and_error_channel(native):
     assert native.lib.osb_abi_version() == 1
     assert native.launch_count() >= 0

@@ -104,7 +104,7 @@ def test_stereobase_config3_subgraph(osb):
     ml, mr, cl, cr = r(1, 96, 32, 64), r(1, 96, 32, 64), r(1, 8, 32, 64), r(1, 8, 32, 64)
     feats = [r(1, 96, 32, 64), r(1, 64, 16, 32), r(1, 192, 8, 16), r(1, 160, 4, 8)]
     m = oagg.StereoBaseCostHead(24, [96, 64, 192, 160], max_disp=192).eval()
-    m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=9, scale={"classifier.weight": 30.0}))
+    m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=9, scale={"classifier.weight": 150.0}))
     with torch.no_grad():
         vol = torch.cat((ocv.build_gwc_volume(ml, mr, 48, 8), ocv.build_concat_volume(cl, cr, 48)), 1)
         geo_want, init_want = m(vol, feats)
