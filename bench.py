@@ -291,7 +291,11 @@ def run_ours(args):
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()
+    if os.environ.get("OSB_NCU_RANGE"):                             # `ncu --profile-from-start off`: capture only the timed steps
+        torch.cuda.cudart().cudaProfilerStart()
     ms, launches, prof, parts = timed(step_resident, args.steps, profile=True)
+    if os.environ.get("OSB_NCU_RANGE"):
+        torch.cuda.cudart().cudaProfilerStop()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, profile=False)
     clocks = sampler.stop(args.gpus) if rank == 0 else None
     if rank != 0:

@@ -84,6 +84,7 @@ __device__ __forceinline__ Item decode_item(const VolParams& p, int it) {
 
 // Persistent kernel: gridDim.x = resident CTAs (2 per SM); each CTA walks the item list with a 2-stage shared-memory
 // ring.  While the warps compute item i out of buffer s, the TMA engine is already filling buffer s^1 for item i+grid.
+template <bool VEC, bool K4>
 __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ CUtensorMap tgt_map, const VolParams p,
                                                         const int total_items) {
   extern __shared__ __align__(128) float smem[];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ 
   const size_t buf_floats = (size_t)rows * kRowW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * buf_floats);
   const size_t HW = (size_t)p.H * p.W;
-  const bool vec = p.vec_ok != 0;
+  constexpr bool vec = VEC;
   const uint32_t tx_bytes = (uint32_t)rows * kRowW * 4u;
 
   if (p.use_tma && threadIdx.x == 0) {
@@ -168,11 +169,12 @@ __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ 
             float4 lq[4];                                           // four independent global loads in flight
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              lq[kk] = (k0 + kk < p.K) ? load_quad(lrow + (size_t)(k0 + kk) * HW, wq, p.W, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+              lq[kk] = (K4 || k0 + kk < p.K) ? load_quad(lrow + (size_t)(k0 + kk) * HW, wq, p.W, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              if (k0 + kk < p.K) {
-                const float l[4] = {lq[kk].x, lq[kk].y, lq[kk].z, lq[kk].w};
+              if (K4 || k0 + kk < p.K) {
+                // the 1/K of the mean is folded into the left operand (4 multiplies per channel instead of 64 per pass)
+                const float l[4] = {lq[kk].x * p.inv_k, lq[kk].y * p.inv_k, lq[kk].z * p.inv_k, lq[kk].w * p.inv_k};
                 float r[20];
                 const float4* rp = reinterpret_cast<const float4*>(rbase + (size_t)(k0 + kk) * kRowW + win);
 #pragma unroll
@@ -196,10 +198,10 @@ __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ 
               const int d = d0 + 4 * (j0 + jj) + i;
               if (4 * (j0 + jj) + i < nd) {
                 float4 v;
-                v.x = (wq + 0 >= d) ? acc[jj][i][0] * p.inv_k : 0.f;
-                v.y = (wq + 1 >= d) ? acc[jj][i][1] * p.inv_k : 0.f;
-                v.z = (wq + 2 >= d) ? acc[jj][i][2] * p.inv_k : 0.f;
-                v.w = (wq + 3 >= d) ? acc[jj][i][3] * p.inv_k : 0.f;
+                v.x = (wq + 0 >= d) ? acc[jj][i][0] : 0.f;
+                v.y = (wq + 1 >= d) ? acc[jj][i][1] : 0.f;
+                v.z = (wq + 2 >= d) ? acc[jj][i][2] : 0.f;
+                v.w = (wq + 3 >= d) ? acc[jj][i][3] : 0.f;
                 store_quad(obase + (size_t)d * HW, wq, p.W, vec, v);
               }
             }
@@ -310,19 +312,25 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
                            kRowW, 1, (uint32_t)rows))
       p.use_tma = 1;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  using KernelFn = void (*)(const CUtensorMap, const VolParams, const int);
+  const bool k4 = (K % 4 == 0);                                   // K = 0 (concat only) counts as a multiple
+  const int variant = (p.vec_ok ? 2 : 0) | (k4 ? 1 : 0);
+  static const KernelFn kernels[4] = {volume_kernel<false, false>, volume_kernel<false, true>, volume_kernel<true, false>,
+                                      volume_kernel<true, true>};
+  KernelFn kernel = kernels[variant];
+  static size_t configured[4] = {0, 0, 0, 0};
+  if (smem > configured[variant]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("volume: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = smem;
+    configured[variant] = smem;
   }
   const long long total = (long long)(p.n_gwc_units + p.n_cat_units) * H * B * p.w_tiles * p.d_chunks;
   OSB_REQUIRE(total < (1ll << 31), "volume: too many work items (%lld)", total);
   int per_sm = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, volume_kernel, 32 * GU, smem);
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * GU, smem);
   if (oe != cudaSuccess || per_sm < 1) {
     set_error("volume: occupancy query failed (%s), smem=%zu", cudaGetErrorString(oe), smem);
     (void)cudaGetLastError();
@@ -330,7 +338,7 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   }
   long long grid = (long long)sm_count() * per_sm;                // persistent: every CTA resident, multiple of the SM count
   if (grid > total) grid = total;
-  volume_kernel<<<(unsigned)grid, 32 * GU, smem, stream>>>(map, p, (int)total);
+  kernel<<<(unsigned)grid, 32 * GU, smem, stream>>>(map, p, (int)total);
   count_launch();
   return check_launch("volume_kernel");
 }

@@ -255,3 +255,47 @@ def conv3d_1x1(x0, w_packed, scale=None, shift=None, residual=None, gate=None, a
     _call("osb_conv3d_1x1_bn_act_fwd", x0.data_ptr(), _ptr(x1), c0, w_packed.data_ptr(), _ptr(scale), _ptr(shift),
               _ptr(residual), _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, act, 1 if sigmoid_out else 0, _stream())
     return y.squeeze(2) if squeeze else y
+
+
+# --------------------------------------------------------------------------- tensor-core conv (tcgen05, 3xTF32)
+def conv3d_tc_supported(cin, cout, w, stride=1):
+    return bool(_lib.lib.osb_conv3d_tc_supported(int(cin), int(cout), int(w), int(stride)))
+
+
+def pack_tc_weight(weight):
+    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/16][3 kh][3*Cout (kw-major)][16] fp32.
+    hi = the value with its low 13 mantissa bits cleared (what a kind::tf32 MMA reads), lo = value - hi (exact)."""
+    w = weight.detach().float()
+    cout, cin = w.shape[:2]
+    assert cin % 16 == 0 and tuple(w.shape[2:]) == (3, 3, 3)
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    lo = w - hi
+    both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
+    both = both.view(2, cout, cin // 16, 16, 3, 3, 3)                  # (2, co, chunk, ci16, kd, kh, kw)
+    both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci16)
+    return both.reshape(2, 3, cin // 16, 3, 3 * cout, 16).contiguous()
+
+
+def to_ndhwc(x):
+    """(B,C,D,H,W) -> (B,D,H,W,C) contiguous fp32, on the device."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
+    b, c, d, h, w = x.shape
+    y = torch.empty((b, d, h, w, c), dtype=torch.float32, device=x.device)
+    _call("osb_ncdhw_to_ndhwc", x.data_ptr(), y.data_ptr(), b, c, d, h, w, _stream())
+    return y
+
+
+def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=True, res_ndhwc=True):
+    """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    cout = w_split.shape[4] // 3
+    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    shape = (b, d, h, w, cout) if out_ndhwc else (b, cout, d, h, w)
+    y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
+    if residual is not None:
+        want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
+        assert tuple(residual.shape) == want and residual.is_contiguous()
+    _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+    return y

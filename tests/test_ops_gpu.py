@@ -254,3 +254,33 @@ def test_conv3d_1x1(ops):
     wt = rnd(47, 8, 16, 1, 1, scale=0.3)
     got = ops.conv3d_1x1(dev(f), dev(wt.view(8, 16).t().contiguous()), act=ops.ACT_LEAKY)
     rel_close(got, F.leaky_relu(F.conv2d(f, wt)), 1e-5, "1x1 2d")
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core conv (3xTF32)
+def test_to_ndhwc(ops):
+    x = rnd(50, 2, 40, 3, 5, 16)
+    assert torch.equal(ops.to_ndhwc(dev(x)).cpu(), x.permute(0, 2, 3, 4, 1).contiguous())
+
+
+@pytest.mark.parametrize("b,cin,d,h", [(1, 16, 1, 5), (1, 32, 3, 7), (2, 64, 4, 11), (1, 32, 2, 64)])
+def test_conv3d_tc_matches_fp32(ops, b, cin, d, h):
+    """3xTF32 tensor-core conv vs the fp32 reference conv: same 1e-5 bar as the CUDA-core kernel."""
+    import torch.nn.functional as F
+    w, cout = 128, 32
+    assert ops.conv3d_tc_supported(cin, cout, w)
+    x, wt = rnd(60, b, cin, d, h, w), rnd(61, cout, cin, 3, 3, 3, scale=0.2)
+    sc, sh = torch.rand(cout, generator=torch.Generator().manual_seed(62)) + 0.5, rnd(63, cout, scale=0.1)
+    want = F.conv3d(x.double(), wt.double(), padding=1).float()
+    xc = ops.to_ndhwc(dev(x))
+    wp = ops.pack_tc_weight(dev(wt))
+    got = ops.conv3d_k3_tc(xc, wp, out_ndhwc=False)
+    rel_close(got, want, 1e-5, "tc plain ncdhw-out")
+    got = ops.conv3d_k3_tc(xc, wp, out_ndhwc=True)
+    rel_close(got.permute(0, 4, 1, 2, 3), want, 1e-5, "tc plain ndhwc-out")
+    res = rnd(64, *want.shape)
+    want2 = F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res)
+    got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res), ops.ACT_RELU, out_ndhwc=False, res_ndhwc=False)
+    rel_close(got, want2, 1e-5, "tc bn+res+relu ncdhw")
+    got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
+                           out_ndhwc=True, res_ndhwc=True)
+    rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tc bn+res+relu ndhwc")

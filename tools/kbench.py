@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="volume,softargmin,conv")
+    ap.add_argument("--tc-only", action="store_true")
     a = ap.parse_args()
     only = set(a.only.split(","))
     B = a.batch
@@ -93,7 +94,8 @@ def main():
             do, ho, wo = (d - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
             report(name, ms, best, flops=2 * B * cout * cin * 27 * do * ho * wo)
 
-        conv_case("conv3d_64to32_full", 64, 32, 48, 64, 128, 1)
+        if not a.tc_only:
+            conv_case("conv3d_64to32_full", 64, 32, 48, 64, 128, 1)
         conv_case("conv3d_32to32_full", 32, 32, 48, 64, 128, 1)
         conv_case("conv3d_32to64_s2", 32, 64, 48, 64, 128, 2)
         conv_case("conv3d_64to64_half", 64, 64, 24, 32, 64, 1)
@@ -105,6 +107,16 @@ def main():
             wp = ops.pack_deconv_weight(torch.randn(cin, cout, 3, 3, 3, device=dev) * 0.05)
             ms, best = timeit(lambda: ops.deconv3d(x, wp, None, None, None, 3, ops.ACT_RELU), a.iters, flush)
             report(name, ms, best, flops=2 * B * cout * cin * 27 * d * h * w)
+        for cin in (32, 64):
+            x = torch.randn(B, 48, 64, 128, cin, device=dev)
+            wp = ops.pack_tc_weight(torch.randn(32, cin, 3, 3, 3, device=dev) * 0.05)
+            sc, sh = torch.rand(32, device=dev) + 0.5, torch.randn(32, device=dev) * 0.1
+            ms, best = timeit(lambda: ops.conv3d_k3_tc(x, wp, sc, sh, None, ops.ACT_RELU), a.iters, flush)
+            report("conv3d_tc_%dto32_full" % cin, ms, best, flops=2 * B * 32 * cin * 27 * 48 * 64 * 128)
+        xn = torch.randn(B, 64, 48, 64, 128, device=dev)
+        ms, best = timeit(lambda: ops.to_ndhwc(xn), a.iters, flush)
+        report("ncdhw_to_ndhwc_64ch", ms, best, bytes_=4 * 2 * xn.numel())
+        del xn
         x = torch.randn(B, 32, 48, 64, 128, device=dev)
         wp = (torch.randn(32, 32, device=dev) * 0.1).contiguous()
         ms, best = timeit(lambda: ops.conv3d_1x1(x, wp), a.iters, flush)
