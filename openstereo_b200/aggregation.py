@@ -20,9 +20,11 @@ from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 class _Packed:
     """One conv/deconv (+BN) layer, packed for the kernels."""
-    __slots__ = ("w", "scale", "shift", "stride", "kernel", "transposed")
+    __slots__ = ("w", "scale", "shift", "stride", "kernel", "transposed", "cin", "cout", "tc_w")
 
     def __init__(self, conv, bn=None):
+        self.tc_w = None
+        self.cin, self.cout = (conv.in_channels, conv.out_channels)
         self.transposed = isinstance(conv, (torch.nn.ConvTranspose3d, torch.nn.ConvTranspose2d))
         self.kernel = int(conv.kernel_size[0])
         self.stride = int(conv.stride[0])
@@ -35,6 +37,9 @@ class _Packed:
             self.w = ops.pack_conv_weight(wt)
         if self.kernel == 1:
             self.w = self.w.reshape(self.w.shape[0], self.w.shape[2]).contiguous()
+        if (not self.transposed) and self.kernel == 3 and self.stride == 1 and conv.weight.dim() == 5 \
+                and ops.conv3d_tc_supported(self.cin, self.cout, ops.TC_WIDTH):
+            self.tc_w = ops.pack_tc_weight(conv.weight)      # hi/lo split for the tcgen05 path (full-resolution layers)
         self.scale, self.shift = (None, None)
         if bn is not None:
             if bn.training:
@@ -49,6 +54,17 @@ def _conv(layer, x, act=ACT_NONE, residual=None, gate=None):
     if layer.kernel == 1:
         return ops.conv3d_1x1(x, layer.w, layer.scale, layer.shift, residual, gate, act)
     return ops.conv3d_k3(x, layer.w, layer.scale, layer.shift, residual, gate, layer.stride, act)
+
+
+USE_TENSOR_CORES = True      # set False to force every conv onto the fp32 CUDA-core kernels
+
+
+def _tc_ok(layer, width):
+    return USE_TENSOR_CORES and layer.tc_w is not None and width == ops.TC_WIDTH
+
+
+def _conv_tc(layer, x_ndhwc, act=ACT_NONE, residual=None, out_ndhwc=True, res_ndhwc=True):
+    return ops.conv3d_k3_tc(x_ndhwc, layer.tc_w, layer.scale, layer.shift, residual, act, out_ndhwc, res_ndhwc)
 
 
 def _deconv(layer, x, act=ACT_NONE, residual=None):
@@ -112,12 +128,22 @@ class GwcAggregation(_Engine):
     def logits(self, volume):
         volume = self._check(volume)
         self._ensure(volume.device)
-        c = _conv(self.dres0[1], _conv(self.dres0[0], volume, ACT_RELU), ACT_RELU)
-        cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+        width = volume.shape[-1]
+        if all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1])):
+            # full-resolution stem on the tensor cores: channels-last inside, NCDHW handed to the hourglasses
+            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)
+            cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)
+        else:
+            c = _conv(self.dres0[1], _conv(self.dres0[0], volume, ACT_RELU), ACT_RELU)
+            cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
         out = cost0
         for hg in self.hg:
             out = hg(out)
-        return _conv(self.classif3[1], _conv(self.classif3[0], out, ACT_RELU))
+        if _tc_ok(self.classif3[0], width):
+            head = _conv_tc(self.classif3[0], ops.to_ndhwc(out), ACT_RELU, out_ndhwc=False)
+        else:
+            head = _conv(self.classif3[0], out, ACT_RELU)
+        return _conv(self.classif3[1], head)
 
     def __call__(self, volume, h, w):
         return ops.upsample_softargmin(self.logits(volume), self.module.maxdisp, h, w, align_corners=False)
@@ -152,14 +178,25 @@ class PSMAggregation(_Engine):
     def logits(self, raw_cost):
         raw_cost = self._check(raw_cost)
         self._ensure(raw_cost.device)
-        c = _conv(self.dres0[1], _conv(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
-        cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+        width = raw_cost.shape[-1]
+        if all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1])):
+            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(raw_cost), ACT_RELU), ACT_RELU)
+            cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)
+        else:
+            c = _conv(self.dres0[1], _conv(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
+            cost0 = _conv(self.dres1[1], _conv(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
         out1, pre1, post1 = self.hg[0](cost0, None, None, cost0)
         out2, pre2, post2 = self.hg[1](out1, pre1, post1, cost0)
         out3, pre3, post3 = self.hg[2](out2, pre2, post2, cost0)
-        cost1 = _conv(self.heads[0][1], _conv(self.heads[0][0], out1, ACT_RELU))
-        cost2 = _conv(self.heads[1][1], _conv(self.heads[1][0], out2, ACT_RELU), residual=cost1)
-        cost3 = _conv(self.heads[2][1], _conv(self.heads[2][0], out3, ACT_RELU), residual=cost2)
+
+        def head(i, x):
+            if _tc_ok(self.heads[i][0], width):
+                return _conv_tc(self.heads[i][0], ops.to_ndhwc(x), ACT_RELU, out_ndhwc=False)
+            return _conv(self.heads[i][0], x, ACT_RELU)
+
+        cost1 = _conv(self.heads[0][1], head(0, out1))
+        cost2 = _conv(self.heads[1][1], head(1, out2), residual=cost1)
+        cost3 = _conv(self.heads[2][1], head(2, out3), residual=cost2)
         return [cost1, cost2, cost3]
 
     def __call__(self, raw_cost):

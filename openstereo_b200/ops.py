@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+TC_WIDTH = 128      # image width (at 1/4 resolution) handled by the tensor-core conv kernel
 
 
 def _stream():

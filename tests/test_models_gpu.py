@@ -200,3 +200,30 @@ def test_engine_repacks_after_weight_update(osb):
         m.classif3[2].weight.mul_(2.0)
     b = eng.logits(x)
     assert torch.allclose(b, 2.0 * a, rtol=1e-5, atol=1e-6)
+
+
+def test_gwc_aggregation_full_width_tensor_cores(osb):
+    """W' = 128 (a 512-pixel-wide input): the stem and classifier convs run on the tcgen05 3xTF32 kernel.  Compared with
+    the CPU oracle on a short volume (D'=8, H'=10) and with the CUDA-core path of the same engine."""
+    _, agg, _, _ = osb
+    m = oagg.GwcDispProcessor(maxdisp=32, downsample=4, num_groups=40, use_concat_volume=True, concat_channels=12).eval()
+    m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=41, scale={"classif3.2.weight": 60.0}))
+    vol = torch.randn(1, 64, 8, 12, 128, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        want_logits = m.aggregate(vol)
+        want = m(vol, 48, 512)
+    m.cuda()
+    eng = agg.GwcAggregation(m)
+    assert agg.USE_TENSOR_CORES and eng._ensure(torch.device("cuda", 0)) is None and eng.dres0[0].tc_w is not None
+    got_logits = eng.logits(vol.cuda())
+    assert rel_err(got_logits, want_logits) <= 5e-5
+    got = eng(vol.cuda(), 48, 512)
+    e = epe(got, want)
+    print("GwcNet aggregation (tensor-core stem) EPE vs oracle: %.3e" % e)
+    assert e <= EPE_BAR * 0.2 and want.std() > 1.0
+    agg.USE_TENSOR_CORES = False
+    try:
+        ref_logits = agg.GwcAggregation(m).logits(vol.cuda())
+    finally:
+        agg.USE_TENSOR_CORES = True
+    assert rel_err(got_logits, ref_logits.cpu()) <= 5e-5
