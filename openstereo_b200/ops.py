@@ -12,6 +12,7 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 TC_WIDTH = 128      # image width (at 1/4 resolution) handled by the tensor-core conv kernel
+TC_KC = 32          # input channels per K chunk of the tensor-core conv (128-byte K-major rows)
 
 
 def _stream():
@@ -264,17 +265,17 @@ def conv3d_tc_supported(cin, cout, w, stride=1):
 
 
 def pack_tc_weight(weight):
-    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/16][3 kh][3*Cout (kw-major)][16] fp32.
+    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/32][3 kh][3*Cout (kw-major)][32] fp32.
     hi = the value with its low 13 mantissa bits cleared (what a kind::tf32 MMA reads), lo = value - hi (exact)."""
     w = weight.detach().float()
     cout, cin = w.shape[:2]
-    assert cin % 16 == 0 and tuple(w.shape[2:]) == (3, 3, 3)
+    assert cin % TC_KC == 0 and tuple(w.shape[2:]) == (3, 3, 3)
     hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
     lo = w - hi
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
-    both = both.view(2, cout, cin // 16, 16, 3, 3, 3)                  # (2, co, chunk, ci16, kd, kh, kw)
-    both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci16)
-    return both.reshape(2, 3, cin // 16, 3, 3 * cout, 16).contiguous()
+    both = both.view(2, cout, cin // TC_KC, TC_KC, 3, 3, 3)            # (2, co, chunk, ci, kd, kh, kw)
+    both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci)
+    return both.reshape(2, 3, cin // TC_KC, 3, 3 * cout, TC_KC).contiguous()
 
 
 def to_ndhwc(x):
@@ -291,7 +292,7 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
     cout = w_split.shape[4] // 3
-    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    assert w_split.shape == (2, 3, cin // TC_KC, 3, 3 * cout, TC_KC) and w_split.is_contiguous()
     shape = (b, d, h, w, cout) if out_ndhwc else (b, cout, d, h, w)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:

@@ -44,6 +44,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {   // K-major SWIZZLE_64B, 512-byte 8-row atoms
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address
@@ -150,17 +159,29 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
         mma_tf32(tmem + N, make_desc(a_hi + 32 * k, 1024, p.base_off), make_desc(b_lo + 32 * k, 1024, 0), idN, k > 0);
       for (int k = 0; k < 4; ++k) mma_tf32(tmem, make_desc(a_hi + 32 * k, 1024, p.base_off), make_desc(b_hi + 32 * k, 1024, 0), idN, 1);
       (void)id2N;
-    } else {
+    } else if (p.mode == 2) {
       const uint32_t idesc = make_idesc(128, N);
       t0 = clock64();
       for (int r = 0; r < p.reps; ++r)
         for (int k = 0; k < 4; ++k)
           mma_tf32(tmem, make_desc(a_hi + 32 * k, 1024, 0), make_desc(b_hi + 32 * k, 1024, 0), idesc, (r | k) > 0);
+    } else if (p.mode == 3) {   // SWIZZLE_64B operands (64-byte rows), timing only
+      const uint32_t idesc = make_idesc(128, N);
+      t0 = clock64();
+      for (int r = 0; r < p.reps; ++r)
+        for (int k = 0; k < 4; ++k)
+          mma_tf32(tmem, make_desc64(a_hi + 32 * (k & 1)), make_desc64(b_hi + 32 * (k & 1)), idesc, (r | k) > 0);
+    } else {                    // mode 4: SWIZZLE_128B, MMAs round-robin over 4 accumulator tiles
+      const uint32_t idesc = make_idesc(128, N);
+      t0 = clock64();
+      for (int r = 0; r < p.reps; ++r)
+        for (int k = 0; k < 4; ++k)
+          mma_tf32(tmem + (k & 3) * 128, make_desc(a_hi + 32 * k, 1024, 0), make_desc(b_hi + 32 * k, 1024, 0), idesc, r > 0);
     }
     mma_commit(&bars[1]);
   }
   mbar_wait(&bars[1], 0);
-  if (tid == 0 && p.mode == 2) {
+  if (tid == 0 && p.mode >= 2) {
     t1 = clock64();
     p.cycles[0] = t1 - t0;
   }
@@ -296,6 +317,24 @@ int main() {
     CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
     printf("rate N=%3d: %.1f cycles per M128xN%dxK8 MMA  (ideal N/2 = %d) -> %.0f MAC/clk\n", N, (double)cyc / (2000 * 4), N, N / 2,
            128.0 * N * 8 / ((double)cyc / (2000 * 4)));
+  }
+  for (int mode : {3, 4})
+    for (int N : {32, 64, 96, 128}) {
+      Params p{};
+      p.mode = mode, p.N = N, p.reps = 2000;
+      run(p);
+      long long cyc;
+      CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+      printf("rate mode=%d (%s) N=%3d: %.1f cycles per MMA\n", mode, mode == 3 ? "SW64 operands" : "SW128, 4 accumulators round-robin", N,
+             (double)cyc / (2000 * 4));
+    }
+  {
+    Params p{};
+    p.mode = 2, p.N = 96, p.reps = 2000;
+    run(p);
+    long long cyc;
+    CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+    printf("rate mode=2 (SW128, one accumulator) N= 96: %.1f cycles per MMA\n", (double)cyc / (2000 * 4));
   }
   return 0;
 }
