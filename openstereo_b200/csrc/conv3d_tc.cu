@@ -59,6 +59,20 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------ small PTX wrappers
+// Wait used by the helper roles (loaders, epilogue): they run AHEAD of the MMA warp and would otherwise burn issue
+// slots of the shared schedulers in a tight try_wait loop; back off between probes.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -142,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   float* xchg = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parities][4 warps][2][COUT] boundary exchange
   float* s_scale = xchg + 2 * 4 * 2 * COUT;                // [COUT]
   float* s_shift = s_scale + COUT;
+  float* zeros = s_shift + COUT;                           // [COUT] of 0.f (image-edge neighbours)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / TC_KC;
@@ -168,6 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   for (int c = threadIdx.x; c < COUT; c += blockDim.x) {
     s_scale[c] = p.scale ? p.scale[c] : 1.f;
     s_shift[c] = p.shift ? p.shift[c] : 0.f;
+    zeros[c] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     uint32_t rowc = 0;
     auto store_row = [&](const float4 (&v)[8]) {
       const uint32_t s = rowc % TC_STAGES, par = (rowc / TC_STAGES) & 1;
-      mbar_wait(&a_empty[s], par ^ 1);                // the MMAs that read this slot last time have completed
+      mbar_wait_relaxed(&a_empty[s], par ^ 1);        // the MMAs that read this slot last time have completed
       uint8_t* hi = a_hi + s * TC_ROW_BYTES;
       uint8_t* lo = a_lo + s * TC_ROW_BYTES;
 #pragma unroll
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const int ntiles = min(TC_TILES, p.H - h0);
       // D[m] = P0[m-1] + P1[m] + P2[m+1], tile by tile as the MMA warp releases them
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&acc_full[t], itc & 1);
+        mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
         const int h = h0 + t;
         const size_t vox = (((size_t)b * p.D + d) * p.H + h) * TC_W + m;           // NDHWC voxel index
@@ -358,13 +374,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           for (int i = 0; i < COUT; ++i) xb[(q * 2 + 1) * COUT + i] = __uint_as_float(raw[2][i]);
         }
         named_bar_sync(1, 128);
+        const float* xl = (q > 0) ? xb + ((q - 1) * 2) * COUT : zeros;
+        const float* xr = (q < 3) ? xb + ((q + 1) * 2 + 1) * COUT : zeros;
         float out[COUT];
 #pragma unroll
         for (int i = 0; i < COUT; ++i) {
           float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), 1);
           float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);
-          if (lane == 0) left = (q > 0) ? xb[((q - 1) * 2) * COUT + i] : 0.f;            // m-1 of the previous quadrant
-          if (lane == 31) right = (q < 3) ? xb[((q + 1) * 2 + 1) * COUT + i] : 0.f;      // m+1 of the next quadrant
+          left = (lane == 0) ? xl[i] : left;          // m-1 lives in the previous quadrant (zero at the image edge)
+          right = (lane == 31) ? xr[i] : right;       // m+1 lives in the next quadrant
           out[i] = (left + __uint_as_float(raw[1][i])) + right;
           out[i] = fmaf(out[i], s_scale[i], s_shift[i]);
         }
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
 #pragma unroll
               for (int j = 0; j < F4_PER_HALF / 64; ++j)
                 v[half][j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
-            mbar_wait(&b_empty[kh], (phc & 1) ^ 1);   // last reader of this slice (row 4+kh of the previous phase) is done
+            mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);   // last reader (row 4+kh of the previous phase) is done
 #pragma unroll
             for (int half = 0; half < 2; ++half)
 #pragma unroll
@@ -471,7 +489,7 @@ template <int COUT>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   constexpr int N3 = 3 * COUT;
   const size_t smem = 1024 + 2 * (size_t)TC_STAGES * TC_ROW_BYTES + 3 * 2 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
-                      2 * COUT * 4;
+                      3 * COUT * 4;
   auto kernel = conv3d_tc_kernel<COUT>;
   static bool configured = false;
   if (!configured) {
