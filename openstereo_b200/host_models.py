@@ -86,14 +86,65 @@ class _GwcFeatureExtraction(nn.Module):
         return out
 
 
+def _fold_conv_bn(module):
+    """Copy of a 2D feature extractor with every eval-mode Conv2d+BatchNorm2d pair folded into one conv (the BN affine is
+    absorbed into the weights/bias), so cuDNN runs one kernel where PyTorch would run conv, batch_norm as two.  The
+    original module keeps the parameters (state_dict unchanged); the folded copy is runtime-only."""
+    import copy
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    fused = copy.deepcopy(module).eval()
+
+    def walk(m):
+        for name, child in list(m.named_children()):
+            if isinstance(child, nn.Sequential):
+                mods = list(child.children())
+                out, i = [], 0
+                while i < len(mods):
+                    if i + 1 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                        out.append(fuse_conv_bn_eval(mods[i], mods[i + 1]))
+                        i += 2
+                    else:
+                        out.append(mods[i])
+                        i += 1
+                new = nn.Sequential(*out)
+                setattr(m, name, new)
+                walk(new)
+            else:
+                walk(child)
+    walk(fused)
+    for q in fused.parameters():
+        q.requires_grad_(False)
+    return fused
+
+
+class _FoldedRuntime:
+    """Lazily (re)built BN-folded twin of a backbone; rebuilt when a parameter/buffer changes or moves."""
+
+    def __init__(self, module):
+        self.module, self.stamp, self.fused = module, None, None
+
+    def get(self):
+        m = self.module
+        stamp = tuple((t._version, t.data_ptr()) for t in list(m.parameters()) + list(m.buffers()))
+        if stamp != self.stamp:
+            with torch.no_grad():
+                self.fused = _fold_conv_bn(m)
+            self.stamp = stamp
+        return self.fused
+
+
 class _GwcBackbone(nn.Module):
     def __init__(self, use_concat_volume, concat_channels):
         super().__init__()
         self.feature_extraction = _GwcFeatureExtraction(use_concat_volume, concat_channels)
+        self._rt = None
 
     def forward(self, inputs):
+        if self._rt is None:
+            self._rt = _FoldedRuntime(self.feature_extraction)
+        fe = self.feature_extraction if self.training else self._rt.get()
         # left and right share weights: one batched pass (B*2) instead of two (gwcnet_backbone.py:101-107)
-        both = self.feature_extraction(torch.cat((inputs["left"], inputs["right"]), 0))
+        both = fe(torch.cat((inputs["left"], inputs["right"]), 0))
         b = inputs["left"].shape[0]
         return {"ref_feature": {k: v[:b] for k, v in both.items()}, "tgt_feature": {k: v[b:] for k, v in both.items()}}
 
@@ -126,7 +177,10 @@ class _PsmBackbone(nn.Module):
         return self.lastconv(torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1))
 
     def forward(self, inputs):
-        both = self._forward(torch.cat((inputs["left"], inputs["right"]), 0))
+        if getattr(self, "_rt", None) is None:
+            object.__setattr__(self, "_rt", _FoldedRuntime(self))
+        net = self if self.training else self._rt.get()
+        both = net._forward(torch.cat((inputs["left"], inputs["right"]), 0))
         b = inputs["left"].shape[0]
         return {"ref_feature": both[:b], "tgt_feature": both[b:]}
 
