@@ -133,11 +133,14 @@ int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const 
 /* ------------------------------------------------------- tensor-core (tcgen05) variant of the 3x3x3 conv ----- */
 
 /* Same operator as osb_conv3d_k3_bn_act_fwd (stride 1) for the full-resolution layers, computed on the 5th-gen tensor
- * cores with 3xTF32 operand splitting (fp32-accurate, see csrc/conv3d_tc.cu).  Supported: W == 128, Cin % 32 == 0,
- * Cout == 32 (osb_conv3d_tc_supported).  x is CHANNELS-LAST (B,D,H,W,Cin); w_split is the host-split weight tensor
- * [2 (hi,lo)][3 kd][Cin/32][3 kh][3*Cout (kw-major)][32] (ops.pack_tc_weight); y and residual are NCDHW or NDHWC
+ * cores with 3xTF32 operand splitting (fp32-accurate, see csrc/conv3d_tc.cu, conv3d_tcg.cu).  Supported shapes:
+ * osb_conv3d_tc_supported / osb_conv3d_tc_kc.  x is CHANNELS-LAST (B,D,H,W,Cin); w_split is the host-split weight tensor
+ * [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] (ops.pack_tc_weight); y and residual are NCDHW or NDHWC
  * according to out_ndhwc / res_ndhwc. */
 int osb_conv3d_tc_supported(int Cin, int Cout, int W, int stride);
+/* K chunk (16 or 32 input channels per operand tile) the weight tensor must be packed with; 0 = unsupported shape.
+ * Variants: W=128/Cout=32 (kc 32); W=64/Cout=64, W=32/Cout=64|128 (kc 16, M tile = 128/W image rows). */
+int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
 int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream);

@@ -1,9 +1,17 @@
 """B200-native cost-volume hot path for OpenStereo (sm_100a CUDA kernels behind a C ABI).
 
-Importing the package loads ``lib/libopenstereo_b200.so``; if it has not been built the import
-raises -- there is no PyTorch/CPU fallback for the product path.
+Sub-modules are loaded on first access (``openstereo_b200.ops`` etc.) so that ``python -m openstereo_b200.build`` can
+run before the shared library exists.  The first access to ``ops`` / ``_lib`` loads ``lib/libopenstereo_b200.so`` and
+RAISES if it is missing or lacks a symbol -- there is no PyTorch/CPU fallback for the product path.
 """
-from . import _lib  # noqa: F401  (fails loudly when the native library is missing)
-from . import ops  # noqa: F401
+import importlib
 
-__all__ = ["ops"]
+_SUBMODULES = ("_lib", "ops", "aggregation", "host_models", "patch", "distributed", "build")
+
+__all__ = ["ops", "aggregation", "host_models", "patch", "distributed"]
+
+
+def __getattr__(name):
+    if name in _SUBMODULES:
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

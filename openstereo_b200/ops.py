@@ -264,18 +264,24 @@ def conv3d_tc_supported(cin, cout, w, stride=1):
     return bool(_lib.lib.osb_conv3d_tc_supported(int(cin), int(cout), int(w), int(stride)))
 
 
-def pack_tc_weight(weight):
-    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/32][3 kh][3*Cout (kw-major)][32] fp32.
+def conv3d_tc_kc(cin, cout, w, stride=1):
+    """K chunk (16 / 32) of the tensor-core kernel variant serving this shape, 0 if there is none."""
+    return int(_lib.lib.osb_conv3d_tc_kc(int(cin), int(cout), int(w), int(stride)))
+
+
+def pack_tc_weight(weight, kc=None):
+    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] fp32.
     hi = the value with its low 13 mantissa bits cleared (what a kind::tf32 MMA reads), lo = value - hi (exact)."""
     w = weight.detach().float()
     cout, cin = w.shape[:2]
-    assert cin % TC_KC == 0 and tuple(w.shape[2:]) == (3, 3, 3)
+    kc = TC_KC if kc is None else kc
+    assert kc in (16, 32) and cin % kc == 0 and tuple(w.shape[2:]) == (3, 3, 3)
     hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
     lo = w - hi
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
-    both = both.view(2, cout, cin // TC_KC, TC_KC, 3, 3, 3)            # (2, co, chunk, ci, kd, kh, kw)
+    both = both.view(2, cout, cin // kc, kc, 3, 3, 3)                  # (2, co, chunk, ci, kd, kh, kw)
     both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci)
-    return both.reshape(2, 3, cin // TC_KC, 3, 3 * cout, TC_KC).contiguous()
+    return both.reshape(2, 3, cin // kc, 3, 3 * cout, kc).contiguous()
 
 
 def to_ndhwc(x):
@@ -292,7 +298,8 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
     cout = w_split.shape[4] // 3
-    assert w_split.shape == (2, 3, cin // TC_KC, 3, 3 * cout, TC_KC) and w_split.is_contiguous()
+    kc = conv3d_tc_kc(cin, cout, w)
+    assert kc and w_split.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and w_split.is_contiguous()
     shape = (b, d, h, w, cout) if out_ndhwc else (b, cout, d, h, w)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:

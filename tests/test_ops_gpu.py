@@ -284,3 +284,30 @@ def test_conv3d_tc_matches_fp32(ops, b, cin, d, h):
     got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
                            out_ndhwc=True, res_ndhwc=True)
     rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tc bn+res+relu ndhwc")
+
+
+@pytest.mark.parametrize("b,cin,cout,d,h,w", [
+    (1, 64, 64, 3, 8, 64),      # GwcNet/PSMNet conv2 @ 1/8 (two image rows per M tile)
+    (2, 16, 64, 2, 5, 64),      # ragged H (5 rows, blocks of 4)
+    (1, 128, 128, 3, 8, 32),    # GwcNet conv4 @ 1/16 (four rows per tile, N = 3 x 128)
+    (1, 64, 64, 2, 16, 32),     # PSMNet conv4
+    (1, 32, 128, 1, 3, 32),     # ragged H, single plane
+])
+def test_conv3d_tc_generic_tiles(ops, b, cin, cout, d, h, w):
+    """Multi-row-tile tensor-core conv (conv3d_tcg.cu) vs the fp64 reference conv."""
+    import torch.nn.functional as F
+    assert ops.conv3d_tc_supported(cin, cout, w) and ops.conv3d_tc_kc(cin, cout, w) == 16
+    x, wt = rnd(70, b, cin, d, h, w), rnd(71, cout, cin, 3, 3, 3, scale=0.2)
+    sc, sh = torch.rand(cout, generator=torch.Generator().manual_seed(72)) + 0.5, rnd(73, cout, scale=0.1)
+    want = F.conv3d(x.double(), wt.double(), padding=1).float()
+    xc = ops.to_ndhwc(dev(x))
+    wp = ops.pack_tc_weight(dev(wt), 16)
+    got = ops.conv3d_k3_tc(xc, wp, out_ndhwc=False)
+    rel_close(got, want, 1e-5, "tcg plain ncdhw-out")
+    res = rnd(74, *want.shape)
+    want2 = F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res)
+    got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res), ops.ACT_RELU, out_ndhwc=False, res_ndhwc=False)
+    rel_close(got, want2, 1e-5, "tcg bn+res+relu ncdhw")
+    got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
+                           out_ndhwc=True, res_ndhwc=True)
+    rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tcg bn+res+relu ndhwc")

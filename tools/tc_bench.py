@@ -29,3 +29,21 @@ for cin in (32, 64):
     print(json.dumps({"cin": cin, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3), "to_ndhwc_ms": round(ms2, 3),
                       "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
                       "rel_err_vs_cuda_core": err}), flush=True)
+
+# hourglass-interior shapes (generic multi-row-tile kernel)
+for name, cin, cout, d, h, w in [("conv2_64to64_w64", 64, 64, 24, 32, 64), ("conv4_128to128_w32", 128, 128, 12, 16, 32)]:
+    wgt = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.05
+    sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1
+    xn = torch.randn(B, cin, d, h, w, device=dev)
+    xc = ops.to_ndhwc(xn)
+    wp, wt = ops.pack_conv_weight(wgt), ops.pack_tc_weight(wgt, 16)
+    flops = 2 * B * cout * cin * 27 * d * h * w
+    ref = ops.conv3d_k3(xn, wp, sc, sh, None, None, 1, ops.ACT_RELU)
+    got = ops.conv3d_k3_tc(xc, wt, sc, sh, None, ops.ACT_RELU, out_ndhwc=False)
+    err = ((ref - got).abs().max() / ref.abs().max()).item()
+    ms0, _ = timeit(lambda: ops.conv3d_k3(xn, wp, sc, sh, None, None, 1, ops.ACT_RELU), 5, flush)
+    ms1, _ = timeit(lambda: ops.conv3d_k3_tc(xc, wt, sc, sh, None, ops.ACT_RELU, out_ndhwc=False), 5, flush)
+    ms2, _ = timeit(lambda: ops.to_ndhwc(xn), 5, flush)
+    print(json.dumps({"layer": name, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3), "to_ndhwc_ms": round(ms2, 3),
+                      "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
+                      "rel_err_vs_cuda_core": err}), flush=True)
