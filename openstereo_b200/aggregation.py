@@ -20,10 +20,11 @@ from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 class _Packed:
     """One conv/deconv (+BN) layer, packed for the kernels."""
-    __slots__ = ("w", "scale", "shift", "stride", "kernel", "transposed", "cin", "cout", "tc_w")
+    __slots__ = ("w", "scale", "shift", "stride", "kernel", "transposed", "cin", "cout", "_w5", "_tc")
 
     def __init__(self, conv, bn=None):
-        self.tc_w = None
+        self._tc = {}                                           # K-chunk -> hi/lo split weight for the tcgen05 kernels
+        self._w5 = conv.weight.detach() if conv.weight.dim() == 5 else None
         self.cin, self.cout = (conv.in_channels, conv.out_channels)
         self.transposed = isinstance(conv, (torch.nn.ConvTranspose3d, torch.nn.ConvTranspose2d))
         self.kernel = int(conv.kernel_size[0])
@@ -37,9 +38,6 @@ class _Packed:
             self.w = ops.pack_conv_weight(wt)
         if self.kernel == 1:
             self.w = self.w.reshape(self.w.shape[0], self.w.shape[2]).contiguous()
-        if (not self.transposed) and self.kernel == 3 and self.stride == 1 and conv.weight.dim() == 5 \
-                and ops.conv3d_tc_supported(self.cin, self.cout, ops.TC_WIDTH):
-            self.tc_w = ops.pack_tc_weight(conv.weight)      # hi/lo split for the tcgen05 path (full-resolution layers)
         self.scale, self.shift = (None, None)
         if bn is not None:
             if bn.training:
@@ -59,12 +57,32 @@ def _conv(layer, x, act=ACT_NONE, residual=None, gate=None):
 USE_TENSOR_CORES = True      # set False to force every conv onto the fp32 CUDA-core kernels
 
 
+def _tc_weight(layer, width):
+    """hi/lo split weight of a 3x3x3 stride-1 layer for the tensor-core kernel variant serving `width`, or None."""
+    if not USE_TENSOR_CORES or layer.transposed or layer.kernel != 3 or layer.stride != 1 or layer._w5 is None:
+        return None
+    kc = ops.conv3d_tc_kc(layer.cin, layer.cout, width)
+    if not kc:
+        return None
+    if kc not in layer._tc:
+        layer._tc[kc] = ops.pack_tc_weight(layer._w5, kc)
+    return layer._tc[kc]
+
+
 def _tc_ok(layer, width):
-    return USE_TENSOR_CORES and layer.tc_w is not None and width == ops.TC_WIDTH
+    return _tc_weight(layer, width) is not None
 
 
 def _conv_tc(layer, x_ndhwc, act=ACT_NONE, residual=None, out_ndhwc=True, res_ndhwc=True):
-    return ops.conv3d_k3_tc(x_ndhwc, layer.tc_w, layer.scale, layer.shift, residual, act, out_ndhwc, res_ndhwc)
+    wt = _tc_weight(layer, x_ndhwc.shape[3])
+    return ops.conv3d_k3_tc(x_ndhwc, wt, layer.scale, layer.shift, residual, act, out_ndhwc, res_ndhwc)
+
+
+def _conv_auto(layer, x, act=ACT_NONE, residual=None):
+    """3x3x3 stride-1 conv on an NCDHW tensor, NCDHW result: tensor cores when a variant exists, CUDA cores otherwise."""
+    if _tc_ok(layer, x.shape[-1]):
+        return _conv_tc(layer, ops.to_ndhwc(x), act, residual, out_ndhwc=False, res_ndhwc=False)
+    return _conv(layer, x, act, residual)
 
 
 def _deconv(layer, x, act=ACT_NONE, residual=None):
@@ -108,9 +126,9 @@ class _GwcHourglass:
 
     def __call__(self, x):
         c1 = _conv(self.conv1, x, ACT_RELU)
-        c2 = _conv(self.conv2, c1, ACT_RELU)
+        c2 = _conv_auto(self.conv2, c1, ACT_RELU)
         c3 = _conv(self.conv3, c2, ACT_RELU)
-        c4 = _conv(self.conv4, c3, ACT_RELU)
+        c4 = _conv_auto(self.conv4, c3, ACT_RELU)
         c5 = _deconv(self.conv5, c4, ACT_RELU, residual=_conv(self.redir2, c2))
         return _deconv(self.conv6, c5, ACT_RELU, residual=_conv(self.redir1, x))
 
@@ -158,8 +176,8 @@ class _PSMHourglass:
 
     def __call__(self, x, presqu, postsqu, skip):
         out = _conv(self.conv1, x, ACT_RELU)
-        pre = _conv(self.conv2, out, ACT_RELU, residual=postsqu)
-        out = _conv(self.conv4, _conv(self.conv3, pre, ACT_RELU), ACT_RELU)
+        pre = _conv_auto(self.conv2, out, ACT_RELU, residual=postsqu)
+        out = _conv_auto(self.conv4, _conv(self.conv3, pre, ACT_RELU), ACT_RELU)
         post = _deconv(self.conv5, out, ACT_RELU, residual=presqu if presqu is not None else pre)
         # `out_i = hourglass(...) + cost0` (psmnet_cost_processor.py:188-194) rides on conv6's epilogue
         return _deconv(self.conv6, post, ACT_NONE, residual=skip), pre, post
