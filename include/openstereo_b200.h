@@ -144,6 +144,13 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
 int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* Stride-2 variant (the down-sampling convs of the hourglasses): x (B,D,H,W,Cin) channels-last with even D,H,W ->
+ * y (B,Cout,D/2,H/2,W/2) or channels-last.  w_split like above but with the kw slices stored in the order (1,0,2)
+ * (ops.pack_tc_weight(..., kw_order=(1,0,2))), 16-channel K chunks.  Supported: W=128/Cout=64, W=64/Cout=64|128. */
+int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W);
+int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                            int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* (B,C,D,H,W) -> (B,D,H,W,C) layout change feeding the tensor-core conv. */
 int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream);
 

@@ -79,9 +79,15 @@ def _conv_tc(layer, x_ndhwc, act=ACT_NONE, residual=None, out_ndhwc=True, res_nd
 
 
 def _conv_auto(layer, x, act=ACT_NONE, residual=None):
-    """3x3x3 stride-1 conv on an NCDHW tensor, NCDHW result: tensor cores when a variant exists, CUDA cores otherwise."""
-    if _tc_ok(layer, x.shape[-1]):
+    """3x3x3 conv (stride 1 or 2) on an NCDHW tensor, NCDHW result: tensor cores when a kernel variant exists for the
+    shape, the fp32 CUDA-core kernel otherwise."""
+    if layer.stride == 1 and _tc_ok(layer, x.shape[-1]):
         return _conv_tc(layer, ops.to_ndhwc(x), act, residual, out_ndhwc=False, res_ndhwc=False)
+    if (USE_TENSOR_CORES and layer.stride == 2 and layer.kernel == 3 and not layer.transposed and layer._w5 is not None
+            and ops.conv3d_s2_tc_supported(layer.cin, layer.cout, x.shape[2], x.shape[3], x.shape[4])):
+        if "s2" not in layer._tc:
+            layer._tc["s2"] = ops.pack_tc_weight(layer._w5, 16, kw_order=(1, 0, 2))
+        return ops.conv3d_k3_s2_tc(ops.to_ndhwc(x), layer._tc["s2"], layer.scale, layer.shift, residual, act)
     return _conv(layer, x, act, residual)
 
 
@@ -125,9 +131,9 @@ class _GwcHourglass:
         self.redir1, self.redir2 = _Packed(m.redir1[0], m.redir1[1]), _Packed(m.redir2[0], m.redir2[1])
 
     def __call__(self, x):
-        c1 = _conv(self.conv1, x, ACT_RELU)
+        c1 = _conv_auto(self.conv1, x, ACT_RELU)
         c2 = _conv_auto(self.conv2, c1, ACT_RELU)
-        c3 = _conv(self.conv3, c2, ACT_RELU)
+        c3 = _conv_auto(self.conv3, c2, ACT_RELU)
         c4 = _conv_auto(self.conv4, c3, ACT_RELU)
         c5 = _deconv(self.conv5, c4, ACT_RELU, residual=_conv(self.redir2, c2))
         return _deconv(self.conv6, c5, ACT_RELU, residual=_conv(self.redir1, x))
@@ -175,9 +181,9 @@ class _PSMHourglass:
         self.conv5, self.conv6 = _Packed(m.conv5[0], m.conv5[1]), _Packed(m.conv6[0], m.conv6[1])
 
     def __call__(self, x, presqu, postsqu, skip):
-        out = _conv(self.conv1, x, ACT_RELU)
+        out = _conv_auto(self.conv1, x, ACT_RELU)
         pre = _conv_auto(self.conv2, out, ACT_RELU, residual=postsqu)
-        out = _conv_auto(self.conv4, _conv(self.conv3, pre, ACT_RELU), ACT_RELU)
+        out = _conv_auto(self.conv4, _conv_auto(self.conv3, pre, ACT_RELU), ACT_RELU)
         post = _deconv(self.conv5, out, ACT_RELU, residual=presqu if presqu is not None else pre)
         # `out_i = hourglass(...) + cost0` (psmnet_cost_processor.py:188-194) rides on conv6's epilogue
         return _deconv(self.conv6, post, ACT_NONE, residual=skip), pre, post

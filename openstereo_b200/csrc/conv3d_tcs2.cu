@@ -1,0 +1,416 @@
+// Tensor-core (tcgen05) Conv3d 3x3x3 STRIDE 2, pad 1: the down-sampling convs of the hourglasses
+//   conv1 32->64 (1/4 -> 1/8 res) and conv3 64->128 / 64->64 (1/8 -> 1/16 res): gwcnet/hourglass.py:19-29,
+//   psmnet/psmnet_cost_processor.py:79-94.
+// Same machinery as conv3d_tcg.cu (3xTF32 split, LDG-staged swizzled operands, warp-specialised persistent CTA, taps
+// stacked along N and recombined in the epilogue); what changes is the gather:
+//   out[ow] = in[2ow-1].W0 + in[2ow].W1 + in[2ow+1].W2.  With E[j] = in[2j] (even columns) and O[j] = in[2j+1] (odd columns)
+//   this is  out[ow] = E[ow].W1 + O[ow].W2 + O[ow-1].W0 ,  so per (output tile, kd, kh) the loaders stage TWO operand tiles
+//   -- the even and the odd columns of the RO = 128/Wo input rows 2*oh + kh - 1 -- and the issuer runs
+//   E x W1 (N = Cout) into accumulator columns [0,Cout) and O x [W0 | W2] (N = 2 Cout) into [Cout, 3 Cout); the epilogue
+//   adds P1[ow] + P2[ow] + P0[ow-1] (a single left shift, zero at ow = 0 = the conv's left padding).
+// Weight slices are packed with the kw order (1, 0, 2) so both MMAs read contiguous rows.
+#include "tc_common.cuh"
+
+namespace osb {
+
+struct Tcs2Params {
+  const float* x;          // (B, D, H, W, Cin) channels-last
+  const float* w;          // [2 (hi,lo)][3 kd][Cin/KC][3 kh][3*Cout][KC]
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  float* y;
+  int B, D, H, Cin;        // INPUT extent D x H x (2*WO); output is D/2 x H/2 x WO
+  int act;
+  int out_ndhwc, res_ndhwc;
+  int items, hblocks;
+};
+
+template <int COUT, int KC, int W, int TILES>     // W = OUTPUT width
+struct Tcs2Cfg {
+  static constexpr int R = 128 / W;                         // OUTPUT image rows per M tile
+  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row
+  static constexpr int UNIT_BYTES = 128 * ROWB;
+  static constexpr int N3 = 3 * COUT;
+  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
+  static constexpr int STAGES = 4;
+  static constexpr int HBLK = TILES * R;                    // output rows per work item
+  static constexpr int KSTEPS = KC / 8;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
+  static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
+  static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4;
+  static_assert(TILES * N3 <= 512, "accumulators exceed TMEM");
+  static_assert(B_SLICE % 1024 == 0 && UNIT_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+  static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "invalid UMMA N");
+};
+
+template <int COUT, int KC, int W, int TILES>
+__global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3d_tcs2_kernel(const Tcs2Params p) {
+  using C = Tcs2Cfg<COUT, KC, W, TILES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = smem + C::A_OFF;
+  uint8_t* a_lo = a_hi + C::STAGES * C::UNIT_BYTES;
+  uint8_t* b_buf = smem + C::B_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
+  uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
+  uint64_t* b_full = a_empty + C::STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
+  uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
+  uint64_t* acc_full = b_empty + 3;                 // [TILES]
+  uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
+  float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
+  float* s_scale = xchg + 2 * 4 * 2 * 32;
+  float* s_shift = s_scale + COUT;
+  float* zeros = s_shift + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = p.Cin / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&a_ready[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(&b_full[k], 64);
+      mbar_init(&b_empty[k], 1);
+    }
+    for (int t = 0; t < TILES; ++t) {
+      mbar_init(&acc_full[t], 1);
+      mbar_init(&acc_empty[t], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int c = threadIdx.x; c < COUT; c += blockDim.x) {
+    s_scale[c] = p.scale ? p.scale[c] : 1.f;
+    s_shift[c] = p.shift ? p.shift[c] : 0.f;
+    zeros[c] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---------------------------------------------------------------------------------------------- MMA issuer
+  if (warp == 0) {
+    const uint32_t idesc_e = idesc_tf32(128, COUT), idesc_o = idesc_tf32(128, 2 * COUT);
+    const uint64_t dbase = (KC == 32) ? desc_sw128_base() : desc_sw64_base();
+    const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
+    const int Do = p.D / 2, Ho = p.H / 2;
+    uint32_t unitc = 0, phc = 0, itc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
+      const int hb = it % p.hblocks;
+      const int od = (it / p.hblocks) % Do;
+      const int ntiles = min(TILES, (Ho - hb * C::HBLK + C::R - 1) / C::R);
+      uint32_t started = 0;
+      for (int kd = 0; kd < 3; ++kd) {
+        const int din = 2 * od + kd - 1;
+        if (din < 0 || din >= p.D) continue;
+        for (int ch = 0; ch < nchunk; ++ch, ++phc) {
+          const bool last_phase = (kd == 2) && (ch == nchunk - 1);     // din = 2*od+1 always exists (even D)
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int par = 0; par < 2; ++par) {       // par 0: even input columns (kw = 1); par 1: odd columns (kw = 0, 2)
+                const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
+                mbar_wait(&a_ready[slot], ph);
+                if (t == 0 && par == 0) mbar_wait(&b_full[kh], phc & 1);   // first use of slice kh in this phase
+                tc_fence_after();
+                if (t < ntiles) {
+                  const uint32_t accum = (started >> (2 * t + par)) & 1;
+                  if (((started >> (2 * t)) & 3u) == 0u) {   // first touch of this tile in this item
+                    mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
+                    tc_fence_after();
+                  }
+                  started |= 1u << (2 * t + par);
+                  if (elect_one()) {
+                    const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+                    const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+                    // slice rows: [W1 (Cout) | W0 (Cout) | W2 (Cout)]; accumulator columns: [P1 | P0 | P2]
+                    const uint32_t acc = tmem + t * C::N3 + (par ? COUT : 0);
+                    const uint64_t dbh0 = dbase | (uint64_t)(b16 + (kh * 2 * C::B_SLICE + (par ? COUT * C::ROWB : 0)) / 16);
+                    const uint64_t dbl0 = dbh0 + C::B_SLICE / 16;
+                    const uint32_t idesc = par ? idesc_o : idesc_e;
+#pragma unroll
+                    for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                      mma_tf32(acc, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                      mma_tf32(acc, dah0 + 2 * ks, dbl0 + 2 * ks, idesc, 1);
+                      mma_tf32(acc, dah0 + 2 * ks, dbh0 + 2 * ks, idesc, 1);
+                    }
+                  }
+                  __syncwarp();
+                }
+                if (elect_one()) {
+                  mma_commit(&a_empty[slot]);
+                  if (t == TILES - 1 && par == 1) mma_commit(&b_empty[kh]);        // last user of slice kh in this phase
+                  if (last_phase && kh == 2 && par == 1) mma_commit(&acc_full[t]); // tile t has received its last tap
+                }
+                __syncwarp();
+                ++unitc;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- A-unit loaders
+  else if (warp < 5) {
+    const int lt = threadIdx.x - 32;                 // 0..127
+    constexpr int CPR = C::ROWB / 16;                // 16-byte chunks per operand row (8 or 4)
+    constexpr int NLD = 128 * CPR / 128;             // float4 loads per thread per unit (8 or 4)
+    constexpr int WI = 2 * W;                        // input width
+    const int Do = p.D / 2;
+    uint32_t unitc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const int hb = it % p.hblocks;
+      const int od = (it / p.hblocks) % Do;
+      const int b = it / (p.hblocks * Do);
+      const int h0 = hb * C::HBLK;                   // first OUTPUT row of the block
+      for (int kd = 0; kd < 3; ++kd) {
+        const int din = 2 * od + kd - 1;
+        if (din < 0 || din >= p.D) continue;
+        const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)WI * p.Cin;
+        for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int par = 0; par < 2; ++par) {
+                float4 v[NLD];
+#pragma unroll
+                for (int j = 0; j < NLD; ++j) {
+                  const int f = lt + 128 * j;
+                  const int vox = f / CPR, c = f % CPR;   // operand row = output voxel (row vox / W, column vox % W)
+                  const int hin = 2 * (h0 + t * C::R + vox / W) + kh - 1, win = 2 * (vox % W) + par;
+                  v[j] = (hin >= 0 && hin < p.H)
+                             ? __ldg(reinterpret_cast<const float4*>(plane + ((size_t)hin * WI + win) * p.Cin + ch * KC + c * 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
+                mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+                uint8_t* hi = a_hi + slot * C::UNIT_BYTES;
+                uint8_t* lo = a_lo + slot * C::UNIT_BYTES;
+#pragma unroll
+                for (int j = 0; j < NLD; ++j) {
+                  const int f = lt + 128 * j;
+                  const int off = swz_offset<KC>(f / CPR, f % CPR);
+                  *reinterpret_cast<float4*>(hi + off) = v[j];
+                  *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_ready[slot]);
+                ++unitc;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- epilogue
+  else if (warp < 9) {
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;                     // operand row owned by this thread
+    const int rr = m / W, wcol = m % W;              // image row inside the tile, image column
+    const bool has_left_q = ((q * 32) % W) != 0;     // the quadrant to the left continues the same image row
+    const int Do = p.D / 2, Ho = p.H / 2;
+    uint32_t itc = 0, exc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
+      const int hb = it % p.hblocks;
+      const int d = (it / p.hblocks) % Do;
+      const int b = it / (p.hblocks * Do);
+      const int h0 = hb * C::HBLK;
+      const int ntiles = min(TILES, (Ho - h0 + C::R - 1) / C::R);
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait_relaxed(&acc_full[t], itc & 1);
+        tc_fence_after();
+        const int h = h0 + t * C::R + rr;
+        const bool live = h < Ho;
+        const size_t vox = (((size_t)b * Do + d) * Ho + h) * W + wcol;             // NDHWC voxel index (output)
+        const size_t plane = (size_t)Do * Ho * W;                                  // NCDHW channel stride (output)
+        const size_t ncdhw0 = (size_t)b * COUT * plane + ((size_t)d * Ho + h) * W + wcol;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
+#pragma unroll 1
+        for (int cg = 0; cg < COUT; cg += 32) {
+          uint32_t raw[3][32];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) tmem_ld16_nowait(trow + kw * COUT + cg + c0, &raw[kw][c0]);
+          tmem_ld_wait();
+          if (cg + 32 >= COUT) {                      // whole tile in registers: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&acc_empty[t]);
+          }
+          float* xb = xchg + (exc & 1) * (4 * 2 * 32);
+          ++exc;
+          // accumulator column groups: raw[0] = P1 (kw=1, even columns), raw[1] = P0 (kw=0), raw[2] = P2 (kw=2)
+          if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xb[(q * 2) * 32 + i] = __uint_as_float(raw[1][i]);
+          }
+          named_bar_sync(1, 128);
+          const float* xl = has_left_q ? xb + ((q - 1) * 2) * 32 : zeros;
+          float out[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[1][i]), 1);   // P0 of output column ow-1
+            left = (lane == 0) ? xl[i] : left;                                        // zero at ow = 0 (left padding)
+            out[i] = (left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i]);
+            out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
+          }
+          if (live) {
+            if (p.residual) {
+              if (p.res_ndhwc) {
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 rv = __ldg(rp + i);
+                  out[4 * i] += rv.x, out[4 * i + 1] += rv.y, out[4 * i + 2] += rv.z, out[4 * i + 3] += rv.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) out[i] += __ldg(p.residual + ncdhw0 + (size_t)(cg + i) * plane);
+              }
+            }
+            if (p.act == OSB_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) out[i] = fmaxf(out[i], 0.f);
+            } else if (p.act == OSB_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) out[i] = out[i] > 0.f ? out[i] : 0.01f * out[i];
+            }
+            if (p.out_ndhwc) {
+              float4* yp = reinterpret_cast<float4*>(p.y + vox * COUT + cg);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) yp[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) p.y[ncdhw0 + (size_t)(cg + i) * plane] = out[i];
+            }
+          }
+        }
+      }
+      for (int t = ntiles; t < TILES; ++t) {            // unused tiles keep the barrier phases in step
+        mbar_wait_relaxed(&acc_full[t], itc & 1);
+        mbar_arrive(&acc_empty[t]);
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- weight-slice loaders
+  else {
+    const int wt = threadIdx.x - 9 * 32;             // 0..63
+    constexpr int F4 = C::B_SLICE / 16;              // float4 per (kh, hi|lo)
+    constexpr int PER = F4 / 64;                     // per thread
+    constexpr int CPR = C::ROWB / 16;
+    static_assert(F4 % 64 == 0, "weight slice must split evenly over 64 loader threads");
+    uint32_t phc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const int od = (it / p.hblocks) % (p.D / 2);
+      for (int kd = 0; kd < 3; ++kd) {
+        const int din = 2 * od + kd - 1;              // must enumerate the same phases as the MMA warp and the loaders
+        if (din < 0 || din >= p.D) continue;
+        for (int ch = 0; ch < nchunk; ++ch, ++phc) {
+          for (int kh = 0; kh < 3; ++kh) {
+            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)(C::N3 * KC);
+            const size_t half_stride = (size_t)3 * nchunk * 3 * C::N3 * KC;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float4 v[PER];
+#pragma unroll
+              for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
+              if (half == 0) mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);
+#pragma unroll
+              for (int j = 0; j < PER; ++j) {
+                const int f = wt + 64 * j;
+                *reinterpret_cast<float4*>(b_buf + (kh * 2 + half) * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(&b_full[kh]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int COUT, int KC, int W, int TILES>
+static int launch_tcs2(Tcs2Params& p, cudaStream_t stream) {
+  using C = Tcs2Cfg<COUT, KC, W, TILES>;
+  auto kernel = conv3d_tcs2_kernel<COUT, KC, W, TILES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv3d_tcg: cannot reserve %zu bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return OSB_ECUDA;
+    }
+    configured = true;
+  }
+  p.hblocks = (p.H / 2 + C::HBLK - 1) / C::HBLK;
+  const long long items = (long long)p.B * (p.D / 2) * p.hblocks;
+  OSB_REQUIRE(items < (1ll << 31), "conv3d_tcs2: too many work items");
+  p.items = (int)items;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    sms = 148;
+  }
+  const int grid = p.items < sms ? p.items : sms;
+  kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
+  count_launch();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa{};
+    (void)cudaFuncGetAttributes(&fa, kernel);
+    set_error("conv3d_tcs2_kernel<%d,%d,%d,%d>: launch failed: %s (threads %d, kernel maxThreadsPerBlock %d, regs %d, static smem %zu, "
+              "dynamic smem %zu, max dynamic %d)", COUT, KC, W, TILES, cudaGetErrorString(le), C::THREADS, fa.maxThreadsPerBlock,
+              fa.numRegs, fa.sharedSizeBytes, C::SMEM, fa.maxDynamicSharedSizeBytes);
+    return OSB_ECUDA;
+  }
+  return OSB_OK;
+}
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
+  if (Cin % 16 != 0 || Cin < 16 || D % 2 || H % 2 || W % 2) return 0;
+  return ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 128))) ? 1 : 0;
+}
+
+int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                            int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x_ndhwc && w_split && y, "conv3d_k3_s2_tc: null pointer");
+  OSB_REQUIRE(B > 0 && D > 0 && H > 0, "conv3d_k3_s2_tc: empty shape");
+  OSB_REQUIRE(osb_conv3d_s2_tc_supported(Cin, Cout, D, H, W), "conv3d_k3_s2_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d", Cin,
+              Cout, D, H, W);
+  OSB_REQUIRE(act >= 0 && act <= 2, "conv3d_k3_s2_tc: unknown activation %d", act);
+  Tcs2Params p{};
+  p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
+  p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (W == 128 && Cout == 64) return launch_tcs2<64, 16, 64, 2>(p, s);
+  if (W == 64 && Cout == 64) return launch_tcs2<64, 16, 32, 2>(p, s);
+  return launch_tcs2<128, 16, 32, 1>(p, s);
+}
+}

@@ -269,7 +269,7 @@ def conv3d_tc_kc(cin, cout, w, stride=1):
     return int(_lib.lib.osb_conv3d_tc_kc(int(cin), int(cout), int(w), int(stride)))
 
 
-def pack_tc_weight(weight, kc=None):
+def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2)):
     """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] fp32.
     hi = the value with its low 13 mantissa bits cleared (what a kind::tf32 MMA reads), lo = value - hi (exact)."""
     w = weight.detach().float()
@@ -279,7 +279,8 @@ def pack_tc_weight(weight, kc=None):
     hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
     lo = w - hi
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
-    both = both.view(2, cout, cin // kc, kc, 3, 3, 3)                  # (2, co, chunk, ci, kd, kh, kw)
+    both = both[..., list(kw_order)]                                   # stride-2 kernel wants kw slices as (1, 0, 2)
+    both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (2, co, chunk, ci, kd, kh, kw)
     both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci)
     return both.reshape(2, 3, cin // kc, 3, 3 * cout, kc).contiguous()
 
@@ -306,5 +307,27 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
         want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
     _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+    return y
+
+
+def conv3d_s2_tc_supported(cin, cout, d, h, w):
+    return bool(_lib.lib.osb_conv3d_s2_tc_supported(int(cin), int(cout), int(d), int(h), int(w)))
+
+
+def conv3d_k3_s2_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=False, res_ndhwc=False):
+    """3x3x3 STRIDE-2 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin), even D,H,W;
+    w_split = pack_tc_weight(weight, 16, kw_order=(1, 0, 2))."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    cout = w_split.shape[4] // 3
+    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    do, ho, wo = d // 2, h // 2, w // 2
+    shape = (b, do, ho, wo, cout) if out_ndhwc else (b, cout, do, ho, wo)
+    y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
+    if residual is not None:
+        want = (b, do, ho, wo, cout) if res_ndhwc else (b, cout, do, ho, wo)
+        assert tuple(residual.shape) == want and residual.is_contiguous()
+    _call("osb_conv3d_k3_s2_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
     return y

@@ -311,3 +311,28 @@ def test_conv3d_tc_generic_tiles(ops, b, cin, cout, d, h, w):
     got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
                            out_ndhwc=True, res_ndhwc=True)
     rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tcg bn+res+relu ndhwc")
+
+
+@pytest.mark.parametrize("b,cin,cout,d,h,w", [
+    (1, 32, 64, 4, 8, 128),     # GwcNet/PSMNet conv1: 1/4 -> 1/8 res
+    (2, 16, 64, 2, 6, 128),     # ragged output rows (3 rows, blocks of 4)
+    (1, 64, 128, 4, 8, 64),     # GwcNet conv3: 1/8 -> 1/16 res (N = 128 + 256)
+    (1, 64, 64, 2, 16, 64),     # PSMNet conv3
+])
+def test_conv3d_s2_tc(ops, b, cin, cout, d, h, w):
+    """Stride-2 tensor-core conv (conv3d_tcs2.cu) vs the fp64 reference conv."""
+    import torch.nn.functional as F
+    assert ops.conv3d_s2_tc_supported(cin, cout, d, h, w)
+    x, wt = rnd(80, b, cin, d, h, w), rnd(81, cout, cin, 3, 3, 3, scale=0.2)
+    sc, sh = torch.rand(cout, generator=torch.Generator().manual_seed(82)) + 0.5, rnd(83, cout, scale=0.1)
+    want = F.conv3d(x.double(), wt.double(), stride=2, padding=1).float()
+    xc = ops.to_ndhwc(dev(x))
+    wp = ops.pack_tc_weight(dev(wt), 16, kw_order=(1, 0, 2))
+    got = ops.conv3d_k3_s2_tc(xc, wp)
+    rel_close(got, want, 1e-5, "s2 tc plain")
+    res = rnd(84, *want.shape)
+    want2 = F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res)
+    got = ops.conv3d_k3_s2_tc(xc, wp, dev(sc), dev(sh), dev(res), ops.ACT_RELU)
+    rel_close(got, want2, 1e-5, "s2 tc bn+res+relu")
+    got = ops.conv3d_k3_s2_tc(xc, wp, dev(sc), dev(sh), None, ops.ACT_RELU, out_ndhwc=True)
+    rel_close(got.permute(0, 4, 1, 2, 3), F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)), 1e-5, "s2 tc ndhwc out")

@@ -47,3 +47,19 @@ for name, cin, cout, d, h, w in [("conv2_64to64_w64", 64, 64, 24, 32, 64), ("con
     print(json.dumps({"layer": name, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3), "to_ndhwc_ms": round(ms2, 3),
                       "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
                       "rel_err_vs_cuda_core": err}), flush=True)
+
+for name, cin, cout, d, h, w in [("conv1_s2_32to64", 32, 64, 48, 64, 128), ("conv3_s2_64to128", 64, 128, 24, 32, 64)]:
+    wgt = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.05
+    sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1
+    xn = torch.randn(B, cin, d, h, w, device=dev)
+    xc = ops.to_ndhwc(xn)
+    wp, wt = ops.pack_conv_weight(wgt), ops.pack_tc_weight(wgt, 16, kw_order=(1, 0, 2))
+    flops = 2 * B * cout * cin * 27 * (d // 2) * (h // 2) * (w // 2)
+    ref = ops.conv3d_k3(xn, wp, sc, sh, None, None, 2, ops.ACT_RELU)
+    got = ops.conv3d_k3_s2_tc(xc, wt, sc, sh, None, ops.ACT_RELU)
+    err = ((ref - got).abs().max() / ref.abs().max()).item()
+    ms0, _ = timeit(lambda: ops.conv3d_k3(xn, wp, sc, sh, None, None, 2, ops.ACT_RELU), 5, flush)
+    ms1, _ = timeit(lambda: ops.conv3d_k3_s2_tc(xc, wt, sc, sh, None, ops.ACT_RELU), 5, flush)
+    print(json.dumps({"layer": name, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3),
+                      "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
+                      "rel_err_vs_cuda_core": err}), flush=True)
