@@ -151,6 +151,13 @@ int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W);
 int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
                             const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                             int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) on the tensor cores: x (B,D,H,W,Cin) channels-last ->
+ * y (B,Cout,2D,2H,2W) or channels-last.  w_split = ops.pack_tc_deconv_weight(weight): the (Cin,Cout,3,3,3) parameter split
+ * hi/lo, 16-channel K chunks, kw slices stored as (1,2,0).  Supported: W=32/Cout=64 (conv5), W=64/Cout=32 (conv6). */
+int osb_deconv3d_tc_supported(int Cin, int Cout, int W);
+int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+                           const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                           int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* (B,C,D,H,W) -> (B,D,H,W,C) layout change feeding the tensor-core conv. */
 int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream);
 

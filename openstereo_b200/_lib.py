@@ -29,6 +29,8 @@ SIGNATURES = {
     "osb_conv3d_tc_supported": [_i, _i, _i, _i],
     "osb_conv3d_tc_kc": [_i, _i, _i, _i],
     "osb_conv3d_s2_tc_supported": [_i, _i, _i, _i, _i],
+    "osb_deconv3d_tc_supported": [_i, _i, _i],
+    "osb_deconv3d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv3d_k3_s2_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv3d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_ncdhw_to_ndhwc": [_f32p, _f32p, _i, _i, _i, _i, _i, _s],

@@ -92,6 +92,11 @@ def _conv_auto(layer, x, act=ACT_NONE, residual=None):
 
 
 def _deconv(layer, x, act=ACT_NONE, residual=None):
+    if (USE_TENSOR_CORES and layer.transposed and layer.kernel == 3 and layer._w5 is not None
+            and ops.deconv3d_tc_supported(layer.cin, layer.cout, x.shape[-1])):
+        if "dc" not in layer._tc:
+            layer._tc["dc"] = ops.pack_tc_deconv_weight(layer._w5)
+        return ops.deconv3d_k3_tc(ops.to_ndhwc(x), layer._tc["dc"], layer.scale, layer.shift, residual, act)
     return ops.deconv3d(x, layer.w, layer.scale, layer.shift, residual, layer.kernel, act)
 
 

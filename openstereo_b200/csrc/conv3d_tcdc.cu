@@ -1,0 +1,440 @@
+// Tensor-core (tcgen05) ConvTranspose3d k=3, stride 2, padding 1, output_padding 1: the up-sampling convs of the hourglasses
+//   conv5 128->64 / 64->64 (1/16 -> 1/8 res) and conv6 64->32 (1/8 -> 1/4 res): gwcnet/hourglass.py:35-41,
+//   psmnet/psmnet_cost_processor.py:99-106 (deconv3d_bn).
+// Per dimension an output index o gathers  o even (=2m): tap k=1 from input m;  o odd (=2m+1): k=0 from m+1 and k=2 from m.
+// Same machinery as conv3d_tcg.cu / conv3d_tcs2.cu (3xTF32 split, LDG-staged swizzled operands, warp-specialised
+// persistent CTA).  An accumulator tile holds the output rows of ONE parity class: plane od, rows oh = 2j + ph for
+// R = 128/Win consecutive j, all 2*Win output columns.  For each valid tap pair (kd, kh) the operand tile is the R input
+// rows j (+1 for k=0) of input plane id, un-shifted in w, and one MMA with the kw slices stacked along N gives
+//   E[m] = A[m].W1 -> output column 2m,      P2[m] = A[m].W2 and P0[m] = A[m].W0 -> output column 2m+1 = P2[m] + P0[m+1];
+// the epilogue does that single right shift (zero at m = Win-1: the column beyond the input) and writes both columns.
+// Tap pairs per tile: 1, 2, 2 or 4 depending on (od&1, ph); work items interleave the classes so every CTA gets a mix.
+#include "tc_common.cuh"
+
+namespace osb {
+
+struct TcdcParams {
+  const float* x;          // (B, D, H, W, Cin) channels-last
+  const float* w;          // [2 (hi,lo)][3 kd][Cin/KC][3 kh][3*Cout][KC]
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  float* y;
+  int B, D, H, Cin;        // INPUT extent D x H x W; output is 2D x 2H x 2W
+  int act;
+  int out_ndhwc, res_ndhwc;
+  int items, hblocks;
+};
+
+template <int COUT, int KC, int W, int TILES>     // W = INPUT width
+struct TcdcCfg {
+  static constexpr int R = 128 / W;                         // input rows (= output rows of one parity) per M tile
+  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row
+  static constexpr int UNIT_BYTES = 128 * ROWB;
+  static constexpr int N3 = 3 * COUT;
+  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
+  static constexpr int STAGES = 4;
+  static constexpr int HBLK = TILES * R;                    // output rows per work item
+  static constexpr int KSTEPS = KC / 8;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
+  static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
+  static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4;
+  static_assert(TILES * N3 <= 512, "accumulators exceed TMEM");
+  static_assert(B_SLICE % 1024 == 0 && UNIT_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+  static_assert(N3 % 16 == 0 && N3 <= 256, "invalid UMMA N");
+};
+
+// work item = (image b, output plane od, row parity ph, block of TILES*R input rows); parity bits vary fastest so that the
+// 1/2/2/4-tap classes are interleaved over the persistent CTAs
+struct ItemDc {
+  int b, od, ph, j0, last_kd, last_kh;
+};
+template <class C>
+__device__ __forceinline__ ItemDc decode_dc(const TcdcParams& p, int it) {
+  ItemDc w;
+  w.ph = it & 1;
+  it >>= 1;
+  const int Do = 2 * p.D;
+  w.od = it % Do;
+  it /= Do;
+  w.j0 = (it % p.hblocks) * C::HBLK;
+  w.b = it / p.hblocks;
+  w.last_kd = (w.od & 1) ? 2 : 1;
+  w.last_kh = w.ph ? 2 : 1;
+  return w;
+}
+// output index o gathers tap k from input (o + 1 - k) / 2 when that is an integer inside [0, n)
+__device__ __forceinline__ bool kd_valid(int od, int kd, int D) {
+  const int num = od + 1 - kd;
+  return !(num & 1) && (num >> 1) < D;
+}
+__device__ __forceinline__ bool kh_valid(int ph, int kh) { return ((ph + 1 - kh) & 1) == 0; }
+
+template <int COUT, int KC, int W, int TILES>
+__global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d_tcdc_kernel(const TcdcParams p) {
+  using C = TcdcCfg<COUT, KC, W, TILES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* a_hi = smem + C::A_OFF;
+  uint8_t* a_lo = a_hi + C::STAGES * C::UNIT_BYTES;
+  uint8_t* b_buf = smem + C::B_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
+  uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
+  uint64_t* b_full = a_empty + C::STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
+  uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
+  uint64_t* acc_full = b_empty + 3;                 // [TILES]
+  uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
+  float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
+  float* s_scale = xchg + 2 * 4 * 2 * 32;
+  float* s_shift = s_scale + COUT;
+  float* zeros = s_shift + COUT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = p.Cin / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&a_ready[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int k = 0; k < 3; ++k) {
+      mbar_init(&b_full[k], 64);
+      mbar_init(&b_empty[k], 1);
+    }
+    for (int t = 0; t < TILES; ++t) {
+      mbar_init(&acc_full[t], 1);
+      mbar_init(&acc_empty[t], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int c = threadIdx.x; c < COUT; c += blockDim.x) {
+    s_scale[c] = p.scale ? p.scale[c] : 1.f;
+    s_shift[c] = p.shift ? p.shift[c] : 0.f;
+    zeros[c] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---------------------------------------------------------------------------------------------- MMA issuer
+  if (warp == 0) {
+    const uint32_t idesc = idesc_tf32(128, C::N3);
+    const uint64_t dbase = (KC == 32) ? desc_sw128_base() : desc_sw64_base();
+    const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
+    uint32_t unitc = 0, itc = 0;
+    uint32_t bph[3] = {0, 0, 0};                      // per-slice use counters (slices are loaded only for valid kh)
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
+      const ItemDc w = decode_dc<C>(p, it);
+      const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
+      uint32_t started = 0;
+      for (int kd = 0; kd < 3; ++kd) {
+        if (!kd_valid(w.od, kd, p.D)) continue;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const bool last_phase = (kd == w.last_kd) && (ch == nchunk - 1);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              if (!kh_valid(w.ph, kh)) continue;        // warp-uniform
+              const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
+              mbar_wait(&a_ready[slot], ph);
+              if (t == 0) mbar_wait(&b_full[kh], bph[kh] & 1);   // first use of slice kh in this phase
+              tc_fence_after();
+              if (t < ntiles) {
+                const uint32_t accum = (started >> t) & 1;
+                if (!accum) {
+                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
+                  tc_fence_after();
+                  started |= 1u << t;
+                }
+                if (elect_one()) {
+                  const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+                  const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+                  const uint32_t acc = tmem + t * C::N3;
+                  const uint64_t dbh0 = dbase | (uint64_t)(b16 + (kh * 2 * C::B_SLICE) / 16);
+                  const uint64_t dbl0 = dbh0 + C::B_SLICE / 16;
+#pragma unroll
+                  for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                    mma_tf32(acc, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                    mma_tf32(acc, dah0 + 2 * ks, dbl0 + 2 * ks, idesc, 1);
+                    mma_tf32(acc, dah0 + 2 * ks, dbh0 + 2 * ks, idesc, 1);
+                  }
+                }
+                __syncwarp();
+              }
+              if (elect_one()) {
+                mma_commit(&a_empty[slot]);
+                if (t == TILES - 1) mma_commit(&b_empty[kh]);                    // last user of slice kh in this phase
+                if (last_phase && kh == w.last_kh) mma_commit(&acc_full[t]);     // tile t has received its last tap
+              }
+              __syncwarp();
+              if (t == TILES - 1) ++bph[kh];
+              ++unitc;
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- A-unit loaders
+  else if (warp < 5) {
+    const int lt = threadIdx.x - 32;                 // 0..127
+    constexpr int CPR = C::ROWB / 16;                // 16-byte chunks per operand row (8 or 4)
+    constexpr int NLD = 128 * CPR / 128;             // float4 loads per thread per unit (8 or 4)
+    uint32_t unitc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const ItemDc w = decode_dc<C>(p, it);
+      for (int kd = 0; kd < 3; ++kd) {
+        if (!kd_valid(w.od, kd, p.D)) continue;
+        const int id = (w.od + 1 - kd) >> 1;         // input plane feeding output plane od through tap kd
+        const float* plane = p.x + ((size_t)w.b * p.D + id) * p.H * (size_t)W * p.Cin;
+        for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              if (!kh_valid(w.ph, kh)) continue;
+              float4 v[NLD];
+#pragma unroll
+              for (int j = 0; j < NLD; ++j) {
+                const int f = lt + 128 * j;
+                const int vox = f / CPR, c = f % CPR;   // operand row = input voxel (row vox / W, column vox % W)
+                const int hin = w.j0 + t * C::R + vox / W + (kh == 0 ? 1 : 0), win = vox % W;
+                v[j] = (hin < p.H) ? __ldg(reinterpret_cast<const float4*>(plane + ((size_t)hin * W + win) * p.Cin + ch * KC + c * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
+              mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+              uint8_t* hi = a_hi + slot * C::UNIT_BYTES;
+              uint8_t* lo = a_lo + slot * C::UNIT_BYTES;
+#pragma unroll
+              for (int j = 0; j < NLD; ++j) {
+                const int f = lt + 128 * j;
+                const int off = swz_offset<KC>(f / CPR, f % CPR);
+                *reinterpret_cast<float4*>(hi + off) = v[j];
+                *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+              }
+              fence_proxy_async();
+              mbar_arrive(&a_ready[slot]);
+              ++unitc;
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- epilogue
+  else if (warp < 9) {
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;                     // operand row owned by this thread
+    const int rr = m / W, wcol = m % W;              // input row inside the tile, input column
+    const bool has_right_q = (((q + 1) * 32) % W) != 0;   // the next quadrant continues the same image row
+    const int Do = 2 * p.D, Ho = 2 * p.H;
+    constexpr int Wo = 2 * W;
+    uint32_t itc = 0, exc = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
+      const ItemDc w = decode_dc<C>(p, it);
+      const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait_relaxed(&acc_full[t], itc & 1);
+        tc_fence_after();
+        const int j = w.j0 + t * C::R + rr;
+        const bool live = j < p.H;
+        const int oh = 2 * j + w.ph;
+        const size_t vox = (((size_t)w.b * Do + w.od) * Ho + oh) * Wo + 2 * wcol;      // NDHWC index of the EVEN output voxel
+        const size_t plane = (size_t)Do * Ho * Wo;                                   // NCDHW channel stride
+        const size_t ncdhw0 = (size_t)w.b * COUT * plane + ((size_t)w.od * Ho + oh) * Wo + 2 * wcol;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
+#pragma unroll 1
+        for (int cg = 0; cg < COUT; cg += 32) {
+          // accumulator column groups: raw[0] = E (kw=1), raw[1] = P2 (kw=2), raw[2] = P0 (kw=0)
+          uint32_t raw[3][32];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) tmem_ld16_nowait(trow + kw * COUT + cg + c0, &raw[kw][c0]);
+          tmem_ld_wait();
+          if (cg + 32 >= COUT) {                      // whole tile in registers: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&acc_empty[t]);
+          }
+          float* xb = xchg + (exc & 1) * (4 * 2 * 32);
+          ++exc;
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xb[(q * 2) * 32 + i] = __uint_as_float(raw[2][i]);
+          }
+          named_bar_sync(1, 128);
+          const float* xr = has_right_q ? xb + ((q + 1) * 2) * 32 : zeros;
+          float ev[32], od_[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
+            right = (lane == 31) ? xr[i] : right;                                        // zero beyond the last input column
+            ev[i] = fmaf(__uint_as_float(raw[0][i]), s_scale[cg + i], s_shift[cg + i]);
+            od_[i] = fmaf(__uint_as_float(raw[1][i]) + right, s_scale[cg + i], s_shift[cg + i]);
+          }
+          if (live) {
+            if (p.residual) {
+              if (p.res_ndhwc) {
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);
+                const float4* rq = reinterpret_cast<const float4*>(p.residual + (vox + 1) * COUT + cg);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 a = __ldg(rp + i), bq = __ldg(rq + i);
+                  ev[4 * i] += a.x, ev[4 * i + 1] += a.y, ev[4 * i + 2] += a.z, ev[4 * i + 3] += a.w;
+                  od_[4 * i] += bq.x, od_[4 * i + 1] += bq.y, od_[4 * i + 2] += bq.z, od_[4 * i + 3] += bq.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float2 rv = __ldg(reinterpret_cast<const float2*>(p.residual + ncdhw0 + (size_t)(cg + i) * plane));
+                  ev[i] += rv.x, od_[i] += rv.y;
+                }
+              }
+            }
+            if (p.act == OSB_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ev[i] = fmaxf(ev[i], 0.f), od_[i] = fmaxf(od_[i], 0.f);
+            } else if (p.act == OSB_ACT_LEAKY) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                ev[i] = ev[i] > 0.f ? ev[i] : 0.01f * ev[i];
+                od_[i] = od_[i] > 0.f ? od_[i] : 0.01f * od_[i];
+              }
+            }
+            if (p.out_ndhwc) {
+              float4* yp = reinterpret_cast<float4*>(p.y + vox * COUT + cg);
+              float4* yq = reinterpret_cast<float4*>(p.y + (vox + 1) * COUT + cg);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                yp[i] = make_float4(ev[4 * i], ev[4 * i + 1], ev[4 * i + 2], ev[4 * i + 3]);
+                yq[i] = make_float4(od_[4 * i], od_[4 * i + 1], od_[4 * i + 2], od_[4 * i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)             // columns 2w, 2w+1 of consecutive lanes: 256 contiguous bytes per warp
+                *reinterpret_cast<float2*>(p.y + ncdhw0 + (size_t)(cg + i) * plane) = make_float2(ev[i], od_[i]);
+            }
+          }
+        }
+      }
+      for (int t = ntiles; t < TILES; ++t) {            // unused tiles keep the barrier phases in step
+        mbar_wait_relaxed(&acc_full[t], itc & 1);
+        mbar_arrive(&acc_empty[t]);
+      }
+    }
+  }
+  // ---------------------------------------------------------------------------------------------- weight-slice loaders
+  else {
+    const int wt = threadIdx.x - 9 * 32;             // 0..63
+    constexpr int F4 = C::B_SLICE / 16;              // float4 per (kh, hi|lo)
+    constexpr int PER = F4 / 64;                     // per thread
+    constexpr int CPR = C::ROWB / 16;
+    static_assert(F4 % 64 == 0, "weight slice must split evenly over 64 loader threads");
+    uint32_t bph[3] = {0, 0, 0};
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const ItemDc w = decode_dc<C>(p, it);
+      for (int kd = 0; kd < 3; ++kd) {
+        if (!kd_valid(w.od, kd, p.D)) continue;         // same phase enumeration as the MMA warp and the A loaders
+        for (int ch = 0; ch < nchunk; ++ch) {
+          for (int kh = 0; kh < 3; ++kh) {
+            if (!kh_valid(w.ph, kh)) continue;
+            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)(C::N3 * KC);
+            const size_t half_stride = (size_t)3 * nchunk * 3 * C::N3 * KC;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float4 v[PER];
+#pragma unroll
+              for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
+              if (half == 0) mbar_wait_relaxed(&b_empty[kh], (bph[kh] & 1) ^ 1);
+#pragma unroll
+              for (int j = 0; j < PER; ++j) {
+                const int f = wt + 64 * j;
+                *reinterpret_cast<float4*>(b_buf + (kh * 2 + half) * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(&b_full[kh]);
+            ++bph[kh];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int COUT, int KC, int W, int TILES>
+static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
+  using C = TcdcCfg<COUT, KC, W, TILES>;
+  auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv3d_tcg: cannot reserve %zu bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return OSB_ECUDA;
+    }
+    configured = true;
+  }
+  p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
+  const long long items = (long long)p.B * (2 * p.D) * 2 * p.hblocks;
+  OSB_REQUIRE(items < (1ll << 31), "conv3d_tcdc: too many work items");
+  p.items = (int)items;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    sms = 148;
+  }
+  const int grid = p.items < sms ? p.items : sms;
+  kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
+  count_launch();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa{};
+    (void)cudaFuncGetAttributes(&fa, kernel);
+    set_error("conv3d_tcdc_kernel<%d,%d,%d,%d>: launch failed: %s (threads %d, kernel maxThreadsPerBlock %d, regs %d, static smem %zu, "
+              "dynamic smem %zu, max dynamic %d)", COUT, KC, W, TILES, cudaGetErrorString(le), C::THREADS, fa.maxThreadsPerBlock,
+              fa.numRegs, fa.sharedSizeBytes, C::SMEM, fa.maxDynamicSharedSizeBytes);
+    return OSB_ECUDA;
+  }
+  return OSB_OK;
+}
+
+}  // namespace osb
+
+extern "C" {
+
+int osb_deconv3d_tc_supported(int Cin, int Cout, int W) {
+  if (Cin % 16 != 0 || Cin < 16) return 0;
+  return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) ? 1 : 0;
+}
+
+int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+                           const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                           int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x_ndhwc && w_split && y, "deconv3d_k3_tc: null pointer");
+  OSB_REQUIRE(B > 0 && D > 0 && H > 0, "deconv3d_k3_tc: empty shape");
+  OSB_REQUIRE(osb_deconv3d_tc_supported(Cin, Cout, W), "deconv3d_k3_tc: unsupported shape Cin=%d Cout=%d W=%d", Cin, Cout, W);
+  OSB_REQUIRE(act >= 0 && act <= 2, "deconv3d_k3_tc: unknown activation %d", act);
+  TcdcParams p{};
+  p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
+  p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (W == 32) return launch_tcdc<64, 16, 32, 2>(p, s);
+  return launch_tcdc<32, 16, 64, 5>(p, s);
+}
+}

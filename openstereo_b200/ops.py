@@ -331,3 +331,29 @@ def conv3d_k3_s2_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act
     _call("osb_conv3d_k3_s2_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
     return y
+
+
+def deconv3d_tc_supported(cin, cout, w):
+    return bool(_lib.lib.osb_deconv3d_tc_supported(int(cin), int(cout), int(w)))
+
+
+def pack_tc_deconv_weight(weight):
+    """(Cin, Cout, 3, 3, 3) ConvTranspose3d parameter -> hi/lo split, 16-channel chunks, kw slices ordered (1, 2, 0):
+    even output columns come from tap 1, odd ones from taps 2 (same input column) and 0 (next input column)."""
+    return pack_tc_weight(weight.detach().float().permute(1, 0, 2, 3, 4).contiguous(), 16, kw_order=(1, 2, 0))
+
+
+def deconv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=False, res_ndhwc=False):
+    """ConvTranspose3d(k3, s2, p1, op1) + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    cout = w_split.shape[4] // 3
+    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    shape = (b, 2 * d, 2 * h, 2 * w, cout) if out_ndhwc else (b, cout, 2 * d, 2 * h, 2 * w)
+    y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
+    if residual is not None:
+        want = (b, 2 * d, 2 * h, 2 * w, cout) if res_ndhwc else (b, cout, 2 * d, 2 * h, 2 * w)
+        assert tuple(residual.shape) == want and residual.is_contiguous()
+    _call("osb_deconv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+    return y

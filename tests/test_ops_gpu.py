@@ -336,3 +336,29 @@ def test_conv3d_s2_tc(ops, b, cin, cout, d, h, w):
     rel_close(got, want2, 1e-5, "s2 tc bn+res+relu")
     got = ops.conv3d_k3_s2_tc(xc, wp, dev(sc), dev(sh), None, ops.ACT_RELU, out_ndhwc=True)
     rel_close(got.permute(0, 4, 1, 2, 3), F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)), 1e-5, "s2 tc ndhwc out")
+
+
+@pytest.mark.parametrize("b,cin,cout,d,h,w", [
+    (1, 128, 64, 3, 8, 32),     # GwcNet conv5: 1/16 -> 1/8 res
+    (2, 64, 64, 2, 5, 32),      # PSMNet conv5, ragged rows
+    (1, 64, 32, 3, 10, 64),     # conv6: 1/8 -> 1/4 res (five 2-row tiles per item)
+    (2, 16, 32, 1, 3, 64),      # ragged, single input plane
+])
+def test_deconv3d_tc(ops, b, cin, cout, d, h, w):
+    """Transposed conv on the tensor cores (conv3d_tcdc.cu) vs the fp64 reference."""
+    import torch.nn.functional as F
+    assert ops.deconv3d_tc_supported(cin, cout, w)
+    x, wt = rnd(90, b, cin, d, h, w), rnd(91, cin, cout, 3, 3, 3, scale=0.2)
+    sc, sh = torch.rand(cout, generator=torch.Generator().manual_seed(92)) + 0.5, rnd(93, cout, scale=0.1)
+    want = F.conv_transpose3d(x.double(), wt.double(), stride=2, padding=1, output_padding=1).float()
+    xc = ops.to_ndhwc(dev(x))
+    wp = ops.pack_tc_deconv_weight(dev(wt))
+    got = ops.deconv3d_k3_tc(xc, wp)
+    rel_close(got, want, 1e-5, "deconv tc plain")
+    res = rnd(94, *want.shape)
+    want2 = F.relu(want * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1) + res)
+    got = ops.deconv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res), ops.ACT_RELU)
+    rel_close(got, want2, 1e-5, "deconv tc bn+res+relu")
+    got = ops.deconv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
+                             out_ndhwc=True, res_ndhwc=True)
+    rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "deconv tc ndhwc")

@@ -63,3 +63,19 @@ for name, cin, cout, d, h, w in [("conv1_s2_32to64", 32, 64, 48, 64, 128), ("con
     print(json.dumps({"layer": name, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3),
                       "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
                       "rel_err_vs_cuda_core": err}), flush=True)
+
+for name, cin, cout, d, h, w in [("deconv5_128to64", 128, 64, 12, 16, 32), ("deconv6_64to32", 64, 32, 24, 32, 64)]:
+    wgt = torch.randn(cin, cout, 3, 3, 3, device=dev) * 0.05
+    sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.1
+    xn = torch.randn(B, cin, d, h, w, device=dev)
+    xc = ops.to_ndhwc(xn)
+    wp, wt = ops.pack_deconv_weight(wgt), ops.pack_tc_deconv_weight(wgt)
+    flops = 2 * B * cout * cin * 27 * d * h * w
+    ref = ops.deconv3d(xn, wp, sc, sh, None, 3, ops.ACT_RELU)
+    got = ops.deconv3d_k3_tc(xc, wt, sc, sh, None, ops.ACT_RELU)
+    err = ((ref - got).abs().max() / ref.abs().max()).item()
+    ms0, _ = timeit(lambda: ops.deconv3d(xn, wp, sc, sh, None, 3, ops.ACT_RELU), 5, flush)
+    ms1, _ = timeit(lambda: ops.deconv3d_k3_tc(xc, wt, sc, sh, None, ops.ACT_RELU), 5, flush)
+    print(json.dumps({"layer": name, "cuda_core_ms": round(ms0, 3), "tensor_core_ms": round(ms1, 3),
+                      "cuda_core_TF": round(flops / ms0 / 1e9, 1), "tensor_core_TF": round(flops / ms1 / 1e9, 1),
+                      "rel_err_vs_cuda_core": err}), flush=True)
