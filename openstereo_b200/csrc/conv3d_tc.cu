@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
               for (int kh = 0; kh < 3; ++kh) {
                 const int t = r - kh;                 // output row tile fed by input row r through tap kh (compile time)
                 if (t < 0 || t >= TC_TILES) continue;
+                const uint32_t accum = (started >> t) & 1;
+                if (!accum) {                         // first touch of this tile in this item: the previous item's epilogue
+                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);     // must have drained it.  Taken for UNUSED tiles too: otherwise
+                  tc_fence_after();                            // acc_full[t] could complete twice before the epilogue looks
+                  started |= 1u << t;                          // and the mbarrier parity would alias (deadlock).
+                }
                 if (t < ntiles) {
-                  const uint32_t accum = (started >> t) & 1;
-                  if (!accum) {                       // first touch of this tile in this item: the previous item's
-                    mbar_wait(&acc_empty[t], (itc & 1) ^ 1);   // epilogue must have drained it
-                    tc_fence_after();
-                    started |= 1u << t;
-                  }
                   const uint32_t acc = tmem + t * N3;
                   const uint64_t dbh0 = dbase | (uint64_t)(b16 + kh * (2 * B_SLICE / 16));
                   const uint64_t dbl0 = dbh0 + B_SLICE / 16;

@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               mbar_wait(&a_ready[slot], ph);
               if (t == 0) mbar_wait(&b_full[kh], bph[kh] & 1);   // first use of slice kh in this phase
               tc_fence_after();
+              const uint32_t accum = (started >> t) & 1;
+              if (!accum) {                             // hand-shake taken for unused tiles too (parity must not alias)
+                mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
+                tc_fence_after();
+                started |= 1u << t;
+              }
               if (t < ntiles) {
-                const uint32_t accum = (started >> t) & 1;
-                if (!accum) {
-                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
-                  tc_fence_after();
-                  started |= 1u << t;
-                }
                 if (elect_one()) {
                   const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
                   const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);

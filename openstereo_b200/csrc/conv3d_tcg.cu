@@ -139,13 +139,13 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
             for (int kh = 0; kh < 3; ++kh) {
               const int t = C::tile_of(s, kh);
               if (t < 0) continue;
+              const uint32_t accum = (started >> t) & 1;
+              if (!accum) {                             // hand-shake taken for unused tiles too (parity must not alias)
+                mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
+                tc_fence_after();
+                started |= 1u << t;
+              }
               if (t < ntiles) {
-                const uint32_t accum = (started >> t) & 1;
-                if (!accum) {
-                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
-                  tc_fence_after();
-                  started |= 1u << t;
-                }
                 if (elect_one()) {
 #pragma unroll
                   for (int mm = 0; mm < C::NMMA; ++mm) {

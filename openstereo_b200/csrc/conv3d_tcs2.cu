@@ -126,13 +126,13 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
                 mbar_wait(&a_ready[slot], ph);
                 if (t == 0 && par == 0) mbar_wait(&b_full[kh], phc & 1);   // first use of slice kh in this phase
                 tc_fence_after();
+                const uint32_t accum = (started >> (2 * t + par)) & 1;
+                if (((started >> (2 * t)) & 3u) == 0u) {     // first touch of this tile in this item (unused tiles too)
+                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
+                  tc_fence_after();
+                }
+                started |= 1u << (2 * t + par);
                 if (t < ntiles) {
-                  const uint32_t accum = (started >> (2 * t + par)) & 1;
-                  if (((started >> (2 * t)) & 3u) == 0u) {   // first touch of this tile in this item
-                    mbar_wait(&acc_empty[t], (itc & 1) ^ 1);
-                    tc_fence_after();
-                  }
-                  started |= 1u << (2 * t + par);
                   if (elect_one()) {
                     const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
                     const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);

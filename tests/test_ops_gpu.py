@@ -362,3 +362,27 @@ def test_deconv3d_tc(ops, b, cin, cout, d, h, w):
     got = ops.deconv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
                              out_ndhwc=True, res_ndhwc=True)
     rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "deconv tc ndhwc")
+
+
+@pytest.mark.timeout(120)
+def test_tc_kernels_partial_blocks_many_items(ops):
+    """Regression for the accumulator hand-off: work items whose row block is partial leave accumulator tiles unused; with
+    several such items per persistent CTA and a slow epilogue (residual reads) the unused tiles' barriers used to complete
+    twice and alias in parity (deadlock).  Shapes: H=32 with 10-row blocks (deconv, 5 tiles) and H=68 with 5-row blocks."""
+    x = torch.randn(4, 64, 12, 32, 64, device="cuda")
+    wt = torch.randn(64, 32, 3, 3, 3, device="cuda") * 0.1
+    sc, sh = torch.rand(32, device="cuda") + 0.5, torch.randn(32, device="cuda") * 0.1
+    res = torch.randn(4, 32, 24, 64, 128, device="cuda")
+    ref = ops.deconv3d(x, ops.pack_deconv_weight(wt), sc, sh, res, 3, ops.ACT_RELU)
+    for _ in range(3):
+        got = ops.deconv3d_k3_tc(ops.to_ndhwc(x), ops.pack_tc_deconv_weight(wt), sc, sh, res, ops.ACT_RELU)
+    torch.cuda.synchronize()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+    x = torch.randn(2, 32, 6, 68, 128, device="cuda")            # 68 rows = 13 full blocks of 5 + one of 3
+    wt = torch.randn(32, 32, 3, 3, 3, device="cuda") * 0.1
+    res = torch.randn(2, 32, 6, 68, 128, device="cuda")
+    ref = ops.conv3d_k3(x, ops.pack_conv_weight(wt), sc, sh, res, None, 1, ops.ACT_RELU)
+    for _ in range(3):
+        got = ops.conv3d_k3_tc(ops.to_ndhwc(x), ops.pack_tc_weight(wt), sc, sh, res, ops.ACT_RELU, out_ndhwc=False, res_ndhwc=False)
+    torch.cuda.synchronize()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() <= 1e-5
