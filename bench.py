@@ -15,7 +15,8 @@ Reported in one JSON line (rank 0):
              and D2H read-back of the per-image EPE inside the timed region, every step
   roofline   the cost-volume kernel named by the metric (HBM-bound), timed live with CUDA events around its launch
              inside the timed steps, against MEASURED_PEAKS.json hbm_gbs
-  roofline_dominant  the kernel that dominates the step (3x3x3 Conv3d, fp32-FMA-bound), same live timing
+  roofline_dominant  the kernel family that dominates the hot path (3x3x3 Conv3d / ConvTranspose3d on tcgen05, 3xTF32),
+             same live timing; roofline_cuda_core = the fp32 layers still on CUDA cores
   cpu_baseline  the oracle port of the reference (same aten CPU kernels) on the host cores, bounded sample
 --impl reference times that oracle port as the reference arm (the reference is pure Python/PyTorch and cannot travel;
 oracle/__init__.py explains the provenance).
@@ -326,37 +327,58 @@ def run_ours(args):
                     "frac_of_8TBs_nominal": round(ach / 8000.0, 4), "peak_source": peak_src,
                     "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4), "traffic": None,
                     "share_of_step": round(vol_total / ms, 4)}
-    # ---- 3D aggregation: tensor-core (tcgen05, 3xTF32) full-resolution layers + fp32 CUDA-core layers
+    # ---- 3D aggregation: MACs per pair of GwcNet-gc at D'=48, H'=64, W'=128
     vox = 48 * 64 * 128
-    tc_macs_pair = vox * 27 * 32 * (64 + 4 * 32)                    # dres0a (64->32), dres0b, dres1a, dres1b, classif3a
-    all_macs_pair = 116.30e9
-    tc_ms, tc_n, tc_total = kernel_stats("osb_conv3d_k3_tc_fwd")
-    bf16_peak = None
+    macs = {
+        # stem dres0a (64->32) + dres0b, dres1a, dres1b, classif3a (32->32) at full resolution; 3 x (conv2, conv4)
+        "osb_conv3d_k3_tc_fwd": vox * 27 * 32 * (64 + 4 * 32) + 3 * (vox // 8 * 27 * 64 * 64 + vox // 64 * 27 * 128 * 128),
+        # 3 x (conv1 32->64 to 1/2, conv3 64->128 to 1/4): MACs counted at the OUTPUT voxels
+        "osb_conv3d_k3_s2_tc_fwd": 3 * (vox // 8 * 27 * 32 * 64 + vox // 64 * 27 * 64 * 128),
+        # 3 x (conv5 128->64, conv6 64->32): every INPUT voxel feeds 27 taps
+        "osb_deconv3d_k3_tc_fwd": 3 * (vox // 64 * 27 * 128 * 64 + vox // 8 * 27 * 64 * 32),
+        # redir1 (32->32, full) and redir2 (64->64, half) of the three hourglasses
+        "osb_conv1x1_ndhwc_fwd": 3 * (vox * 32 * 32 + vox // 8 * 64 * 64),
+        # classif3b 32->1 head
+        "osb_conv3d_k3_bn_act_fwd": vox * 27 * 32,
+    }
+    tc_names = ["osb_conv3d_k3_tc_fwd", "osb_conv3d_k3_s2_tc_fwd", "osb_deconv3d_k3_tc_fwd"]
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             bf16_peak = float(json.load(f).get("bf16_tflops_sustained"))
     except Exception:
         bf16_peak = 1400.0
-    roof_tc = None
-    if tc_total > 0:
-        useful = 2 * tc_macs_pair * B * args.steps / (tc_total / 1e3) / 1e12
-        tf32_peak = bf16_peak / 2.0                                 # dense tf32 = half the bf16 rate
-        roof_tc = {"kernel": "conv3d_tc_kernel<32> (tcgen05 kind::tf32, 3xTF32 split, 5 launches/step)", "bound": "tensor",
-                   "achieved": round(3 * useful, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
-                   "frac": round(3 * useful / tf32_peak, 4), "useful_fp32_equivalent_tflops": round(useful, 1),
-                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 rate); 3 MMAs per fp32-accurate product",
-                   "alg_flops_per_step": 2 * tc_macs_pair * B, "share_of_step": round(tc_total / ms, 4), "traffic": None}
-    conv_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd"]
-    conv_total = sum(kernel_stats(n)[2] for n in conv_names)
-    conv_flops = 2 * (all_macs_pair - (tc_macs_pair if tc_total > 0 else 0)) * B
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                 # derived: SMs x fp32 lanes x 2 x max clock
+    tf32_peak = bf16_peak / 2.0                                     # dense tf32 = half the bf16 rate
     roof_dom = None
-    if conv_total > 0:
-        ach = conv_flops * args.steps / (conv_total / 1e3) / 1e12
-        roof_dom = {"kernel": "conv3d_k3_kernel + deconv3d_kernel + conv3d_1x1_kernel (fp32 CUDA-core layers of the 3D aggregation)",
-                    "bound": "fp32_fma", "achieved": round(ach, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
-                    "frac": round(ach / fp32_peak, 4), "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
-                    "alg_flops_per_step": conv_flops, "share_of_step": round(conv_total / ms, 4), "traffic": None}
+    tc_total = sum(kernel_stats(n)[2] for n in tc_names)
+    if tc_total > 0:
+        per = {}
+        for n in tc_names:
+            _, cnt, tot = kernel_stats(n)
+            if tot > 0:
+                per[n] = {"launches_per_step": cnt // args.steps, "ms_per_step": round(tot / args.steps, 3),
+                          "useful_tflops": round(2 * macs[n] * B * args.steps / (tot / 1e3) / 1e12, 1)}
+        useful = 2 * sum(macs[n] for n in tc_names) * B * args.steps / (tc_total / 1e3) / 1e12
+        roof_dom = {"kernel": "tcgen05 conv family: conv3d_tc_kernel / conv3d_tcg_kernel (3x3x3 s1), conv3d_tcs2_kernel (s2), "
+                              "conv3d_tcdc_kernel (transposed); kind::tf32 with the 3xTF32 split",
+                    "bound": "tensor", "achieved": round(3 * useful, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(3 * useful / tf32_peak, 4), "useful_fp32_equivalent_tflops": round(useful, 1),
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense tf32 rate); achieved counts the 3 MMAs "
+                                   "issued per fp32-accurate product",
+                    "alg_flops_per_step": 2 * sum(macs[n] for n in tc_names) * B, "share_of_step": round(tc_total / ms, 4),
+                    "per_kernel": per, "traffic": None}
+    cc_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd", "osb_conv1x1_ndhwc_fwd"]
+    cc_total = sum(kernel_stats(n)[2] for n in cc_names)
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                 # derived: SMs x fp32 lanes x 2 x max clock
+    roof_cc = None
+    if cc_total > 0:
+        all_macs_pair = sum(macs.values())
+        cc_flops = 2 * (all_macs_pair - (sum(macs[n] for n in tc_names) if tc_total > 0 else 0)) * B
+        ach = cc_flops * args.steps / (cc_total / 1e3) / 1e12
+        roof_cc = {"kernel": "fp32 CUDA-core layers left in the aggregation (classif3b 32->1 head conv3d_k3_kernel, channels-last "
+                             "1x1 redir convs; everything else when the tensor-core variants do not cover a shape)",
+                   "bound": "fp32_fma", "achieved": round(ach, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
+                   "frac": round(ach / fp32_peak, 4), "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
+                   "alg_flops_per_step": cc_flops, "share_of_step": round(cc_total / ms, 4), "traffic": None}
     shares = {}
     for name, ev in prof.items():
         shares[name] = round(sum(a.elapsed_time(b) for a, b in ev) / ms, 4)
@@ -384,7 +406,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "h2d_bytes_per_step": (2 * B * 3 * H * W + B * H * W) * 4, "d2h_bytes_per_step": B * 2 * 4},
         "gpu_launches": launches,
-        "roofline": roofline, "roofline_dominant": roof_dom, "roofline_tensor": roof_tc, "kernel_share_of_step": shares,
+        "roofline": roofline, "roofline_dominant": roof_dom, "roofline_cuda_core": roof_cc, "kernel_share_of_step": shares,
         "cpu_baseline": cpu, "mean_epe_vs_synthetic_gt": round(epe, 3),
     }
     print(json.dumps(line), flush=True)

@@ -144,6 +144,44 @@ class _GwcHourglass:
         return _deconv(self.conv6, c5, ACT_RELU, residual=_conv(self.redir1, x))
 
 
+def _hg_channels_last_ok(hg, x_shape_ndhwc):
+    """True when every layer of a GwcNet hourglass has a tensor-core / channels-last kernel for this input."""
+    if not USE_TENSOR_CORES:
+        return False
+    b, d, h, w, c = x_shape_ndhwc
+    if d % 4 or h % 4 or w % 4:
+        return False
+    return (ops.conv3d_s2_tc_supported(hg.conv1.cin, hg.conv1.cout, d, h, w) and _tc_ok(hg.conv2, w // 2)
+            and ops.conv3d_s2_tc_supported(hg.conv3.cin, hg.conv3.cout, d // 2, h // 2, w // 2) and _tc_ok(hg.conv4, w // 4)
+            and ops.deconv3d_tc_supported(hg.conv5.cin, hg.conv5.cout, w // 4)
+            and ops.deconv3d_tc_supported(hg.conv6.cin, hg.conv6.cout, w // 2)
+            and (hg.redir1.cin, hg.redir1.cout) in ((32, 32), (64, 64)) and (hg.redir2.cin, hg.redir2.cout) in ((32, 32), (64, 64)))
+
+
+def _s2_weight(layer):
+    if "s2" not in layer._tc:
+        layer._tc["s2"] = ops.pack_tc_weight(layer._w5, 16, kw_order=(1, 0, 2))
+    return layer._tc["s2"]
+
+
+def _dc_weight(layer):
+    if "dc" not in layer._tc:
+        layer._tc["dc"] = ops.pack_tc_deconv_weight(layer._w5)
+    return layer._tc["dc"]
+
+
+def _gwc_hourglass_channels_last(hg, x):
+    """GwcNet hourglass (gwcnet/hourglass.py:46-56) with every tensor channels-last: no layout conversion between layers."""
+    c1 = ops.conv3d_k3_s2_tc(x, _s2_weight(hg.conv1), hg.conv1.scale, hg.conv1.shift, None, ACT_RELU, out_ndhwc=True)
+    c2 = _conv_tc(hg.conv2, c1, ACT_RELU)
+    c3 = ops.conv3d_k3_s2_tc(c2, _s2_weight(hg.conv3), hg.conv3.scale, hg.conv3.shift, None, ACT_RELU, out_ndhwc=True)
+    c4 = _conv_tc(hg.conv4, c3, ACT_RELU)
+    r2 = ops.conv1x1_ndhwc(c2, hg.redir2.w, hg.redir2.scale, hg.redir2.shift)
+    c5 = ops.deconv3d_k3_tc(c4, _dc_weight(hg.conv5), hg.conv5.scale, hg.conv5.shift, r2, ACT_RELU, out_ndhwc=True, res_ndhwc=True)
+    r1 = ops.conv1x1_ndhwc(x, hg.redir1.w, hg.redir1.scale, hg.redir1.shift)
+    return ops.deconv3d_k3_tc(c5, _dc_weight(hg.conv6), hg.conv6.scale, hg.conv6.shift, r1, ACT_RELU, out_ndhwc=True, res_ndhwc=True)
+
+
 class GwcAggregation(_Engine):
     """Eval branch of GwcDispProcessor: volume (B,64,D',H',W') -> disparity (B,H,W)."""
 
@@ -158,7 +196,17 @@ class GwcAggregation(_Engine):
         volume = self._check(volume)
         self._ensure(volume.device)
         width = volume.shape[-1]
-        if all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1])):
+        stem_tc = all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1]))
+        b, _, dd, hh, ww = volume.shape
+        if stem_tc and _tc_ok(self.classif3[0], width) and all(_hg_channels_last_ok(hg, (b, dd, hh, ww, 32)) for hg in self.hg):
+            # everything from the volume to the classifier runs channels-last on the tensor cores: ONE layout conversion
+            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)
+            out = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+            for hg in self.hg:
+                out = _gwc_hourglass_channels_last(hg, out)
+            head = _conv_tc(self.classif3[0], out, ACT_RELU, out_ndhwc=False)
+            return _conv(self.classif3[1], head)
+        if stem_tc:
             # full-resolution stem on the tensor cores: channels-last inside, NCDHW handed to the hourglasses
             c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)
             cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)

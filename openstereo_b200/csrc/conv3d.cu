@@ -378,6 +378,57 @@ __global__ void __launch_bounds__(256) conv3d_1x1_kernel(const ConvParams p) {
   }
 }
 
+// --------------------------------------------------------------------------------- channels-last 1x1x1 conv
+// x (V, Cin) -> y (V, Cout), y = act(x.W * scale + shift): the redir1/redir2 branches of the GwcNet hourglass
+// (gwcnet/hourglass.py:43-44, :53-54) when the aggregation runs channels-last for the tensor-core kernels.
+// One thread per voxel: its Cin inputs live in registers, the (Cin x Cout) weight matrix in shared memory (broadcast
+// reads); memory-bound (Cin + Cout floats per voxel).
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) conv1x1_ndhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            float* __restrict__ y, size_t V, int act) {
+  __shared__ __align__(16) float ws[CIN * COUT];
+  __shared__ float s_sc[COUT], s_sh[COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += 256) ws[i] = __ldg(w + i);          // packed (Cin, Cout)
+  for (int i = threadIdx.x; i < COUT; i += 256) {
+    s_sc[i] = scale ? __ldg(scale + i) : 1.f;
+    s_sh[i] = shift ? __ldg(shift + i) : 0.f;
+  }
+  __syncthreads();
+  const size_t v = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= V) return;
+  float xin[CIN];
+  const float4* xp = reinterpret_cast<const float4*>(x + v * CIN);
+#pragma unroll
+  for (int i = 0; i < CIN / 4; ++i) {
+    const float4 t = __ldg(xp + i);
+    xin[4 * i] = t.x, xin[4 * i + 1] = t.y, xin[4 * i + 2] = t.z, xin[4 * i + 3] = t.w;
+  }
+  float4* yp = reinterpret_cast<float4*>(y + v * COUT);
+#pragma unroll 1
+  for (int c0 = 0; c0 < COUT; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float4* wr = reinterpret_cast<const float4*>(ws + ci * COUT + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = wr[q];
+        acc[4 * q + 0] = fmaf(xin[ci], t.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xin[ci], t.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xin[ci], t.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xin[ci], t.w, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = activate(fmaf(acc[j], s_sc[c0 + j], s_sh[c0 + j]), act);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yp[c0 / 4 + q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------- launchers
 template <typename K>
 static int set_smem(K kernel, size_t bytes, const char* what) {
@@ -495,5 +546,24 @@ int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const 
   conv3d_1x1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   count_launch();
   return check_launch("conv3d_1x1_kernel");
+}
+
+int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* scale, const float* shift, float* y,
+                          long long voxels, int Cin, int Cout, int act, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x && w_packed && y, "conv1x1_ndhwc: null pointer");
+  OSB_REQUIRE(voxels > 0, "conv1x1_ndhwc: empty input");
+  OSB_REQUIRE(act >= 0 && act <= 2, "conv1x1_ndhwc: unknown activation %d", act);
+  OSB_REQUIRE(aligned16(x) && aligned16(y), "conv1x1_ndhwc: pointers must be 16-byte aligned");
+  const unsigned blocks = (unsigned)((voxels + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cin == 32 && Cout == 32) conv1x1_ndhwc_kernel<32, 32><<<blocks, 256, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
+  else if (Cin == 64 && Cout == 64) conv1x1_ndhwc_kernel<64, 64><<<blocks, 256, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
+  else {
+    set_error("conv1x1_ndhwc: unsupported channels %d -> %d (32->32 and 64->64 are instantiated)", Cin, Cout);
+    return OSB_EUNSUPPORTED;
+  }
+  count_launch();
+  return check_launch("conv1x1_ndhwc_kernel");
 }
 }

@@ -357,3 +357,14 @@ def deconv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=
     _call("osb_deconv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
     return y
+
+
+def conv1x1_ndhwc(x_ndhwc, w_packed, scale=None, shift=None, act=ACT_NONE):
+    """Channels-last 1x1x1 conv: x (..., Cin) -> (..., Cout); w_packed (Cin, Cout)."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous()
+    cin, cout = w_packed.shape
+    assert x_ndhwc.shape[-1] == cin
+    y = torch.empty(x_ndhwc.shape[:-1] + (cout,), dtype=torch.float32, device=x_ndhwc.device)
+    _call("osb_conv1x1_ndhwc_fwd", x_ndhwc.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(),
+          x_ndhwc.numel() // cin, cin, cout, act, _stream())
+    return y

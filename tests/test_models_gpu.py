@@ -216,6 +216,7 @@ def test_gwc_aggregation_full_width_tensor_cores(osb):
     eng = agg.GwcAggregation(m)
     assert agg.USE_TENSOR_CORES and eng._ensure(torch.device("cuda", 0)) is None and agg._tc_ok(eng.dres0[0], 128)
     assert agg._tc_ok(eng.hg[0].conv2, 64) and agg._tc_ok(eng.hg[0].conv4, 32)     # hourglass interiors too
+    assert agg._hg_channels_last_ok(eng.hg[0], (1, 8, 12, 128, 32))                 # ... with no layout change in between
     got_logits = eng.logits(vol.cuda())
     assert rel_err(got_logits, want_logits) <= 5e-5
     got = eng(vol.cuda(), 48, 512)

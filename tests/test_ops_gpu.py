@@ -256,6 +256,20 @@ def test_conv3d_1x1(ops):
     rel_close(got, F.leaky_relu(F.conv2d(f, wt)), 1e-5, "1x1 2d")
 
 
+def test_conv1x1_channels_last(ops):
+    import torch.nn.functional as F
+    for k, (c, v) in enumerate(((32, (2, 3, 5, 37)), (64, (1, 4, 3, 130)))):            # voxel counts not multiples of 256
+        x = rnd(48 + k, v[0], c, *v[1:])
+        wt = rnd(148 + k, c, c, 1, 1, 1, scale=0.2)
+        sc, sh = rnd(150 + k, c).abs() + 0.5, rnd(152 + k, c)
+        want = F.relu(F.conv3d(x, wt) * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
+        got = ops.conv1x1_ndhwc(dev(x.permute(0, 2, 3, 4, 1).contiguous()), dev(wt.view(c, c).t().contiguous()), dev(sc), dev(sh),
+                                ops.ACT_RELU)
+        rel_close(got, want.contiguous(), 1e-5, "1x1 channels-last C=%d" % c)
+    with pytest.raises(RuntimeError):
+        ops.conv1x1_ndhwc(dev(rnd(1, 4, 16)), dev(rnd(2, 16, 16)))
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core conv (3xTF32)
 def test_to_ndhwc(ops):
     x = rnd(50, 2, 40, 3, 5, 16)
