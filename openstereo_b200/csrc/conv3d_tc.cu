@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   uint64_t* acc_full = b_empty + 3;                 // [TILES]  MMA -> epilogue, one per accumulator tile
   uint64_t* acc_empty = acc_full + TC_TILES;        // [TILES]  epilogue -> MMA       (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_TILES);
-  float* xchg = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parities][4 warps][2][COUT] boundary exchange
+  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned
+  //   // [2 tile parities][4 warps][2][COUT] boundary exchange
   float* s_scale = xchg + 2 * 4 * 2 * COUT;                // [COUT]
   float* s_shift = s_scale + COUT;
   float* zeros = s_shift + COUT;                           // [COUT] of 0.f (image-edge neighbours)
+  float* tpose = zeros + COUT;                      // [4 warps][32][TP_STRIDE] transpose tiles of the epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / TC_KC;
@@ -312,8 +314,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           left = (lane == 0) ? xl[i] : left;          // m-1 lives in the previous quadrant (zero at the image edge)
           right = (lane == 31) ? xr[i] : right;       // m+1 lives in the next quadrant
           out[i] = (left + __uint_as_float(raw[1][i])) + right;
-          out[i] = fmaf(out[i], s_scale[i], s_shift[i]);
         }
+        if (p.out_ndhwc && (!p.residual || p.res_ndhwc)) {       // coalesced channels-last path (BN/residual/act inside)
+          static_assert(COUT == 32, "one 32-channel chunk per voxel");
+          store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT,
+                              p.residual ? p.residual + (vox - lane) * COUT : nullptr, COUT, s_scale, s_shift, p.act);
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < COUT; ++i) out[i] = fmaf(out[i], s_scale[i], s_shift[i]);
         if (p.residual) {
           if (p.res_ndhwc) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT);
@@ -417,7 +426,7 @@ template <int COUT>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   constexpr int N3 = 3 * COUT;
   const size_t smem = 1024 + 2 * (size_t)TC_STAGES * TC_ROW_BYTES + 3 * 2 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
-                      3 * COUT * 4;
+                      3 * COUT * 4 + TP_BYTES;
   auto kernel = conv3d_tc_kernel<COUT>;
   static bool configured = false;
   if (!configured) {

@@ -33,14 +33,15 @@ struct TcdcCfg {
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = 3 * COUT;
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (COUT >= 128) ? 3 : 4;   // the Cout = 128 weight slices leave room for 3
   static constexpr int HBLK = TILES * R;                    // output rows per work item
   static constexpr int KSTEPS = KC / 8;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
   static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
-  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4;
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
+  static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
   static_assert(TILES * N3 <= 512, "accumulators exceed TMEM");
   static_assert(B_SLICE % 1024 == 0 && UNIT_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
   static_assert(N3 % 16 == 0 && N3 <= 256, "invalid UMMA N");
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   float* s_scale = xchg + 2 * 4 * 2 * 32;
   float* s_shift = s_scale + COUT;
   float* zeros = s_shift + COUT;
+  float* tpose = zeros + COUT;                      // [4 warps][32][TP_STRIDE] transpose tiles of the epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
@@ -280,10 +282,22 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           for (int i = 0; i < 32; ++i) {
             float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
             right = (lane == 31) ? xr[i] : right;                                        // zero beyond the last input column
-            ev[i] = fmaf(__uint_as_float(raw[0][i]), s_scale[cg + i], s_shift[cg + i]);
-            od_[i] = fmaf(__uint_as_float(raw[1][i]) + right, s_scale[cg + i], s_shift[cg + i]);
+            ev[i] = __uint_as_float(raw[0][i]);
+            od_[i] = __uint_as_float(raw[1][i]) + right;
           }
-          if (live) {
+          if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
+            // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride
+            float* y0 = p.y + (vox - 2 * lane) * COUT + cg;
+            const float* r0 = p.residual ? p.residual + (vox - 2 * lane) * COUT + cg : nullptr;
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, ev, y0, r0, 2 * COUT, s_scale + cg, s_shift + cg, p.act);
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, od_, y0 + COUT, r0 ? r0 + COUT : nullptr, 2 * COUT, s_scale + cg,
+                                s_shift + cg, p.act);
+          } else if (live) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              ev[i] = fmaf(ev[i], s_scale[cg + i], s_shift[cg + i]);
+              od_[i] = fmaf(od_[i], s_scale[cg + i], s_shift[cg + i]);
+            }
             if (p.residual) {
               if (p.res_ndhwc) {
                 const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);

@@ -94,4 +94,55 @@ __device__ __forceinline__ int swz_offset(int row, int c) {
   else return row * 64 + ((c ^ ((row >> 1) & 3)) << 4);                        // SWIZZLE_64B
 }
 
+
+// ------------------------------------------------------------------------------- coalesced channels-last epilogue output
+// An epilogue thread owns ONE voxel and all of its channels.  Storing those directly makes every STG.128 of a warp touch
+// 32 different 128-byte lines (16 B of each) -- 8x the L1 wavefronts of a coalesced store, on the data pipe the tensor
+// core's operand reads also use (ncu r1_conv3d_tc_v7: tc 49 % + lsu 43 % of that pipe).  Instead the warp transposes its
+// 32 voxels x 32 channels through a private shared-memory tile so one instruction covers 4 voxels x 128 contiguous bytes;
+// folded BN, the channels-last residual and the activation are applied after the transpose, where a lane's four channels
+// are the same for every voxel (scale/shift sit in registers instead of one LDS per channel).
+constexpr int TP_STRIDE = 36;                       // floats per tile row: 144 B keeps STS.128 / LDS.128 conflict-free
+constexpr int TP_WARP_FLOATS = 32 * TP_STRIDE;      // 4608 B per epilogue warp
+constexpr int TP_BYTES = 4 * TP_WARP_FLOATS * 4;    // four epilogue warps
+
+// sum[32]: raw accumulator sums of this lane's voxel for channels [c, c+32).  y0 / res0 point at channel c of the voxel
+// owned by lane 0; lane k's voxel lies vstride floats further per lane.  sc / sh point at channel c of the folded BN.
+__device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const float (&sum)[32], float* y0, const float* res0,
+                                                    size_t vstride, const float* sc, const float* sh, int act) {
+  __syncwarp();                                     // the previous chunk's readers are done with the tile
+  float4* row = reinterpret_cast<float4*>(tbuf + lane * TP_STRIDE);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) row[i] = make_float4(sum[4 * i], sum[4 * i + 1], sum[4 * i + 2], sum[4 * i + 3]);
+  __syncwarp();
+  const int c4 = 4 * (lane & 7), sub = lane >> 3;
+  const float4 a = *reinterpret_cast<const float4*>(sc + c4);
+  const float4 b = *reinterpret_cast<const float4*>(sh + c4);
+  float4 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j] = *reinterpret_cast<const float4*>(tbuf + (4 * j + sub) * TP_STRIDE + c4);
+    o[j].x = fmaf(o[j].x, a.x, b.x), o[j].y = fmaf(o[j].y, a.y, b.y), o[j].z = fmaf(o[j].z, a.z, b.z), o[j].w = fmaf(o[j].w, a.w, b.w);
+  }
+  if (res0) {
+    float4 r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)(4 * j + sub) * vstride + c4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j].x += r[j].x, o[j].y += r[j].y, o[j].z += r[j].z, o[j].w += r[j].w;
+  }
+  if (act == OSB_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j].x = fmaxf(o[j].x, 0.f), o[j].y = fmaxf(o[j].y, 0.f), o[j].z = fmaxf(o[j].z, 0.f), o[j].w = fmaxf(o[j].w, 0.f);
+  } else if (act == OSB_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j].x = o[j].x > 0.f ? o[j].x : 0.01f * o[j].x, o[j].y = o[j].y > 0.f ? o[j].y : 0.01f * o[j].y;
+      o[j].z = o[j].z > 0.f ? o[j].z : 0.01f * o[j].z, o[j].w = o[j].w > 0.f ? o[j].w : 0.01f * o[j].w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(y0 + (size_t)(4 * j + sub) * vstride + c4) = o[j];
+}
+
 }  // namespace osb
