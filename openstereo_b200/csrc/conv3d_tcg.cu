@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
   uint8_t* a_lo = a_hi + C::STAGES * C::UNIT_BYTES;
   uint8_t* b_buf = smem + C::B_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
-  uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
+  uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
   uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
   uint64_t* b_full = a_empty + C::STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
   uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&a_ready[s], 128);
+      mbar_init(&a_ready[s], 32);                     // one loader warp fills a unit
       mbar_init(&a_empty[s], 1);
     }
     for (int k = 0; k < 3; ++k) {
@@ -179,11 +179,43 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
     }
   }
   // ---------------------------------------------------------------------------------------------- A-unit loaders
+  // One loader WARP per unit: warp lw fills ring slot lw (units with unitc % STAGES == lw), so STAGES units' global loads are
+  // in flight per SM and every slot is refilled in order by a single warp (no mbarrier phase can be skipped).  ncu
+  // (profiles/r1_ncu_summary.md, r1_tcdc_conv6): with all four warps on one unit at a time the loaders sat on the load
+  // latency and the tensor pipe was 17 % busy.  The (tile, tap) loops are runtime loops: one copy of the body (unrolled
+  // bodies took the kernel to 254 KB of code).
   else if (warp < 5) {
-    const int lt = threadIdx.x - 32;                 // 0..127
+    const int lw = warp - 1;
     constexpr int CPR = C::ROWB / 16;                // 16-byte chunks per operand row (8 or 4)
-    constexpr int NLD = 128 * CPR / 128;             // float4 loads per thread per unit (8 or 4)
+    constexpr int VPL = 32 / CPR;                    // voxels covered by one warp-wide LDG.128
+    constexpr int NLD = 128 / VPL;                   // loads per lane per unit
+    static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
+    const int v0 = lane / CPR, c = lane % CPR;
+    const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
+    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
+      // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
+      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column)
+      float4 v[NLD];
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int hin = h_first + h_step * ((VPL * j) / W);
+        const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
+        v[j] = (hin >= 0 && hin < p.H) ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const uint32_t ph = (u / C::STAGES) & 1;
+      mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
+      uint8_t* hi = a_hi + lw * C::UNIT_BYTES;
+      uint8_t* lo = a_lo + lw * C::UNIT_BYTES;
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int off = swz_offset<KC>(v0 + VPL * j, c);
+        *reinterpret_cast<float4*>(hi + off) = v[j];
+        *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_ready[lw]);
+    };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int hb = it % p.hblocks;
       const int d = (it / p.hblocks) % p.D;
@@ -194,32 +226,14 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
         if (din < 0 || din >= p.D) continue;
         const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)W * p.Cin;
         for (int ch = 0; ch < nchunk; ++ch) {
-#pragma unroll
+#pragma unroll 1
           for (int s = -1; s <= C::S_LAST; ++s) {
             if (!C::used(s)) continue;
-            float4 v[NLD];
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) {
-              const int f = lt + 128 * j;
-              const int vox = f / CPR, c = f % CPR;  // operand row (voxel of the unit) and 16-byte chunk
-              const int hin = h0 + s + vox / W, win = vox % W;
-              v[j] = (hin >= 0 && hin < p.H)
-                         ? __ldg(reinterpret_cast<const float4*>(plane + ((size_t)hin * W + win) * p.Cin + ch * KC + c * 4))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mine && unitc % C::STAGES == (uint32_t)lw) {
+              // unit = R consecutive image rows starting at h0 + s: operand row v is voxel (h0 + s) * W + v of the plane
+              const float* base = plane + ((ptrdiff_t)(h0 + s) * W + v0) * p.Cin + ch * KC + c * 4;
+              fill(base, (size_t)W * p.Cin, (size_t)p.Cin, h0 + s, 1, unitc);
             }
-            const uint32_t slot = unitc % C::STAGES, par = (unitc / C::STAGES) & 1;
-            mbar_wait_relaxed(&a_empty[slot], par ^ 1);
-            uint8_t* hi = a_hi + slot * C::UNIT_BYTES;
-            uint8_t* lo = a_lo + slot * C::UNIT_BYTES;
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) {
-              const int f = lt + 128 * j;
-              const int off = swz_offset<KC>(f / CPR, f % CPR);
-              *reinterpret_cast<float4*>(hi + off) = v[j];
-              *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
-            }
-            fence_proxy_async();
-            mbar_arrive(&a_ready[slot]);
             ++unitc;
           }
         }
