@@ -162,6 +162,11 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const flo
  * x (voxels, Cin) -> y (voxels, Cout); w_packed (Cin, Cout).  32->32 and 64->64. */
 int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* scale, const float* shift, float* y,
                           long long voxels, int Cin, int Cout, int act, osb_stream_t stream);
+/* Classifier head Conv3d(Cin, 1, 3, 1, 1) (gwcnet_disp_processor.py:60-70 classif*[2]) on a channels-last input:
+ * x (B,D,H,W,Cin) -> y (B,1,D,H,W) = (B,D,H,W); w_taps (27, Cin) tap-major [kd][kh][kw][ci]; scale/shift: optional 1-element
+ * arrays (folded BN / bias).  Cin = 32. */
+int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const float* scale, const float* shift, float* y, int B,
+                               int Cin, int D, int H, int W, osb_stream_t stream);
 /* (B,C,D,H,W) -> (B,D,H,W,C) layout change feeding the tensor-core conv. */
 int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream);
 

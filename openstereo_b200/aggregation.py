@@ -204,8 +204,14 @@ class GwcAggregation(_Engine):
             out = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
             for hg in self.hg:
                 out = _gwc_hourglass_channels_last(hg, out)
+            cls = self.classif3[1]
+            if cls.cin == 32 and cls.cout == 1 and cls._w5 is not None and cls.stride == 1:
+                if "c1" not in cls._tc:
+                    cls._tc["c1"] = ops.pack_c1_weight(cls._w5)
+                head = _conv_tc(self.classif3[0], out, ACT_RELU)           # stays channels-last for the 1-channel head
+                return ops.conv3d_k3_c1_ndhwc(head, cls._tc["c1"], cls.scale, cls.shift)
             head = _conv_tc(self.classif3[0], out, ACT_RELU, out_ndhwc=False)
-            return _conv(self.classif3[1], head)
+            return _conv(cls, head)
         if stem_tc:
             # full-resolution stem on the tensor cores: channels-last inside, NCDHW handed to the hourglasses
             c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)

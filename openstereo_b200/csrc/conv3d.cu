@@ -15,6 +15,8 @@
 // (~22 FMA per shared-memory load instruction), so the kernel is bound by the fp32 FMA pipe, not by LDS or HBM.
 // BatchNorm (eval) is folded into a per-channel scale/shift epilogue together with the residual add, the activation
 // and StereoBase's sigmoid channel gate, so no elementwise pass ever touches HBM.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace osb {
@@ -381,51 +383,139 @@ __global__ void __launch_bounds__(256) conv3d_1x1_kernel(const ConvParams p) {
 // --------------------------------------------------------------------------------- channels-last 1x1x1 conv
 // x (V, Cin) -> y (V, Cout), y = act(x.W * scale + shift): the redir1/redir2 branches of the GwcNet hourglass
 // (gwcnet/hourglass.py:43-44, :53-54) when the aggregation runs channels-last for the tensor-core kernels.
-// One thread per voxel: its Cin inputs live in registers, the (Cin x Cout) weight matrix in shared memory (broadcast
-// reads); memory-bound (Cin + Cout floats per voxel).
+// A warp owns 32 consecutive voxels: it reads their 32 x Cin block with fully coalesced LDG.128 (a thread-per-voxel read
+// touches 32 different lines per instruction), transposes it through a private shared-memory tile so that each lane then
+// holds one voxel's Cin inputs in registers, multiplies by the (Cin x Cout) matrix broadcast from shared memory, and writes
+// the result back through the same tile, again coalesced.  Memory-bound: Cin + Cout floats per voxel.
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) conv1x1_ndhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                            const float* __restrict__ scale, const float* __restrict__ shift,
-                                                            float* __restrict__ y, size_t V, int act) {
+__global__ void __launch_bounds__(64) conv1x1_ndhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           float* __restrict__ y, size_t V, int act) {
+  static_assert(CIN == COUT, "the in/out tiles share one buffer");
+  constexpr int TS = CIN + 4;                       // tile row stride (floats): 16-byte aligned, conflict-free per quarter warp
+  constexpr int F4 = CIN / 4;                       // float4 per voxel
   __shared__ __align__(16) float ws[CIN * COUT];
-  __shared__ float s_sc[COUT], s_sh[COUT];
-  for (int i = threadIdx.x; i < CIN * COUT; i += 256) ws[i] = __ldg(w + i);          // packed (Cin, Cout)
-  for (int i = threadIdx.x; i < COUT; i += 256) {
+  __shared__ __align__(16) float tile[2][32 * TS];
+  __shared__ __align__(16) float s_sc[COUT];
+  __shared__ __align__(16) float s_sh[COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += 64) ws[i] = __ldg(w + i);           // packed (Cin, Cout)
+  for (int i = threadIdx.x; i < COUT; i += 64) {
     s_sc[i] = scale ? __ldg(scale + i) : 1.f;
     s_sh[i] = shift ? __ldg(shift + i) : 0.f;
   }
   __syncthreads();
-  const size_t v = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (v >= V) return;
-  float xin[CIN];
-  const float4* xp = reinterpret_cast<const float4*>(x + v * CIN);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tl = tile[warp];
+  const size_t ngroups = (V + 31) / 32;
+  for (size_t g = (size_t)blockIdx.x * 2 + warp; g < ngroups; g += (size_t)gridDim.x * 2) {
+    const size_t v0 = g * 32;
+    const int nv = (int)min((size_t)32, V - v0);
+    const float4* src = reinterpret_cast<const float4*>(x + v0 * CIN);
+    __syncwarp();
 #pragma unroll
-  for (int i = 0; i < CIN / 4; ++i) {
-    const float4 t = __ldg(xp + i);
-    xin[4 * i] = t.x, xin[4 * i + 1] = t.y, xin[4 * i + 2] = t.z, xin[4 * i + 3] = t.w;
-  }
-  float4* yp = reinterpret_cast<float4*>(y + v * COUT);
-#pragma unroll 1
-  for (int c0 = 0; c0 < COUT; c0 += 16) {
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-      const float4* wr = reinterpret_cast<const float4*>(ws + ci * COUT + c0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = wr[q];
-        acc[4 * q + 0] = fmaf(xin[ci], t.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(xin[ci], t.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(xin[ci], t.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(xin[ci], t.w, acc[4 * q + 3]);
-      }
+    for (int j = 0; j < F4; ++j) {                  // coalesced: 512 contiguous bytes per instruction
+      const int f = lane + 32 * j, vox = f / F4, ch = f % F4;
+      const float4 t = (vox < nv) ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(tl + vox * TS + 4 * ch) = t;
     }
+    __syncwarp();
+    float xin[CIN];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = activate(fmaf(acc[j], s_sc[c0 + j], s_sh[c0 + j]), act);
+    for (int i = 0; i < F4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(tl + lane * TS + 4 * i);
+      xin[4 * i] = t.x, xin[4 * i + 1] = t.y, xin[4 * i + 2] = t.z, xin[4 * i + 3] = t.w;
+    }
+    __syncwarp();                                   // everyone has its row: the tile can take the outputs
+#pragma unroll 1
+    for (int c0 = 0; c0 < COUT; c0 += 16) {
+      float acc[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) yp[c0 / 4 + q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ci * COUT + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = wr[q];
+          acc[4 * q + 0] = fmaf(xin[ci], t.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xin[ci], t.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xin[ci], t.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xin[ci], t.w, acc[4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = activate(fmaf(acc[j], s_sc[c0 + j], s_sh[c0 + j]), act);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(tl + lane * TS + c0 + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(y + v0 * COUT);
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      const int f = lane + 32 * j, vox = f / F4, ch = f % F4;
+      if (vox < nv) dst[f] = *reinterpret_cast<const float4*>(tl + vox * TS + 4 * ch);
+    }
+  }
+}
+
+// --------------------------------------------------------------------- channels-last 3x3x3 conv to ONE output channel
+// The classifier head `classif*[2]` = Conv3d(32, 1, 3, 1, 1, bias=False) (gwcnet_disp_processor.py:60-70,
+// psmnet_cost_processor.py:106-124) on a channels-last input: with one output channel there is no GEMM N dimension to
+// feed the tensor cores, and the NCDHW CUDA-core kernel spends its time on 8-channel register tiles that are 7/8 empty.
+// Here a CTA stages a (2+2) x (4+2) x (32+2) voxel halo with all 32 channels (coalesced 128-byte voxel rows, 144-byte
+// padded in shared memory so LDS.128 is conflict-free) and each thread forms one output voxel's 27 x 32 dot product.
+constexpr int C1_TD = 2, C1_TH = 4, C1_TW = 32;
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3d_k3_c1_ndhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 float* __restrict__ y, int D, int H, int W, int tiles_w, int tiles_h,
+                                                                 int tiles_d) {
+  constexpr int HD = C1_TD + 2, HH = C1_TH + 2, HW = C1_TW + 2, VS = CIN + 4, F4 = CIN / 4;
+  extern __shared__ __align__(16) float c1_smem[];
+  float* xs = c1_smem;                              // [HD][HH][HW][VS]
+  float* ws = xs + HD * HH * HW * VS;               // [27][CIN]
+  int bid = blockIdx.x;
+  const int tw0 = (bid % tiles_w) * C1_TW;
+  bid /= tiles_w;
+  const int th0 = (bid % tiles_h) * C1_TH;
+  bid /= tiles_h;
+  const int td0 = (bid % tiles_d) * C1_TD;
+  const int b = bid / tiles_d;
+  for (int i = threadIdx.x; i < 27 * CIN; i += 256) ws[i] = __ldg(w + i);
+  const float* xb = x + (size_t)b * D * H * W * CIN;
+  for (int i = threadIdx.x; i < HD * HH * HW * F4; i += 256) {
+    const int ch = i % F4, vox = i / F4;
+    const int wx = vox % HW, hy = (vox / HW) % HH, dz = vox / (HW * HH);
+    const int d = td0 - 1 + dz, h = th0 - 1 + hy, ww = tw0 - 1 + wx;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d >= 0 && d < D && h >= 0 && h < H && ww >= 0 && ww < W)
+      t = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)d * H + h) * W + ww) * CIN) + ch);
+    *reinterpret_cast<float4*>(xs + vox * VS + 4 * ch) = t;
+  }
+  __syncthreads();
+  const int tw = threadIdx.x % C1_TW, th = (threadIdx.x / C1_TW) % C1_TH, td = threadIdx.x / (C1_TW * C1_TH);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float* xp = xs + (((td + kd) * HH + th + kh) * HW + tw + kw) * VS;
+        const float* wp = ws + ((kd * 3 + kh) * 3 + kw) * CIN;
+#pragma unroll
+        for (int q = 0; q < F4; ++q) {
+          const float4 xv = *reinterpret_cast<const float4*>(xp + 4 * q);
+          const float4 wv = *reinterpret_cast<const float4*>(wp + 4 * q);
+          a0 = fmaf(xv.x, wv.x, a0), a1 = fmaf(xv.y, wv.y, a1), a2 = fmaf(xv.z, wv.z, a2), a3 = fmaf(xv.w, wv.w, a3);
+        }
+      }
+  const int d = td0 + td, h = th0 + th, ww = tw0 + tw;
+  if (d < D && h < H && ww < W) {
+    float r = (a0 + a1) + (a2 + a3);
+    r = fmaf(r, scale ? __ldg(scale) : 1.f, shift ? __ldg(shift) : 0.f);
+    y[(((size_t)b * D + d) * H + h) * W + ww] = r;
   }
 }
 
@@ -555,15 +645,45 @@ int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* sc
   OSB_REQUIRE(voxels > 0, "conv1x1_ndhwc: empty input");
   OSB_REQUIRE(act >= 0 && act <= 2, "conv1x1_ndhwc: unknown activation %d", act);
   OSB_REQUIRE(aligned16(x) && aligned16(y), "conv1x1_ndhwc: pointers must be 16-byte aligned");
-  const unsigned blocks = (unsigned)((voxels + 255) / 256);
+  const long long groups = (voxels + 31) / 32;
+  const unsigned blocks = (unsigned)std::min<long long>((groups + 1) / 2, 148ll * 16);   // 2 warps per CTA, grid-stride over 32-voxel groups
   cudaStream_t s = (cudaStream_t)stream;
-  if (Cin == 32 && Cout == 32) conv1x1_ndhwc_kernel<32, 32><<<blocks, 256, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
-  else if (Cin == 64 && Cout == 64) conv1x1_ndhwc_kernel<64, 64><<<blocks, 256, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
+  if (Cin == 32 && Cout == 32) conv1x1_ndhwc_kernel<32, 32><<<blocks, 64, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
+  else if (Cin == 64 && Cout == 64) conv1x1_ndhwc_kernel<64, 64><<<blocks, 64, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
   else {
     set_error("conv1x1_ndhwc: unsupported channels %d -> %d (32->32 and 64->64 are instantiated)", Cin, Cout);
     return OSB_EUNSUPPORTED;
   }
   count_launch();
   return check_launch("conv1x1_ndhwc_kernel");
+}
+
+int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const float* scale, const float* shift, float* y, int B,
+                               int Cin, int D, int H, int W, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x_ndhwc && w_taps && y, "conv3d_k3_c1_ndhwc: null pointer");
+  OSB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_k3_c1_ndhwc: empty shape");
+  OSB_REQUIRE(aligned16(x_ndhwc) && aligned16(w_taps), "conv3d_k3_c1_ndhwc: pointers must be 16-byte aligned");
+  if (Cin != 32) {
+    set_error("conv3d_k3_c1_ndhwc: Cin = %d unsupported (32 is instantiated)", Cin);
+    return OSB_EUNSUPPORTED;
+  }
+  const int tiles_w = (W + C1_TW - 1) / C1_TW, tiles_h = (H + C1_TH - 1) / C1_TH, tiles_d = (D + C1_TD - 1) / C1_TD;
+  const long long blocks = (long long)B * tiles_d * tiles_h * tiles_w;
+  OSB_REQUIRE(blocks < (1ll << 31), "conv3d_k3_c1_ndhwc: too many tiles");
+  constexpr size_t smem = ((size_t)(C1_TD + 2) * (C1_TH + 2) * (C1_TW + 2) * (32 + 4) + 27 * 32) * sizeof(float);
+  auto kernel = conv3d_k3_c1_ndhwc_kernel<32>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv3d_k3_c1_ndhwc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return OSB_ECUDA;
+    }
+    configured = true;
+  }
+  kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(x_ndhwc, w_taps, scale, shift, y, D, H, W, tiles_w, tiles_h, tiles_d);
+  count_launch();
+  return check_launch("conv3d_k3_c1_ndhwc_kernel");
 }
 }

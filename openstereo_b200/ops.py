@@ -368,3 +368,20 @@ def conv1x1_ndhwc(x_ndhwc, w_packed, scale=None, shift=None, act=ACT_NONE):
     _call("osb_conv1x1_ndhwc_fwd", x_ndhwc.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(),
           x_ndhwc.numel() // cin, cin, cout, act, _stream())
     return y
+
+
+def pack_c1_weight(weight):
+    """(1, Cin, 3, 3, 3) Conv3d parameter -> (27, Cin) tap-major fp32 for conv3d_k3_c1_ndhwc."""
+    assert weight.dim() == 5 and weight.shape[0] == 1 and tuple(weight.shape[2:]) == (3, 3, 3)
+    return weight.detach().float()[0].permute(1, 2, 3, 0).reshape(27, -1).contiguous()
+
+
+def conv3d_k3_c1_ndhwc(x_ndhwc, w_taps, scale=None, shift=None):
+    """Single-output-channel 3x3x3 conv (classifier head) on a channels-last volume: (B,D,H,W,Cin) -> (B,1,D,H,W)."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    assert w_taps.shape == (27, cin) and w_taps.is_contiguous()
+    y = torch.empty((b, 1, d, h, w), dtype=torch.float32, device=x_ndhwc.device)
+    _call("osb_conv3d_k3_c1_ndhwc_fwd", x_ndhwc.data_ptr(), w_taps.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(), b, cin, d, h, w,
+          _stream())
+    return y

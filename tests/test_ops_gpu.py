@@ -270,6 +270,22 @@ def test_conv1x1_channels_last(ops):
         ops.conv1x1_ndhwc(dev(rnd(1, 4, 16)), dev(rnd(2, 16, 16)))
 
 
+def test_conv3d_head_channels_last(ops):
+    """Conv3d(32, 1, 3, 1, 1) classifier head on a channels-last input, ragged sizes (partial tiles in D, H and W)."""
+    import torch.nn.functional as F
+    for k, shape in enumerate(((2, 32, 5, 7, 45), (1, 32, 2, 4, 32), (1, 32, 3, 9, 130))):
+        x = rnd(160 + k, *shape)
+        wt = rnd(170 + k, 1, 32, 3, 3, 3, scale=0.1)
+        want = F.conv3d(x, wt, padding=1)
+        got = ops.conv3d_k3_c1_ndhwc(dev(x.permute(0, 2, 3, 4, 1).contiguous()), dev(ops.pack_c1_weight(wt)))
+        rel_close(got, want, 1e-5, "head conv %s" % (shape,))
+    sc, sh = torch.tensor([1.7]), torch.tensor([-0.3])
+    got = ops.conv3d_k3_c1_ndhwc(dev(x.permute(0, 2, 3, 4, 1).contiguous()), dev(ops.pack_c1_weight(wt)), dev(sc), dev(sh))
+    rel_close(got, want * 1.7 - 0.3, 1e-5, "head conv scale/shift")
+    with pytest.raises(RuntimeError):
+        ops.conv3d_k3_c1_ndhwc(dev(rnd(1, 1, 2, 2, 4, 16)), dev(rnd(2, 27, 16)))
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core conv (3xTF32)
 def test_to_ndhwc(ops):
     x = rnd(50, 2, 40, 3, 5, 16)
