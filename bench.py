@@ -325,7 +325,11 @@ def run_ours(args):
         roofline = {"kernel": "volume_kernel (gwc+concat fused, osb_gwc_concat_volume_fwd)", "bound": "hbm",
                     "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
                     "frac_of_8TBs_nominal": round(ach / 8000.0, 4), "peak_source": peak_src,
-                    "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4), "traffic": None,
+                    "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4),
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture of the same
+                    # command (profiles/r1_ncu_summary_final.md, r1_volume_final): 174.2 MB read (= the algorithmic input)
+                    # + 745.8 MB written (the rest of the 805.3 MB output is still dirty in the 126 MB L2 at kernel end)
+                    "traffic": 919946496 if B == 8 else None,
                     "share_of_step": round(vol_total / ms, 4)}
     # ---- 3D aggregation: MACs per pair of GwcNet-gc at D'=48, H'=64, W'=128
     vox = 48 * 64 * 128
@@ -365,7 +369,10 @@ def run_ours(args):
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense tf32 rate); achieved counts the 3 MMAs "
                                    "issued per fp32-accurate product",
                     "alg_flops_per_step": 2 * sum(macs[n] for n in tc_names) * B, "share_of_step": round(tc_total / ms, 4),
-                    "per_kernel": per, "traffic": None}
+                    "per_kernel": per,
+                    # conv3d_tc_kernel<32> (32->32 stem layer), ncu --set full: 403.2 MB read + 362.8 MB written per launch =
+                    # its algorithmic 402.7 + 402.7 MB (profiles/r1_ncu_summary_final.md, r1_conv3d_tc_final)
+                    "traffic": 765931264 if B == 8 else None}
     cc_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd", "osb_conv1x1_ndhwc_fwd"]
     cc_total = sum(kernel_stats(n)[2] for n in cc_names)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                 # derived: SMs x fp32 lanes x 2 x max clock
