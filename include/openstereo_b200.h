@@ -167,6 +167,24 @@ int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* sc
  * arrays (folded BN / bias).  Cin = 32. */
 int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const float* scale, const float* shift, float* y, int B,
                                int Cin, int D, int H, int W, osb_stream_t stream);
+/* ---- GRU-iteration lookups of IGEV / StereoBase ------------------------------------
+ * Pair-average along the middle axis of a (outer, n, inner) array -> (outer, n/2, inner): the F.avg_pool2d(.., [1,2],
+ * stride=[1,2]) pyramid of Combined_Geo_Encoding_Volume.__init__ (igev/geometry.py:24-30, stereobase/gru_blocks.py:187-193)
+ * on the volume's native (B,C,D,H,W) layout (outer=B*C, n=D, inner=H*W) and on the all-pairs correlation
+ * (outer=B*H*W1, n=W2, inner=1). */
+int osb_avgpool_pairs_fwd(const float* x, float* y, long long outer, int n, long long inner, osb_stream_t stream);
+/* Combined_Geo_Encoding_Volume.__call__ (igev/geometry.py:32-57) == CombinedGeoEncodingVolume.__call__
+ * (stereobase/gru_blocks.py:195-220): per pyramid level i < num_levels, 2*radius+1 zero-padded bilinear taps of
+ *   geo_i (B, C, D>>i, H, W) at d = disp/2^i + dx            -> channels [i*(C+1)*T + c*T + k]
+ *   corr_i (B, H, W, W2>>i) at x = coords/2^i - disp/2^i + dx -> channels [i*(C+1)*T + C*T + k],   T = 2*radius+1
+ * disp (B,1,H,W), coords (B,H,W), out (B, num_levels*(C+1)*T, H, W).  Unused level pointers are NULL. */
+int osb_geo_lookup_fwd(const float* geo0, const float* geo1, const float* geo2, const float* geo3, const float* corr0,
+                       const float* corr1, const float* corr2, const float* corr3, const float* disp, const float* coords,
+                       float* out, int B, int C, int D, int H, int W, int W2, int num_levels, int radius, osb_stream_t stream);
+/* context_upsample (stereobase/igev_blocks.py:51-63, igev/submodule.py:253-265): disp_low (B,1,h,w), up_weights
+ * (B,9,scale*h,scale*w) -> out (B, scale*h, scale*w) = sum over the 3x3 low-resolution neighbourhood (zero padded). */
+int osb_context_upsample_fwd(const float* disp_low, const float* up_weights, float* out, int B, int h, int w, int scale,
+                             osb_stream_t stream);
 /* (B,C,D,H,W) -> (B,D,H,W,C) layout change feeding the tensor-core conv. */
 int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream);
 

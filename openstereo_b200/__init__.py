@@ -6,9 +6,9 @@ RAISES if it is missing or lacks a symbol -- there is no PyTorch/CPU fallback fo
 """
 import importlib
 
-_SUBMODULES = ("_lib", "ops", "aggregation", "host_models", "patch", "distributed", "build")
+_SUBMODULES = ("_lib", "ops", "aggregation", "host_models", "patch", "distributed", "geo", "build")
 
-__all__ = ["ops", "aggregation", "host_models", "patch", "distributed"]
+__all__ = ["ops", "aggregation", "host_models", "patch", "distributed", "geo"]
 
 
 def __getattr__(name):

@@ -385,3 +385,50 @@ def conv3d_k3_c1_ndhwc(x_ndhwc, w_taps, scale=None, shift=None):
     _call("osb_conv3d_k3_c1_ndhwc_fwd", x_ndhwc.data_ptr(), w_taps.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(), b, cin, d, h, w,
           _stream())
     return y
+
+
+# ------------------------------------------------------------------ GRU-iteration lookups
+def avgpool_pairs(x, axis):
+    """Average adjacent pairs along `axis` (a trailing odd element is dropped) == F.avg_pool2d(.., [1, 2], stride=[1, 2])
+    applied along that axis (igev/geometry.py:24-30)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    axis = axis % x.dim()
+    n = x.shape[axis]
+    outer = int(torch.tensor(x.shape[:axis]).prod()) if axis > 0 else 1
+    inner = int(torch.tensor(x.shape[axis + 1:]).prod()) if axis + 1 < x.dim() else 1
+    y = torch.empty(x.shape[:axis] + (n // 2,) + x.shape[axis + 1:], dtype=torch.float32, device=x.device)
+    _call("osb_avgpool_pairs_fwd", x.data_ptr(), y.data_ptr(), outer, n, inner, _stream())
+    return y
+
+
+def geo_lookup(geo_levels, corr_levels, disp, coords, radius):
+    """One lookup of the combined geometry-encoding volume (igev/geometry.py:32-57): geo_levels[i] (B,C,D>>i,H,W),
+    corr_levels[i] (B,H,W,W2>>i), disp (B,1,H,W), coords (B,H,W[,1]) -> (B, L*(C+1)*(2r+1), H, W)."""
+    levels = len(geo_levels)
+    assert levels == len(corr_levels) and 1 <= levels <= 4
+    b, c, d, h, w = geo_levels[0].shape
+    w2 = corr_levels[0].shape[-1]
+    for i in range(levels):
+        g, cr = geo_levels[i], corr_levels[i]
+        assert g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (b, c, d >> i, h, w)
+        assert cr.is_cuda and cr.dtype == torch.float32 and cr.is_contiguous() and tuple(cr.shape) == (b, h, w, w2 >> i)
+    disp = disp.contiguous().float()
+    coords = coords.reshape(b, h, w).contiguous().float()
+    assert tuple(disp.shape) == (b, 1, h, w)
+    out = torch.empty((b, levels * (c + 1) * (2 * radius + 1), h, w), dtype=torch.float32, device=disp.device)
+    gp = [geo_levels[i].data_ptr() if i < levels else None for i in range(4)]
+    cp = [corr_levels[i].data_ptr() if i < levels else None for i in range(4)]
+    _call("osb_geo_lookup_fwd", *gp, *cp, disp.data_ptr(), coords.data_ptr(), out.data_ptr(), b, c, d, h, w, w2, levels, radius,
+          _stream())
+    return out
+
+
+def context_upsample(disp_low, up_weights, scale_factor=4):
+    """stereobase/igev_blocks.py:51-63: disp_low (B,1,h,w), up_weights (B,9,s*h,s*w) -> (B, s*h, s*w)."""
+    assert disp_low.is_cuda and disp_low.dim() == 4 and disp_low.shape[1] == 1
+    b, _, h, w = disp_low.shape
+    assert tuple(up_weights.shape) == (b, 9, h * scale_factor, w * scale_factor)
+    disp_low, up_weights = disp_low.contiguous().float(), up_weights.contiguous().float()
+    out = torch.empty((b, h * scale_factor, w * scale_factor), dtype=torch.float32, device=disp_low.device)
+    _call("osb_context_upsample_fwd", disp_low.data_ptr(), up_weights.data_ptr(), out.data_ptr(), b, h, w, scale_factor, _stream())
+    return out

@@ -25,6 +25,7 @@ import torch
 
 from . import ops
 from .aggregation import GwcAggregation, PSMAggregation, StereoBaseAggregation, StereoBaseCostHead
+from .geo import CombinedGeoEncodingVolume
 
 
 def _accelerable(module, *tensors):
@@ -116,6 +117,20 @@ def _patch_stereobase(model, strict):
         return ops.disparity_regression(x, maxdisp) if x.is_cuda else originals["disparity_regression"](x, maxdisp)
 
     mod.build_gwc_volume, mod.build_concat_volume, mod.disparity_regression = gwc, concat, regression
+
+    # the per-GRU-iteration lookup and the convex up-sampling (stereobase_gru.py:172-209)
+    geo_orig, up_orig = mod.CombinedGeoEncodingVolume, mod.context_upsample
+
+    def geo_factory(fmap1, fmap2, volume, num_levels=2, radius=4):
+        cls = CombinedGeoEncodingVolume if volume.is_cuda else geo_orig
+        return cls(fmap1, fmap2, volume, num_levels=num_levels, radius=radius)
+
+    def upsample(disp_low, up_weights, scale_factor=4):
+        if disp_low.is_cuda:
+            return ops.context_upsample(disp_low, up_weights, scale_factor).to(disp_low.dtype)
+        return up_orig(disp_low, up_weights, scale_factor)
+
+    mod.CombinedGeoEncodingVolume, mod.context_upsample = geo_factory, upsample
 
     def hg_forward(self, x, features, return_multi=False):
         if return_multi or not _accelerable(self, x):

@@ -5,6 +5,7 @@ import torch
 
 from oracle import aggregation as oagg
 from oracle import cost_volume as ocv
+from oracle import geo_lookup as ogeo
 from oracle import models as omodels
 from oracle import regression as oreg
 from oracle import seeded_init as si
@@ -112,3 +113,18 @@ def test_psmnet_model():
     with torch.no_grad():
         out = m({"left": g["left"], "right": g["right"]})["disp_pred"]
     assert torch.equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", ["geo_lookup_small", "geo_lookup_3lvl"])
+def test_geo_lookup(name):
+    """the oracle reproduces the reference's lookup output and pyramid bit for bit."""
+    g = load_golden(name)
+    vol = ogeo.GeoEncodingVolume(g["fmap1"], g["fmap2"], g["volume"], num_levels=g["levels"], radius=g["radius"])
+    assert torch.equal(vol(g["disp"], g["coords"]), g["out"])
+    assert torch.equal(vol.geo_pyramid[-1], g["geo_last"]) and torch.equal(vol.corr_pyramid[-1], g["corr_last"])
+    assert g["out"].shape[1] == g["levels"] * (g["volume"].shape[1] + 1) * (2 * g["radius"] + 1)
+
+
+def test_context_upsample():
+    g = load_golden("context_upsample")
+    assert torch.equal(ogeo.context_upsample(g["disp_low"], g["up_weights"], g["scale"]), g["out"])

@@ -6,6 +6,7 @@ import torch
 from oracle import _reference_shim as shim
 from oracle import aggregation as oagg
 from oracle import cost_volume as ocv
+from oracle import geo_lookup as ogeo
 from oracle import regression as oreg
 from oracle import seeded_init as si
 
@@ -51,3 +52,21 @@ def test_hourglass_modules():
         pre, post = rnd(8, 1, 16, 2, 4, 4), rnd(9, 1, 16, 2, 4, 4)
         for a, b in zip(ref(x, pre, post), mine(x, pre, post)):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("b,cf,cg,d,h,w,levels,radius", [(1, 5, 8, 24, 4, 30, 2, 4), (2, 3, 2, 9, 2, 11, 1, 3)])
+def test_geo_lookup_classes(b, cf, cg, d, h, w, levels, radius):
+    rgeo = shim.load("stereo.modeling.models.igev.geometry")
+    rsb = shim.load("stereo.modeling.models.stereobase.gru_blocks")
+    f1, f2, vol = rnd(70, b, cf, h, w), rnd(71, b, cf, h, w), rnd(72, b, cg, d, h, w)
+    disp = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(73)) * (d + 4) - 2
+    coords = torch.arange(w).float().reshape(1, 1, w, 1).repeat(b, h, 1, 1)
+    mine = ogeo.GeoEncodingVolume(f1, f2, vol, num_levels=levels, radius=radius)(disp, coords)
+    for cls in (rgeo.Combined_Geo_Encoding_Volume, rsb.CombinedGeoEncodingVolume):
+        assert torch.equal(cls(f1, f2, vol, num_levels=levels, radius=radius)(disp, coords), mine)
+
+
+def test_context_upsample_function():
+    rblk = shim.load("stereo.modeling.models.stereobase.igev_blocks")
+    low, wts = rnd(74, 2, 1, 6, 9).abs() * 30, torch.softmax(rnd(75, 2, 9, 24, 36), dim=1)
+    assert torch.equal(rblk.context_upsample(low, wts), ogeo.context_upsample(low, wts))

@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 from oracle import _reference_shim as shim                      # noqa: E402
 from oracle import aggregation as oagg                          # noqa: E402
 from oracle import cost_volume as ocv                           # noqa: E402
+from oracle import geo_lookup as ogeo                           # noqa: E402
 from oracle import models as omodels                            # noqa: E402
 from oracle import regression as oreg                           # noqa: E402
 from oracle import seeded_init as si                            # noqa: E402
@@ -218,6 +219,37 @@ def models():
              sd_checksum=checksum(sd))
 
 
+def lookups():
+    """geometry-encoding volume lookup and context up-sampling."""
+    rgeo = shim.load("stereo.modeling.models.igev.geometry")
+    rsb = shim.load("stereo.modeling.models.stereobase.gru_blocks")
+    rblk = shim.load("stereo.modeling.models.stereobase.igev_blocks")
+    # (name, B, C_feat, C_geo, D, H, W, levels, radius)
+    for name, b, cf, cg, d, h, w, levels, radius in (("geo_lookup_small", 2, 6, 8, 12, 3, 10, 2, 4),
+                                                     ("geo_lookup_3lvl", 1, 4, 3, 17, 2, 21, 3, 2)):
+        f1, f2 = rnd(60, b, cf, h, w), rnd(61, b, cf, h, w)
+        vol = rnd(62, b, cg, d, h, w)
+        # disparities inside, at the borders of and beyond the volume; two iterations like the GRU loop
+        disp = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(63)) * (d + 6) - 3
+        disp[0, 0, 0, :3] = torch.tensor([0.0, d - 1.0, 2.5])
+        coords = torch.arange(w).float().reshape(1, 1, w, 1).repeat(b, h, 1, 1)
+        ref = rgeo.Combined_Geo_Encoding_Volume(f1, f2, vol, num_levels=levels, radius=radius)
+        ref2 = rsb.CombinedGeoEncodingVolume(f1, f2, vol, num_levels=levels, radius=radius)
+        mine = ogeo.GeoEncodingVolume(f1, f2, vol, num_levels=levels, radius=radius)
+        out = ref(disp, coords)
+        must_equal(out, ref2(disp, coords), name + " igev vs stereobase class")
+        must_equal(out, mine(disp, coords), name)
+        must_equal(ref.init_corr_pyramid[-1], mine.corr_pyramid[-1], name + " corr pyramid")
+        must_equal(ref.geo_volume_pyramid[-1], mine.geo_pyramid[-1], name + " geo pyramid")
+        save(name, fmap1=f1, fmap2=f2, volume=vol, disp=disp, coords=coords, levels=levels, radius=radius, out=out,
+             geo_last=ref.geo_volume_pyramid[-1], corr_last=ref.init_corr_pyramid[-1])
+    low = rnd(64, 2, 1, 5, 7).abs() * 20
+    wts = torch.softmax(rnd(65, 2, 9, 20, 28), dim=1)
+    ref = rblk.context_upsample(low, wts)
+    must_equal(ref, ogeo.context_upsample(low, wts), "context_upsample")
+    save("context_upsample", disp_low=low, up_weights=wts, scale=4, out=ref)
+
+
 if __name__ == "__main__":
     if not shim.available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the authoring container")
@@ -226,4 +258,5 @@ if __name__ == "__main__":
     regression()
     modules()
     models()
+    lookups()
     print("all oracle restatements bit-equal to the reference; golden vectors written to", OUT)
