@@ -459,7 +459,9 @@ extern "C" {
 int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (stride != 1) return 0;
   if (W == osb::TC_W && Cout == 32 && Cin % 32 == 0 && Cin >= 32) return 32;                 // conv3d_tc.cu
-  if (Cin % 16 == 0 && Cin >= 16 && ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 128)))) return 16;   // conv3d_tcg.cu
+  if (Cin % 16 == 0 && Cin >= 16 &&
+      ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 128)) || (W == osb::TC_W && (Cout == 64 || Cout == 128))))
+    return 16;                                                                                  // conv3d_tcg.cu
   return 0;
 }
 

@@ -428,6 +428,8 @@ int launch_tcg_dispatch(const float* x, const float* w, const float* scale, cons
   if (W == 64 && Cout == 64) return launch_tcg<64, 16, 64, 2>(p, stream);
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
+  if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
+  if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
   return -1;
 }
 

@@ -46,36 +46,70 @@ __device__ __forceinline__ float lerp_row(const float* __restrict__ row, size_t 
   return __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
 }
 
+// One thread = one pixel x one "row" (a geometry channel of a level, or a level's correlation row): 2r+1 taps that, up to
+// coordinate rounding, slide over one window of 2r+2 consecutive samples.  The window is loaded once (zero padded) and each
+// tap picks its two samples from registers; a tap whose floor() does not land on window slot k (possible only when the
+// coordinate round trip moves it across an integer) falls back to a direct read.  RADIUS = 0 is the generic path.
+template <int RADIUS>
 __global__ void __launch_bounds__(128) geo_lookup_kernel(const GeoParams p) {
   const int w = blockIdx.x * 128 + threadIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y;
+  const int rows = p.C + 1;
+  const int b = blockIdx.z / (p.levels * rows), lr = blockIdx.z % (p.levels * rows);
+  const int lvl = lr / rows, c = lr % rows;
   if (w >= p.W) return;
   const size_t hw = (size_t)p.H * p.W, pix = (size_t)h * p.W + w;
   const float disp = __ldg(p.disp + (size_t)b * hw + pix);
-  const float cx = __ldg(p.coords + (size_t)b * hw + pix);
-  const int taps = 2 * p.radius + 1;
-  const int per_level = (p.C + 1) * taps;
-  float* out = p.out + (size_t)b * p.levels * per_level * hw + pix;
-  float scale = 1.f;                                   // 1 / 2^level (exact)
+  const int radius = RADIUS > 0 ? RADIUS : p.radius;
+  const int taps = 2 * radius + 1;
+  const float scale = 1.f / (float)(1 << lvl);         // exact
+  const float dq = disp * scale;                       // disp / 2^lvl, exact
+  const float* row;
+  size_t stride;
+  int len;
+  float base;                                          // tap k samples at base + (k - radius): the reference adds dx + base for
+                                                       // the geometry rows and base + dx for the correlation (same fp32 sum)
+  // constant indices only: a runtime index would make the compiler copy the pointer arrays to local memory
+  const float* geo = lvl == 0 ? p.geo[0] : lvl == 1 ? p.geo[1] : lvl == 2 ? p.geo[2] : p.geo[3];
+  const float* corr = lvl == 0 ? p.corr[0] : lvl == 1 ? p.corr[1] : lvl == 2 ? p.corr[2] : p.corr[3];
+  if (c < p.C) {
+    len = p.D >> lvl;
+    row = geo + ((size_t)b * p.C + c) * len * hw + pix;
+    stride = hw;
+    base = dq;
+  } else {
+    len = p.W2 >> lvl;
+    row = corr + ((size_t)b * hw + pix) * len;
+    stride = 1;
+    base = __fsub_rn(__ldg(p.coords + (size_t)b * hw + pix) * scale, dq);            // coords / 2^lvl - disp / 2^lvl
+  }
+  float* o = p.out + (((size_t)b * p.levels + lvl) * rows * taps + (size_t)c * taps) * hw + pix;
+  if (RADIUS > 0) {
+    constexpr int T = 2 * RADIUS + 1;
+    const float x0 = roundtrip(__fadd_rn((float)(-RADIUS), base), len);
+    const int i0 = (int)floorf(x0);
+    float win[T + 1];
 #pragma unroll
-  for (int lvl = 0; lvl < GEO_MAX_LEVELS; ++lvl, scale *= 0.5f) {   // unrolled so the level pointers stay in the parameter bank
-    if (lvl >= p.levels) break;
-    const int dl = p.D >> lvl, wl = p.W2 >> lvl;
-    const float dq = disp * scale;                     // disp / 2^lvl, exact
-    const float cq = __fsub_rn(cx * scale, dq);        // coords / 2^lvl - disp / 2^lvl
-    float* o = out + (size_t)lvl * per_level * hw;
-    for (int c = 0; c < p.C; ++c) {
-      const float* row = p.geo[lvl] + ((size_t)b * p.C + c) * dl * hw + pix;          // element d lies d * H*W further
-      for (int k = 0; k < taps; ++k) {
-        const float x = __fadd_rn((float)(k - p.radius), dq);                          // dx + disp / 2^lvl
-        o[(size_t)(c * taps + k) * hw] = lerp_row(row, hw, dl, roundtrip(x, dl));
+    for (int j = 0; j <= T; ++j) {
+      const int i = i0 + j;
+      win[j] = (i >= 0 && i < len) ? __ldg(row + (size_t)i * stride) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      const float ix = roundtrip(__fadd_rn((float)(k - RADIUS), base), len);
+      const float fl = floorf(ix);
+      float v;
+      if ((int)fl == i0 + k) {
+        const float w1 = __fsub_rn(ix, fl), w0 = __fsub_rn(__fadd_rn(fl, 1.f), ix);
+        v = __fadd_rn(__fmul_rn(win[k], w0), __fmul_rn(win[k + 1], w1));
+      } else {
+        v = lerp_row(row, stride, len, ix);
       }
+      o[(size_t)k * hw] = v;
     }
-    const float* crow = p.corr[lvl] + ((size_t)b * hw + pix) * wl;
-    for (int k = 0; k < taps; ++k) {
-      const float x = __fadd_rn(cq, (float)(k - p.radius));
-      o[(size_t)(p.C * taps + k) * hw] = lerp_row(crow, 1, wl, roundtrip(x, wl));
-    }
+  } else {
+    for (int k = 0; k < taps; ++k)
+      o[(size_t)k * hw] = lerp_row(row, stride, len, roundtrip(__fadd_rn((float)(k - radius), base), len));
   }
 }
 
@@ -163,8 +197,10 @@ int osb_geo_lookup_fwd(const float* geo0, const float* geo1, const float* geo2, 
   }
   p.disp = disp, p.coords = coords, p.out = out;
   p.B = B, p.C = C, p.D = D, p.H = H, p.W = W, p.W2 = W2, p.levels = num_levels, p.radius = radius;
-  dim3 grid((W + 127) / 128, H, B);
-  geo_lookup_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+  OSB_REQUIRE((long long)B * num_levels * (C + 1) <= 65535, "geo_lookup: B * levels * (C + 1) must fit a grid dimension");
+  dim3 grid((W + 127) / 128, H, B * num_levels * (C + 1));
+  if (radius == 4) geo_lookup_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(p);      // IGEV / StereoBase default (corr_radius 4)
+  else geo_lookup_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
   count_launch();
   return check_launch("geo_lookup_kernel");
 }

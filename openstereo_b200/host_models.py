@@ -9,14 +9,16 @@ machine without easydict/timm; where it IS importable, us
 ``openstereo_b200.patch.patch(reference_model)`` instead and nothing here is needed.
 
 Division of labour: the 2D feature extractors are out of the kernel scope (SURVEY.md section 2.1
-row 12) and stay torch.nn/cuDNN; everything from the cost volume to the disparity map runs in the
-sm_100a kernels through the engines of aggregation.py.  The 3D modules below are PARAMETER
+row 12) and stay torch.nn/cuDNN -- except their 1/2-resolution front (eight 32->32 3x3 convs), which
+reuses the tcgen05 conv kernel when the input is 256 rows high (_front_tc); everything from the cost
+volume to the disparity map runs in the sm_100a kernels through the engines of aggregation.py.  The 3D modules below are PARAMETER
 CONTAINERS: they are never called, only read by the engines.
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import aggregation as _agg
 from . import ops
 from .aggregation import GwcAggregation, PSMAggregation
 
@@ -31,6 +33,72 @@ def _cfg_get(cfgs, key, default=None):
 def _cb(cin, cout, k, stride, pad, dilation, bias=False):
     return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=dilation if dilation > 1 else pad,
                                    dilation=dilation, bias=bias), nn.BatchNorm2d(cout))
+
+
+def _front_tc_ok(net, x):
+    """The 1/2-resolution front of the backbone (firstconv[1:], layer1: eight 32->32 3x3 convs, where cuDNN's best fp32
+    kernel reaches ~8 TFLOP/s) can run on the tcgen05 conv kernel when the half-resolution HEIGHT is the 128-voxel UMMA tile:
+    a 2D conv commutes with transposing the image, so the kernel sees (rows = W/2, columns = H/2 = 128) and the 3x3 weights
+    with kh/kw swapped, as a one-plane 3D conv (the kd != 1 phases are skipped for D = 1)."""
+    return (getattr(net, "_osb_folded", False) and x.is_cuda and x.dim() == 4 and x.shape[2] == 2 * ops.TC_WIDTH and x.shape[3] % 2 == 0
+            and _agg.USE_TENSOR_CORES and x.dtype == torch.float32 and ops.conv3d_tc_kc(32, 32, ops.TC_WIDTH) == 32)
+
+
+def _front_tc(net, x):
+    convs = [m for m in net.firstconv.modules() if isinstance(m, nn.Conv2d)]
+    blocks = list(net.layer1.children())
+    y = F.relu(convs[0](x))                                                      # 3 -> 32, stride 2: stays cuDNN
+    t = y.permute(0, 3, 2, 1).contiguous().unsqueeze(1)                          # (B, 1, W/2, H/2 = 128, 32) channels-last
+    t = _tc2d(net, convs[2], _tc2d(net, convs[1], t, ops.ACT_RELU, transpose=True), ops.ACT_RELU, transpose=True)
+    for i, blk in enumerate(blocks):                                             # conv-bn-relu, conv-bn, += identity
+        c1, c2 = _block_convs(blk)
+        assert blk.downsample is None
+        t = _tc2d(net, c2, _tc2d(net, c1, t, ops.ACT_RELU, transpose=True), ops.ACT_NONE, residual=t, last=(i == len(blocks) - 1),
+                  transpose=True)
+    return t.squeeze(2).transpose(2, 3).contiguous()                             # (B, 32, 1, W/2, 128) -> (B, 32, 128, W/2)
+
+
+def _tc2d(net, conv, t, act, residual=None, last=False, transpose=False):
+    """One BN-folded 3x3 Conv2d as a one-plane 3x3x3 conv on the tcgen05 kernels: t (B, 1, rows, 128, Cin) channels-last."""
+    cache = net.__dict__.setdefault("_osb_tc2d", {})
+    if id(conv) not in cache:
+        assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+        w5 = torch.zeros(conv.out_channels, conv.in_channels, 3, 3, 3, dtype=torch.float32, device=conv.weight.device)
+        w2 = conv.weight.detach().float()
+        w5[:, :, 1] = w2.transpose(2, 3) if transpose else w2                   # image transposed -> taps transposed
+        kc = ops.conv3d_tc_kc(conv.in_channels, conv.out_channels, ops.TC_WIDTH)
+        cache[id(conv)] = (ops.pack_tc_weight(w5, kc), None if conv.bias is None else conv.bias.detach().float().contiguous())
+    wp, bias = cache[id(conv)]
+    return ops.conv3d_k3_tc(t, wp, None, bias, residual, act, out_ndhwc=not last, res_ndhwc=True)
+
+
+def _block_convs(blk):
+    c1 = [m for m in blk.conv1.modules() if isinstance(m, nn.Conv2d)][0]
+    c2 = [m for m in blk.conv2.modules() if isinstance(m, nn.Conv2d)][0]
+    return c1, c2
+
+
+def _stage_tc(net, stage, x):
+    """A residual stage (layer2 / layer3 of the PSMNet-style extractor: gwcnet_backbone.py:38-60): the first block (stride /
+    channel change + 1x1 downsample) stays cuDNN; the remaining identical 3x3 blocks run on the tcgen05 kernel when the
+    feature map is 128 columns wide, channels-last in between and back to NCHW in the last epilogue."""
+    blocks = list(stage.children())
+    y = blocks[0](x)
+    rest = blocks[1:]
+    c = y.shape[1]
+    ok = (getattr(net, "_osb_folded", False) and rest and y.is_cuda and y.dtype == torch.float32 and y.shape[3] == ops.TC_WIDTH
+          and _agg.USE_TENSOR_CORES and ops.conv3d_tc_kc(c, c, ops.TC_WIDTH) != 0
+          and all(b.downsample is None and all(cv.dilation == (1, 1) and cv.in_channels == c and cv.out_channels == c
+                                               for cv in _block_convs(b)) for b in rest))
+    if not ok:
+        for b in rest:
+            y = b(y)
+        return y
+    t = ops.to_ndhwc(y.unsqueeze(2).contiguous())                                 # (B, 1, H, 128, C)
+    for i, b in enumerate(rest):
+        c1, c2 = _block_convs(b)
+        t = _tc2d(net, c2, _tc2d(net, c1, t, ops.ACT_RELU), ops.ACT_NONE, residual=t, last=(i == len(rest) - 1))
+    return t.squeeze(2)                                                           # (B, C, 1, H, 128) -> NCHW
 
 
 class _ResBlock(nn.Module):
@@ -75,9 +143,9 @@ class _GwcFeatureExtraction(nn.Module):
                                           nn.Conv2d(128, concat_channels, kernel_size=1, padding=0, stride=1, bias=False))
 
     def forward(self, x):
-        x = self.layer1(self.firstconv(x))
-        l2 = self.layer2(x)
-        l3 = self.layer3(l2)
+        x = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
+        l2 = _stage_tc(self, self.layer2, x)
+        l3 = _stage_tc(self, self.layer3, l2)
         l4 = self.layer4(l3)
         gwc = torch.cat((l2, l3, l4), dim=1)
         out = {"gwc_feature": gwc}
@@ -114,6 +182,7 @@ def _fold_conv_bn(module):
     walk(fused)
     for q in fused.parameters():
         q.requires_grad_(False)
+    fused._osb_folded = not any(isinstance(m, nn.BatchNorm2d) for m in fused.modules())   # every BN absorbed: convs carry the affine
     return fused
 
 
@@ -169,9 +238,9 @@ class _PsmBackbone(nn.Module):
                                       nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, dilation=1, bias=False))
 
     def _forward(self, x):
-        o2 = self.layer1(self.firstconv(x))
-        o4_0 = self.layer2(o2)
-        o8 = self.layer4(self.layer3(o4_0))
+        o2 = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
+        o4_0 = _stage_tc(self, self.layer2, o2)
+        o8 = self.layer4(_stage_tc(self, self.layer3, o4_0))
         size = (o8.size()[2], o8.size()[3])
         up = [F.interpolate(getattr(self, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
         return self.lastconv(torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1))

@@ -229,3 +229,48 @@ def test_gwc_aggregation_full_width_tensor_cores(osb):
     finally:
         agg.USE_TENSOR_CORES = True
     assert rel_err(got_logits, ref_logits.cpu()) <= 5e-5
+
+
+def test_backbone_front_tensor_cores(osb):
+    """256-row inputs: firstconv[1:] + layer1 (eight 32->32 3x3 convs at 1/2 resolution) run on the tcgen05 conv kernel
+    through the transposed-image mapping.  Compared with cuDNN on the same BN-folded weights and with the unfolded module
+    on the CPU (fp32); 3xTF32 keeps fp32 accuracy, so the tolerance is the usual accumulation-order one."""
+    _, agg, hm, _ = osb
+    torch.manual_seed(7)
+    m = hm._GwcFeatureExtraction(True, 12).eval()
+    with torch.no_grad():
+        for mod in m.modules():                              # non-trivial BN statistics so that the folding matters
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2), mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5), mod.bias.normal_(0, 0.2)
+        x = torch.randn(2, 3, 256, 96)
+        want_cpu = m.layer1(m.firstconv(x))
+        x512 = torch.randn(1, 3, 32, 512)                    # 1/4-resolution width 128: layer2 / layer3 blocks on tensor cores
+        want512 = m(x512)["gwc_feature"]
+        f = hm._fold_conv_bn(m).cuda()
+        xg = x.cuda()
+        assert hm._front_tc_ok(f, xg) and not hm._front_tc_ok(f, xg[:, :, :128])
+        got = hm._front_tc(f, xg)
+        cudnn = f.layer1(f.firstconv(xg))
+        assert got.shape == cudnn.shape == (2, 32, 128, 48) and got.is_contiguous()
+        assert rel_err(got, cudnn.cpu()) <= 2e-5
+        assert rel_err(got, want_cpu) <= 5e-5
+        full = f(xg)                                         # the whole extractor takes the tensor-core front by itself
+        agg.USE_TENSOR_CORES = False
+        try:
+            ref = f(xg)
+        finally:
+            agg.USE_TENSOR_CORES = True
+        assert rel_err(full["gwc_feature"], ref["gwc_feature"].cpu()) <= 5e-5
+        # residual stages: 15 + 2 blocks of layer2 / layer3 leave cuDNN when the 1/4-resolution map is 128 columns wide
+        from openstereo_b200 import _lib
+        before = _lib.launch_count()
+        got512 = f(x512.cuda())["gwc_feature"]
+        assert _lib.launch_count() - before == 1 + 30 + 1 + 4      # two layout changes + 30 + 4 convs (front not taken: H != 256)
+        assert rel_err(got512, want512) <= 1e-4
+        agg.USE_TENSOR_CORES = False
+        try:
+            ref512 = f(x512.cuda())["gwc_feature"]
+        finally:
+            agg.USE_TENSOR_CORES = True
+        assert rel_err(got512, ref512.cpu()) <= 1e-4

@@ -322,6 +322,9 @@ def test_conv3d_tc_matches_fp32(ops, b, cin, d, h):
     (1, 128, 128, 3, 8, 32),    # GwcNet conv4 @ 1/16 (four rows per tile, N = 3 x 128)
     (1, 64, 64, 2, 16, 32),     # PSMNet conv4
     (1, 32, 128, 1, 3, 32),     # ragged H, single plane
+    (2, 64, 64, 1, 7, 128),     # 2D backbone layer2 as a one-plane volume: full-width rows, two tiles per item, ragged H
+    (1, 128, 128, 1, 5, 128),   # 2D backbone layer3: N = 3 x 128 at full width
+    (1, 64, 64, 2, 4, 128),     # the same kernel on a real volume (kd taps live)
 ])
 def test_conv3d_tc_generic_tiles(ops, b, cin, cout, d, h, w):
     """Multi-row-tile tensor-core conv (conv3d_tcg.cu) vs the fp64 reference conv."""

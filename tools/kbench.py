@@ -52,7 +52,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--only", default="volume,softargmin,conv")
+    ap.add_argument("--only", default="volume,softargmin,conv,lookup")
     ap.add_argument("--tc-only", action="store_true")
     a = ap.parse_args()
     only = set(a.only.split(","))
@@ -121,6 +121,30 @@ def main():
         wp = (torch.randn(32, 32, device=dev) * 0.1).contiguous()
         ms, best = timeit(lambda: ops.conv3d_1x1(x, wp), a.iters, flush)
         report("conv1x1_32to32_full", ms, best, bytes_=4 * 2 * B * 32 * 48 * 64 * 128)
+    if "lookup" in only:
+        # SURVEY.md section 8(f) rows 1 and 3 at config 5 (IGEV/StereoBase @480x640, B=8): H'=120, W'=160, D'=48, 8 geometry
+        # channels, 2 levels, radius 4 -> 162 output channels (99.5 MB written per GRU iteration)
+        from openstereo_b200 import geo
+        hb, wb, c, lv, r = 120, 160, 8, 2, 4
+        vol = torch.randn(B, c, D, hb, wb, device=dev)
+        f1, f2 = torch.randn(B, 96, hb, wb, device=dev), torch.randn(B, 96, hb, wb, device=dev)
+        gv = geo.CombinedGeoEncodingVolume(f1, f2, vol, num_levels=lv, radius=r)
+        coords = torch.arange(wb, device=dev).float().reshape(1, 1, wb, 1).repeat(B, hb, 1, 1)
+        taps = 2 * r + 1
+        out_bytes = 4 * B * lv * (c + 1) * taps * hb * wb
+        read_bytes = 4 * B * hb * wb * (lv * (c + 1) * (taps + 1) + 2)        # one (taps+1)-sample window per row, disp, coords
+        smooth = (torch.arange(wb, device=dev).float().view(1, 1, 1, wb) * 0.2 + torch.arange(hb, device=dev).float().view(1, 1, hb, 1) * 0.1
+                  + torch.rand(B, 1, hb, wb, device=dev)).clamp(0, D - 1).contiguous()
+        rand = (torch.rand(B, 1, hb, wb, device=dev) * (D - 1)).contiguous()
+        for name, disp in (("geo_lookup_smooth_disp", smooth), ("geo_lookup_random_disp", rand)):
+            ms, best = timeit(lambda: gv(disp, coords), a.iters, flush)
+            report(name, ms, best, out_bytes + read_bytes, pixels=B * hb * wb, out_MB=round(out_bytes / 1e6, 1))
+        ms, best = timeit(lambda: geo.CombinedGeoEncodingVolume(f1, f2, vol, num_levels=lv, radius=r), a.iters, flush)
+        report("geo_volume_build (einsum + 2 pair-average launches)", ms, best)
+        low = torch.rand(B, 1, hb, wb, device=dev) * 40
+        wts = torch.softmax(torch.randn(B, 9, 4 * hb, 4 * wb, device=dev), dim=1)
+        ms, best = timeit(lambda: ops.context_upsample(low, wts, 4), a.iters, flush)
+        report("context_upsample_x4", ms, best, 4 * (B * hb * wb + 10 * B * 16 * hb * wb))
 
 
 if __name__ == "__main__":
