@@ -167,6 +167,15 @@ int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* sc
  * arrays (folded BN / bias).  Cin = 32. */
 int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const float* scale, const float* shift, float* y, int B,
                                int Cin, int D, int H, int W, osb_stream_t stream);
+/* 3x3 Conv2d (stride 1, padding = dilation, dilation 1 or 2) + folded BN + residual + activation on the tensor cores, for the
+ * residual blocks of the PSMNet-style feature extractor (BasicBlock gwcnet_backbone.py:13-35, layers :38-60;
+ * psmnet/submodule.py:219-243): x (B,H,W,Cin) channels-last, w_split = the 3x3x3 tensor-core packing of the 2D weight placed
+ * at kd = 1, y (B,H,W,Cout) or (B,Cout,H,W).  dilation 1 = osb_conv3d_k3_tc_fwd with D = 1; dilation 2: W = 128, Cout = 128.
+ * osb_conv2d_tc_kc returns the K chunk of the serving kernel (0 = unsupported). */
+int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation);
+int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const float* w_split, const float* scale, const float* shift, const float* residual,
+                         float* y, int B, int Cin, int Cout, int H, int W, int dilation, int act, int out_nhwc, int res_nhwc,
+                         osb_stream_t stream);
 /* ---- GRU-iteration lookups of IGEV / StereoBase ------------------------------------
  * Pair-average along the middle axis of a (outer, n, inner) array -> (outer, n/2, inner): the F.avg_pool2d(.., [1,2],
  * stride=[1,2]) pyramid of Combined_Geo_Encoding_Volume.__init__ (igev/geometry.py:24-30, stereobase/gru_blocks.py:187-193)

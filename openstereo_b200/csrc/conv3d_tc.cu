@@ -450,6 +450,8 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
 
 int launch_tcg_dispatch(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
+int launch_tcg_dilated2(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+                        int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
 
 }  // namespace osb
 
@@ -501,5 +503,29 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");
   p.items = (int)items;
   return launch_tc<32>(p, (cudaStream_t)stream);
+}
+
+int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation) {
+  if (dilation == 1) return osb_conv3d_tc_kc(Cin, Cout, W, 1);
+  if (dilation == 2 && W == osb::TC_W && Cout == 128 && Cin % 16 == 0 && Cin >= 16) return 16;
+  return 0;
+}
+
+int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const float* w_split, const float* scale, const float* shift, const float* residual,
+                         float* y, int B, int Cin, int Cout, int H, int W, int dilation, int act, int out_nhwc, int res_nhwc,
+                         osb_stream_t stream) {
+  using namespace osb;
+  if (dilation == 1)
+    return osb_conv3d_k3_tc_fwd(x_nhwc, w_split, scale, shift, residual, y, B, Cin, Cout, 1, H, W, act, out_nhwc, res_nhwc, stream);
+  OSB_REQUIRE(x_nhwc && w_split && y, "conv2d_k3_tc: null pointer");
+  OSB_REQUIRE(B > 0 && H > 0, "conv2d_k3_tc: empty shape");
+  OSB_REQUIRE(osb_conv2d_tc_kc(Cin, Cout, W, dilation) != 0, "conv2d_k3_tc: unsupported shape Cin=%d Cout=%d W=%d dilation=%d", Cin, Cout,
+              W, dilation);
+  OSB_REQUIRE(act >= 0 && act <= 2, "conv2d_k3_tc: unknown activation %d", act);
+  OSB_REQUIRE((reinterpret_cast<uintptr_t>(x_nhwc) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_split) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+              "conv2d_k3_tc: pointers must be 16-byte aligned");
+  return launch_tcg_dilated2(x_nhwc, w_split, scale, shift, residual, y, B, Cin, Cout, H, W, act, out_nhwc, res_nhwc,
+                             (cudaStream_t)stream);
 }
 }

@@ -27,8 +27,11 @@ struct TcgParams {
   int items, hblocks;
 };
 
-template <int COUT, int KC, int W, int TILES>
+template <int COUT, int KC, int W, int TILES, int DIL = 1>
 struct TcgCfg {
+  // DIL = 2: dilated 2D convs of the backbone (layer4 of gwcnet_backbone.py:38-60, psmnet_backbone.py) as one-plane volumes:
+  // tap kh of output row t reads input row t + (kh-1)*DIL, the kw-stacked partial sums are un-shifted by DIL columns.
+  static_assert(DIL == 1 || (W == 128 && DIL == 2 && COUT >= 64), "dilation 2 is instantiated for full-width rows only");
   static constexpr int R = 128 / W;                         // image rows per M tile
   static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row
   static constexpr int UNIT_BYTES = 128 * ROWB;
@@ -37,29 +40,30 @@ struct TcgCfg {
   static constexpr int NPER = N3 / NMMA;
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
   static constexpr int STAGES = (COUT >= 128) ? 3 : 4;   // the Cout = 128 weight slices leave room for 3
-  static constexpr int S_LAST = (TILES - 1) * R + 1;        // unit start rows run from -1 to S_LAST (block-relative)
+  static constexpr int S_FIRST = -DIL;                      // unit start rows run from S_FIRST to S_LAST (block-relative)
+  static constexpr int S_LAST = (TILES - 1) * R + DIL;
   static constexpr int HBLK = TILES * R;                    // output rows per work item
   static constexpr int KSTEPS = KC / 8;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
   static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
-  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * DIL * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
   static_assert(TILES * N3 <= 512, "accumulators exceed TMEM");
   static_assert(B_SLICE % 1024 == 0 && UNIT_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
   static_assert(NPER % 16 == 0 && NPER <= 256, "invalid UMMA N");
   // tile fed by unit s through tap kh, or -1
   static constexpr int tile_of(int s, int kh) {
-    const int num = s + 1 - kh;
+    const int num = s - (kh - 1) * DIL;
     return (num >= 0 && num % R == 0 && num / R < TILES) ? num / R : -1;
   }
   static constexpr bool used(int s) { return tile_of(s, 0) >= 0 || tile_of(s, 1) >= 0 || tile_of(s, 2) >= 0; }
 };
 
-template <int COUT, int KC, int W, int TILES>
-__global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d_tcg_kernel(const TcgParams p) {
-  using C = TcgCfg<COUT, KC, W, TILES>;
+template <int COUT, int KC, int W, int TILES, int DIL = 1>
+__global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) conv3d_tcg_kernel(const TcgParams p) {
+  using C = TcgCfg<COUT, KC, W, TILES, DIL>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_hi = smem + C::A_OFF;
@@ -73,8 +77,8 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
   uint64_t* acc_full = b_empty + 3;                 // [TILES]
   uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
-  float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
-  float* s_scale = xchg + 2 * 4 * 2 * 32;
+  float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][DIL columns][32]
+  float* s_scale = xchg + 2 * 4 * 2 * DIL * 32;
   float* s_shift = s_scale + COUT;
   float* zeros = s_shift + COUT;
   float* tpose = zeros + COUT;                      // [4 warps][32][TP_STRIDE] transpose tiles of the epilogue
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
         for (int ch = 0; ch < nchunk; ++ch, ++phc) {
           const bool last_phase = (kd == last_kd) && (ch == nchunk - 1);
 #pragma unroll
-          for (int s = -1; s <= C::S_LAST; ++s) {
+          for (int s = C::S_FIRST; s <= C::S_LAST; ++s) {
             if (!C::used(s)) continue;
             const uint32_t slot = unitc % C::STAGES, par = (unitc / C::STAGES) & 1;
             mbar_wait(&a_ready[slot], par);
-            if (s + 1 >= 0 && s + 1 < 3) mbar_wait(&b_full[s + 1], phc & 1);   // slice kh = s+1 is first needed by unit s
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+              if (C::tile_of(s, kh) == 0) mbar_wait(&b_full[kh], phc & 1);      // slice kh is first needed by the unit feeding tile 0
             tc_fence_after();
             const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
             const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
         const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)W * p.Cin;
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
-          for (int s = -1; s <= C::S_LAST; ++s) {
+          for (int s = C::S_FIRST; s <= C::S_LAST; ++s) {
             if (!C::used(s)) continue;
             if (mine && unitc % C::STAGES == (uint32_t)lw) {
               // unit = R consecutive image rows starting at h0 + s: operand row v is voxel (h0 + s) * W + v of the plane
@@ -275,26 +281,26 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
             tc_fence_before();
             mbar_arrive(&acc_empty[t]);
           }
-          float* xb = xchg + (exc & 1) * (4 * 2 * 32);
+          float* xb = xchg + (exc & 1) * (4 * 2 * DIL * 32);
           ++exc;
-          if (lane == 31) {
+          if (lane >= 32 - DIL) {                     // the next quadrant's first DIL columns need these P0 values
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xb[(q * 2) * 32 + i] = __uint_as_float(raw[0][i]);
+            for (int i = 0; i < 32; ++i) xb[((q * 2) * DIL + lane - (32 - DIL)) * 32 + i] = __uint_as_float(raw[0][i]);
           }
-          if (lane == 0) {
+          if (lane < DIL) {                           // the previous quadrant's last DIL columns need these P2 values
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xb[(q * 2 + 1) * 32 + i] = __uint_as_float(raw[2][i]);
+            for (int i = 0; i < 32; ++i) xb[((q * 2 + 1) * DIL + lane) * 32 + i] = __uint_as_float(raw[2][i]);
           }
           named_bar_sync(1, 128);
-          const float* xl = has_left_q ? xb + ((q - 1) * 2) * 32 : zeros;
-          const float* xr = has_right_q ? xb + ((q + 1) * 2 + 1) * 32 : zeros;
+          const float* xl = has_left_q ? xb + (((q - 1) * 2) * DIL + (lane < DIL ? lane : 0)) * 32 : zeros;
+          const float* xr = has_right_q ? xb + (((q + 1) * 2 + 1) * DIL + (lane >= 32 - DIL ? lane - (32 - DIL) : 0)) * 32 : zeros;
           float out[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), 1);
-            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);
-            left = (lane == 0) ? xl[i] : left;        // column w-1 (zero at the image edge)
-            right = (lane == 31) ? xr[i] : right;     // column w+1
+            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), DIL);
+            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), DIL);
+            left = (lane < DIL) ? xl[i] : left;       // column w-DIL (zero at the image edge)
+            right = (lane >= 32 - DIL) ? xr[i] : right;   // column w+DIL
             out[i] = (left + __uint_as_float(raw[1][i])) + right;
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
@@ -381,10 +387,10 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES>
+template <int COUT, int KC, int W, int TILES, int DIL = 1>
 static int launch_tcg(TcgParams& p, cudaStream_t stream) {
-  using C = TcgCfg<COUT, KC, W, TILES>;
-  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES>;
+  using C = TcgCfg<COUT, KC, W, TILES, DIL>;
+  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -430,6 +436,17 @@ int launch_tcg_dispatch(const float* x, const float* w, const float* scale, cons
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
   if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
+  return -1;
+}
+
+// dilated (2) one-plane variant for the 2D backbone: same parameters with D == 1
+int launch_tcg_dilated2(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+                        int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream) {
+  TcgParams p{};
+  p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
+  p.B = B, p.D = 1, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  if (Cin % 16 != 0 || Cin < 16) return -1;
+  if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1, 2>(p, stream);
   return -1;
 }
 

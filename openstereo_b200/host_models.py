@@ -48,28 +48,29 @@ def _front_tc(net, x):
     convs = [m for m in net.firstconv.modules() if isinstance(m, nn.Conv2d)]
     blocks = list(net.layer1.children())
     y = F.relu(convs[0](x))                                                      # 3 -> 32, stride 2: stays cuDNN
-    t = y.permute(0, 3, 2, 1).contiguous().unsqueeze(1)                          # (B, 1, W/2, H/2 = 128, 32) channels-last
+    t = y.permute(0, 3, 2, 1).contiguous()                                       # (B, W/2, H/2 = 128, 32) channels-last
     t = _tc2d(net, convs[2], _tc2d(net, convs[1], t, ops.ACT_RELU, transpose=True), ops.ACT_RELU, transpose=True)
     for i, blk in enumerate(blocks):                                             # conv-bn-relu, conv-bn, += identity
         c1, c2 = _block_convs(blk)
         assert blk.downsample is None
         t = _tc2d(net, c2, _tc2d(net, c1, t, ops.ACT_RELU, transpose=True), ops.ACT_NONE, residual=t, last=(i == len(blocks) - 1),
                   transpose=True)
-    return t.squeeze(2).transpose(2, 3).contiguous()                             # (B, 32, 1, W/2, 128) -> (B, 32, 128, W/2)
+    return t.transpose(2, 3).contiguous()                                        # (B, 32, W/2, 128) -> (B, 32, 128, W/2)
 
 
 def _tc2d(net, conv, t, act, residual=None, last=False, transpose=False):
-    """One BN-folded 3x3 Conv2d as a one-plane 3x3x3 conv on the tcgen05 kernels: t (B, 1, rows, 128, Cin) channels-last."""
+    """One BN-folded 3x3 Conv2d (dilation 1 or 2) on the tcgen05 kernels: t (B, rows, 128, Cin) channels-last."""
     cache = net.__dict__.setdefault("_osb_tc2d", {})
+    dil = conv.dilation[0]
     if id(conv) not in cache:
-        assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+        assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (dil, dil) and conv.dilation == (dil, dil)
         w5 = torch.zeros(conv.out_channels, conv.in_channels, 3, 3, 3, dtype=torch.float32, device=conv.weight.device)
         w2 = conv.weight.detach().float()
         w5[:, :, 1] = w2.transpose(2, 3) if transpose else w2                   # image transposed -> taps transposed
-        kc = ops.conv3d_tc_kc(conv.in_channels, conv.out_channels, ops.TC_WIDTH)
+        kc = ops.conv2d_tc_kc(conv.in_channels, conv.out_channels, ops.TC_WIDTH, dil)
         cache[id(conv)] = (ops.pack_tc_weight(w5, kc), None if conv.bias is None else conv.bias.detach().float().contiguous())
     wp, bias = cache[id(conv)]
-    return ops.conv3d_k3_tc(t, wp, None, bias, residual, act, out_ndhwc=not last, res_ndhwc=True)
+    return ops.conv2d_k3_tc(t, wp, None, bias, residual, act, dil, out_nhwc=not last, res_nhwc=True)
 
 
 def _block_convs(blk):
@@ -78,27 +79,35 @@ def _block_convs(blk):
     return c1, c2
 
 
+def _block_tc_ok(blk, c):
+    """An identity-shortcut BasicBlock whose two 3x3 convs (same dilation, c -> c channels) have a tensor-core kernel."""
+    if blk.downsample is not None:
+        return False
+    c1, c2 = _block_convs(blk)
+    dil = c1.dilation[0]
+    return all(cv.kernel_size == (3, 3) and cv.stride == (1, 1) and cv.dilation == (dil, dil) and cv.padding == (dil, dil)
+               and cv.in_channels == c and cv.out_channels == c for cv in (c1, c2)) and ops.conv2d_tc_kc(c, c, ops.TC_WIDTH, dil) != 0
+
+
 def _stage_tc(net, stage, x):
-    """A residual stage (layer2 / layer3 of the PSMNet-style extractor: gwcnet_backbone.py:38-60): the first block (stride /
-    channel change + 1x1 downsample) stays cuDNN; the remaining identical 3x3 blocks run on the tcgen05 kernel when the
-    feature map is 128 columns wide, channels-last in between and back to NCHW in the last epilogue."""
+    """A residual stage (layer2 / layer3 / the dilated layer4 of the PSMNet-style extractor: gwcnet_backbone.py:38-60): a
+    first block that changes stride / channels (+ 1x1 downsample) stays cuDNN; the identity-shortcut 3x3 blocks run on the
+    tcgen05 kernel when the feature map is 128 columns wide, channels-last in between, NCHW out of the last epilogue."""
     blocks = list(stage.children())
-    y = blocks[0](x)
-    rest = blocks[1:]
+    usable = getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES
+    y, rest = x, blocks
+    if not (usable and x.shape[3] == ops.TC_WIDTH and _block_tc_ok(blocks[0], x.shape[1])):
+        y, rest = blocks[0](x), blocks[1:]
     c = y.shape[1]
-    ok = (getattr(net, "_osb_folded", False) and rest and y.is_cuda and y.dtype == torch.float32 and y.shape[3] == ops.TC_WIDTH
-          and _agg.USE_TENSOR_CORES and ops.conv3d_tc_kc(c, c, ops.TC_WIDTH) != 0
-          and all(b.downsample is None and all(cv.dilation == (1, 1) and cv.in_channels == c and cv.out_channels == c
-                                               for cv in _block_convs(b)) for b in rest))
-    if not ok:
+    if not (usable and rest and y.shape[3] == ops.TC_WIDTH and all(_block_tc_ok(b, c) for b in rest)):
         for b in rest:
             y = b(y)
         return y
-    t = ops.to_ndhwc(y.unsqueeze(2).contiguous())                                 # (B, 1, H, 128, C)
+    t = ops.to_ndhwc(y.unsqueeze(2).contiguous()).squeeze(1)                      # (B, H, 128, C)
     for i, b in enumerate(rest):
         c1, c2 = _block_convs(b)
         t = _tc2d(net, c2, _tc2d(net, c1, t, ops.ACT_RELU), ops.ACT_NONE, residual=t, last=(i == len(rest) - 1))
-    return t.squeeze(2)                                                           # (B, C, 1, H, 128) -> NCHW
+    return t                                                                      # (B, C, H, 128)
 
 
 class _ResBlock(nn.Module):
@@ -146,7 +155,7 @@ class _GwcFeatureExtraction(nn.Module):
         x = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
         l2 = _stage_tc(self, self.layer2, x)
         l3 = _stage_tc(self, self.layer3, l2)
-        l4 = self.layer4(l3)
+        l4 = _stage_tc(self, self.layer4, l3)
         gwc = torch.cat((l2, l3, l4), dim=1)
         out = {"gwc_feature": gwc}
         if self.concat_feature:
@@ -240,7 +249,7 @@ class _PsmBackbone(nn.Module):
     def _forward(self, x):
         o2 = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
         o4_0 = _stage_tc(self, self.layer2, o2)
-        o8 = self.layer4(_stage_tc(self, self.layer3, o4_0))
+        o8 = _stage_tc(self, self.layer4, _stage_tc(self, self.layer3, o4_0))
         size = (o8.size()[2], o8.size()[3])
         up = [F.interpolate(getattr(self, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
         return self.lastconv(torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1))

@@ -432,3 +432,24 @@ def context_upsample(disp_low, up_weights, scale_factor=4):
     out = torch.empty((b, h * scale_factor, w * scale_factor), dtype=torch.float32, device=disp_low.device)
     _call("osb_context_upsample_fwd", disp_low.data_ptr(), up_weights.data_ptr(), out.data_ptr(), b, h, w, scale_factor, _stream())
     return out
+
+
+def conv2d_tc_kc(cin, cout, w, dilation=1):
+    """K chunk of the tensor-core kernel serving a 3x3 Conv2d of this shape (0 = none)."""
+    return int(_lib.lib.osb_conv2d_tc_kc(int(cin), int(cout), int(w), int(dilation)))
+
+
+def conv2d_k3_tc(x_nhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, dilation=1, out_nhwc=True, res_nhwc=True):
+    """3x3 Conv2d (stride 1, padding = dilation) + folded BN + residual + activation on the tensor cores.  x_nhwc (B,H,W,Cin);
+    w_split = pack_tc_weight of the 3x3x3 weight that holds the 2D taps at kd = 1."""
+    assert x_nhwc.is_cuda and x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and x_nhwc.dim() == 4
+    b, h, w, cin = x_nhwc.shape
+    cout = w_split.shape[4] // 3
+    kc = conv2d_tc_kc(cin, cout, w, dilation)
+    assert kc and w_split.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and w_split.is_contiguous()
+    y = torch.empty((b, h, w, cout) if out_nhwc else (b, cout, h, w), dtype=torch.float32, device=x_nhwc.device)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.numel() == y.numel()
+    _call("osb_conv2d_k3_tc_fwd", x_nhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, cin,
+          cout, h, w, dilation, act, int(out_nhwc), int(res_nhwc), _stream())
+    return y

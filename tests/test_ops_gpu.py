@@ -346,6 +346,25 @@ def test_conv3d_tc_generic_tiles(ops, b, cin, cout, d, h, w):
     rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tcg bn+res+relu ndhwc")
 
 
+@pytest.mark.parametrize("dil,b,c,h", [(2, 2, 128, 9), (1, 1, 64, 6), (2, 1, 128, 2)])
+def test_conv2d_tc_dilated(ops, dil, b, c, h):
+    """3x3 Conv2d (dilation 1 / 2, padding = dilation) of the backbone's residual blocks on the tensor cores, full-width rows."""
+    import torch.nn.functional as F
+    w = 128
+    assert ops.conv2d_tc_kc(c, c, w, dil) == 16 and ops.conv2d_tc_kc(64, 64, w, 2) == 0
+    x, wt = rnd(180, b, c, h, w), rnd(181, c, c, 3, 3, scale=0.1)
+    bias, res = rnd(182, c, scale=0.1), rnd(183, b, c, h, w)
+    want = F.relu(F.conv2d(x.double(), wt.double(), bias.double(), padding=dil, dilation=dil).float() + res)
+    w5 = torch.zeros(c, c, 3, 3, 3)
+    w5[:, :, 1] = wt
+    wp = ops.pack_tc_weight(dev(w5), 16)
+    xc = dev(x.permute(0, 2, 3, 1).contiguous())
+    got = ops.conv2d_k3_tc(xc, wp, None, dev(bias), dev(res.permute(0, 2, 3, 1).contiguous()), ops.ACT_RELU, dil)
+    rel_close(got.permute(0, 3, 1, 2), want, 1e-5, "conv2d tc nhwc dil=%d" % dil)
+    got = ops.conv2d_k3_tc(xc, wp, None, dev(bias), dev(res), ops.ACT_RELU, dil, out_nhwc=False, res_nhwc=False)
+    rel_close(got, want, 1e-5, "conv2d tc nchw dil=%d" % dil)
+
+
 @pytest.mark.parametrize("b,cin,cout,d,h,w", [
     (1, 32, 64, 4, 8, 128),     # GwcNet/PSMNet conv1: 1/4 -> 1/8 res
     (2, 16, 64, 2, 6, 128),     # ragged output rows (3 rows, blocks of 4)
