@@ -343,9 +343,13 @@ def run_ours(args):
         # redir1 (32->32, full) and redir2 (64->64, half) of the three hourglasses
         "osb_conv1x1_ndhwc_fwd": 3 * (vox * 32 * 32 + vox // 8 * 64 * 64),
         # classif3b 32->1 head
-        "osb_conv3d_k3_bn_act_fwd": vox * 27 * 32,
+        "osb_conv3d_k3_c1_ndhwc_fwd": vox * 27 * 32,
+        # 2D backbone residual blocks on the same kernels (two images per pair): 8 front convs 32->32 @128x256, 30 layer2 convs
+        # 64->64, 4 layer3 + 6 dilated layer4 convs 128->128 @64x128 (gwcnet_backbone.py:38-60)
+        "osb_conv2d_k3_tc_fwd": 2 * 9 * (8 * 128 * 256 * 32 * 32 + 30 * 64 * 128 * 64 * 64 + 10 * 64 * 128 * 128 * 128),
     }
-    tc_names = ["osb_conv3d_k3_tc_fwd", "osb_conv3d_k3_s2_tc_fwd", "osb_deconv3d_k3_tc_fwd"]
+    agg_macs = sum(v for k, v in macs.items() if k != "osb_conv2d_k3_tc_fwd")      # = 116.30 GMAC, SURVEY.md section 8a row a6
+    tc_names = ["osb_conv3d_k3_tc_fwd", "osb_conv3d_k3_s2_tc_fwd", "osb_deconv3d_k3_tc_fwd", "osb_conv2d_k3_tc_fwd"]
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             bf16_peak = float(json.load(f).get("bf16_tflops_sustained"))
@@ -361,27 +365,29 @@ def run_ours(args):
             if tot > 0:
                 per[n] = {"launches_per_step": cnt // args.steps, "ms_per_step": round(tot / args.steps, 3),
                           "useful_tflops": round(2 * macs[n] * B * args.steps / (tot / 1e3) / 1e12, 1)}
-        useful = 2 * sum(macs[n] for n in tc_names) * B * args.steps / (tc_total / 1e3) / 1e12
+        ran = [n for n in tc_names if kernel_stats(n)[2] > 0]
+        useful = 2 * sum(macs[n] for n in ran) * B * args.steps / (tc_total / 1e3) / 1e12
         roof_dom = {"kernel": "tcgen05 conv family: conv3d_tc_kernel / conv3d_tcg_kernel (3x3x3 s1), conv3d_tcs2_kernel (s2), "
-                              "conv3d_tcdc_kernel (transposed); kind::tf32 with the 3xTF32 split",
+                              "conv3d_tcdc_kernel (transposed), incl. the backbone's 3x3 residual blocks as one-plane volumes "
+                              "(osb_conv2d_k3_tc_fwd); kind::tf32 with the 3xTF32 split",
                     "bound": "tensor", "achieved": round(3 * useful, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                     "frac": round(3 * useful / tf32_peak, 4), "useful_fp32_equivalent_tflops": round(useful, 1),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense tf32 rate); achieved counts the 3 MMAs "
                                    "issued per fp32-accurate product",
-                    "alg_flops_per_step": 2 * sum(macs[n] for n in tc_names) * B, "share_of_step": round(tc_total / ms, 4),
+                    "alg_flops_per_step": 2 * sum(macs[n] for n in ran) * B, "share_of_step": round(tc_total / ms, 4),
                     "per_kernel": per,
                     # conv3d_tc_kernel<32> (32->32 stem layer), ncu --set full: 403.2 MB read + 362.8 MB written per launch =
                     # its algorithmic 402.7 + 402.7 MB (profiles/r1_ncu_summary_final.md, r1_conv3d_tc_final)
                     "traffic": 765931264 if B == 8 else None}
-    cc_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd", "osb_conv1x1_ndhwc_fwd"]
+    cc_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd", "osb_conv1x1_ndhwc_fwd",
+                "osb_conv3d_k3_c1_ndhwc_fwd"]
     cc_total = sum(kernel_stats(n)[2] for n in cc_names)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                 # derived: SMs x fp32 lanes x 2 x max clock
     roof_cc = None
     if cc_total > 0:
-        all_macs_pair = sum(macs.values())
-        cc_flops = 2 * (all_macs_pair - (sum(macs[n] for n in tc_names) if tc_total > 0 else 0)) * B
+        cc_flops = 2 * (agg_macs - (sum(macs[n] for n in tc_names[:3]) if tc_total > 0 else 0)) * B
         ach = cc_flops * args.steps / (cc_total / 1e3) / 1e12
-        roof_cc = {"kernel": "fp32 CUDA-core layers left in the aggregation (classif3b 32->1 head conv3d_k3_kernel, channels-last "
+        roof_cc = {"kernel": "fp32 CUDA-core layers left in the aggregation (classif3b 32->1 head conv3d_k3_c1_ndhwc_kernel, channels-last "
                              "1x1 redir convs; everything else when the tensor-core variants do not cover a shape)",
                    "bound": "fp32_fma", "achieved": round(ach, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
                    "frac": round(ach / fp32_peak, 4), "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
