@@ -346,7 +346,9 @@ def run_ours(args):
         "osb_conv3d_k3_c1_ndhwc_fwd": vox * 27 * 32,
         # 2D backbone residual blocks on the same kernels (two images per pair): 8 front convs 32->32 @128x256, 30 layer2 convs
         # 64->64, 4 layer3 + 6 dilated layer4 convs 128->128 @64x128 (gwcnet_backbone.py:38-60)
-        "osb_conv2d_k3_tc_fwd": 2 * 9 * (8 * 128 * 256 * 32 * 32 + 30 * 64 * 128 * 64 * 64 + 10 * 64 * 128 * 128 * 128),
+        # + lastconv's 320->128 3x3
+        "osb_conv2d_k3_tc_fwd": 2 * 9 * (8 * 128 * 256 * 32 * 32 + 30 * 64 * 128 * 64 * 64 + 10 * 64 * 128 * 128 * 128
+                                         + 64 * 128 * 320 * 128),
     }
     agg_macs = sum(v for k, v in macs.items() if k != "osb_conv2d_k3_tc_fwd")      # = 116.30 GMAC, SURVEY.md section 8a row a6
     tc_names = ["osb_conv3d_k3_tc_fwd", "osb_conv3d_k3_s2_tc_fwd", "osb_deconv3d_k3_tc_fwd", "osb_conv2d_k3_tc_fwd"]

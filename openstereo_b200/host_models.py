@@ -110,6 +110,22 @@ def _stage_tc(net, stage, x):
     return t                                                                      # (B, C, H, 128)
 
 
+def _lastconv_tc_ok(net, x):
+    """lastconv = conv3x3(320->128)+BN+ReLU, conv1x1(128->12) (gwcnet_backbone.py:62-67): cuDNN picks an FFT algorithm for the
+    320-channel 3x3 (2.1 ms); on the tcgen05 kernel it is the layer3 conv with 20 K chunks."""
+    convs = [m for m in net.lastconv.modules() if isinstance(m, nn.Conv2d)]
+    return (getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES
+            and x.shape[3] == ops.TC_WIDTH and len(convs) == 2 and convs[0].kernel_size == (3, 3) and convs[0].stride == (1, 1)
+            and convs[0].dilation == (1, 1) and convs[0].padding == (1, 1) and convs[1].kernel_size == (1, 1)
+            and ops.conv2d_tc_kc(convs[0].in_channels, convs[0].out_channels, ops.TC_WIDTH, 1) != 0)
+
+
+def _lastconv_tc(net, x):
+    convs = [m for m in net.lastconv.modules() if isinstance(m, nn.Conv2d)]
+    t = ops.to_ndhwc(x.unsqueeze(2).contiguous()).squeeze(1)                      # (B, H, 128, 320)
+    return convs[1](_tc2d(net, convs[0], t, ops.ACT_RELU, last=True))             # 3x3 + ReLU on tensor cores, 1x1 on cuDNN
+
+
 class _ResBlock(nn.Module):
     """conv-bn-relu, conv-bn, += identity (no trailing relu): gwcnet_backbone.py:13-35, psmnet/submodule.py:219-243."""
 
@@ -159,7 +175,7 @@ class _GwcFeatureExtraction(nn.Module):
         gwc = torch.cat((l2, l3, l4), dim=1)
         out = {"gwc_feature": gwc}
         if self.concat_feature:
-            out["concat_feature"] = self.lastconv(gwc)
+            out["concat_feature"] = _lastconv_tc(self, gwc) if _lastconv_tc_ok(self, gwc) else self.lastconv(gwc)
         return out
 
 
@@ -252,7 +268,8 @@ class _PsmBackbone(nn.Module):
         o8 = _stage_tc(self, self.layer4, _stage_tc(self, self.layer3, o4_0))
         size = (o8.size()[2], o8.size()[3])
         up = [F.interpolate(getattr(self, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
-        return self.lastconv(torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1))
+        cat = torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1)
+        return _lastconv_tc(self, cat) if _lastconv_tc_ok(self, cat) else self.lastconv(cat)
 
     def forward(self, inputs):
         if getattr(self, "_rt", None) is None:

@@ -265,9 +265,12 @@ def test_backbone_front_tensor_cores(osb):
         # residual stages: 15 + 2 + 3 (dilated) blocks of layer2 / layer3 / layer4 leave cuDNN when the 1/4-resolution map is 128 wide
         from openstereo_b200 import _lib
         before = _lib.launch_count()
-        got512 = f(x512.cuda())["gwc_feature"]
-        assert _lib.launch_count() - before == (1 + 30) + (1 + 4) + (1 + 6)   # layout change + convs of layer2, layer3, layer4 (dilated)
+        full512 = f(x512.cuda())
+        got512 = full512["gwc_feature"]
+        # layout change + convs of layer2, layer3, layer4 (dilated), lastconv's 320->128 3x3
+        assert _lib.launch_count() - before == (1 + 30) + (1 + 4) + (1 + 6) + (1 + 1)
         assert rel_err(got512, want512) <= 1e-4
+        assert rel_err(full512["concat_feature"], m(x512)["concat_feature"]) <= 1e-4
         agg.USE_TENSOR_CORES = False
         try:
             ref512 = f(x512.cuda())["gwc_feature"]
