@@ -64,8 +64,19 @@ def _patch_gwcnet(model, strict):
     cp.forward = types.MethodType(cost_forward, cp)
     dp.forward = types.MethodType(disp_forward, dp)
     # the two volume builders stay callable on their own, with the reference's method signatures
-    cp.build_gwc_volume = lambda ref, tgt: ops.build_gwc_volume(ref, tgt, cp.maxdisp // cp.downsample, cp.num_groups)
-    cp.build_concat_volume = lambda ref, tgt: ops.build_concat_volume(ref, tgt, cp.maxdisp // cp.downsample)
+    gwc_orig, cat_orig = cp.build_gwc_volume, cp.build_concat_volume          # the reference's bound methods
+
+    def build_gwc(ref, tgt):
+        if ref.is_cuda or strict:                                              # strict: ops raises on CPU tensors
+            return ops.build_gwc_volume(ref, tgt, cp.maxdisp // cp.downsample, cp.num_groups)
+        return gwc_orig(ref, tgt)
+
+    def build_concat(ref, tgt):
+        if ref.is_cuda or strict:
+            return ops.build_concat_volume(ref, tgt, cp.maxdisp // cp.downsample)
+        return cat_orig(ref, tgt)
+
+    cp.build_gwc_volume, cp.build_concat_volume = build_gwc, build_concat
     return model
 
 
@@ -91,11 +102,23 @@ def _patch_psmnet(model, strict):
 
     cp.forward = types.MethodType(cost_forward, cp)
     dp.forward = types.MethodType(disp_forward, dp)
-    cp.cat_func = lambda l, r: ops.cat_fms(l, r, max_disp=int(max_disp // 4), start_disp=0, dilation=1)
+    cat_orig = cp.cat_func                                          # functools.partial(cat_fms, ...) of the reference
+
+    def cat_func(l, r):
+        if l.is_cuda or strict:                                     # strict: ops raises on CPU tensors
+            return ops.cat_fms(l, r, max_disp=int(max_disp // 4), start_disp=0, dilation=1)
+        return cat_orig(l, r)
+
+    cp.cat_func = cat_func
     sa = dp.disp_processor                                          # FasterSoftArgmin: keep the frozen Conv3d parameter
-    sa.forward = types.MethodType(
-        lambda self, cost: ops.faster_soft_argmin(cost, self.max_disp, self.start_disp, self.dilation, self.alpha,
-                                                  self.normalize), sa)
+    sa_orig = sa.forward
+
+    def sa_forward(self, cost):
+        if cost.is_cuda or strict:
+            return ops.faster_soft_argmin(cost, self.max_disp, self.start_disp, self.dilation, self.alpha, self.normalize)
+        return sa_orig(cost)
+
+    sa.forward = types.MethodType(sa_forward, sa)
     return model
 
 
