@@ -6,6 +6,8 @@ PyTorch is plumbing here: it owns device memory (tensor.data_ptr()) and the stre
 CPU path: a non-CUDA tensor raises, exactly like the reference's own native ops
 (stereo/modeling/models/nmrf/ops/src/ms_deform_attn.h:29-38 -> "Not implemented on the CPU").
 """
+import math
+
 import torch
 
 from . import _lib
@@ -394,8 +396,7 @@ def avgpool_pairs(x, axis):
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
     axis = axis % x.dim()
     n = x.shape[axis]
-    outer = int(torch.tensor(x.shape[:axis]).prod()) if axis > 0 else 1
-    inner = int(torch.tensor(x.shape[axis + 1:]).prod()) if axis + 1 < x.dim() else 1
+    outer, inner = math.prod(x.shape[:axis]), math.prod(x.shape[axis + 1:])
     y = torch.empty(x.shape[:axis] + (n // 2,) + x.shape[axis + 1:], dtype=torch.float32, device=x.device)
     _call("osb_avgpool_pairs_fwd", x.data_ptr(), y.data_ptr(), outer, n, inner, _stream())
     return y
