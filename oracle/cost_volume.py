@@ -10,6 +10,13 @@ Restates, on fp32 CPU tensors, with the same aten ops in the same order:
 * ``correlation_volume``     cost_volume.py:32-41
 * the IGEV-family unmasked-left concat variant  stereo/modeling/models/igev/submodule.py:216-227
 
+Restated ahead of their kernels ("remaining volume flavours"; product side: next round):
+
+* ``build_gwc_volume_normalized``  FoundationStereo's L2-normalised group correlation,
+  stereo/modeling/models/foundationstereo/core/submodule.py:422-446
+* ``coex_cost_volume``             CoExCostVolume.forward, cost_volume.py:9-29 (maxdisp+1 hypotheses, SUM over the group)
+* ``build_corr_volume``            cost_volume.py:95-105 (note its quirk: hypotheses d >= W correlate the UNSHIFTED images)
+
 Every volume is "for each disparity hypothesis d, pair left column w with right
 column w-d; columns w<d stay zero".  The reference spells that as a Python loop
 of slice assignments; the helper ``_hypotheses`` below yields the same slices.
@@ -88,3 +95,48 @@ def gwc_concat_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, maxdisp, num_groups):
     torch.cat((gwc_volume, concat_volume), 1)."""
     return torch.cat((build_gwc_volume(ref_gwc, tgt_gwc, maxdisp, num_groups),
                       build_concat_volume(ref_cat, tgt_cat, maxdisp)), 1)
+
+
+# ------------------------------------------------------------------------------------ SURVEY.md section 8(f) row 4
+def groupwise_correlation_normalized(fea1, fea2, num_groups):
+    """FoundationStereo: each group's channel vector is L2-normalised (F.normalize, eps 1e-12) before the dot product
+    (foundationstereo/core/submodule.py:422-431: "Divide first for numerical stability")."""
+    b, c, h, w = fea1.shape
+    if c % num_groups != 0:
+        raise AssertionError("C:%d, num_groups:%d" % (c, num_groups))
+    k = c // num_groups
+    a = fea1.reshape(b, num_groups, k, h, w)
+    bb = fea2.reshape(b, num_groups, k, h, w)
+    return (torch.nn.functional.normalize(a.float(), dim=2) * torch.nn.functional.normalize(bb.float(), dim=2)).sum(dim=2)
+
+
+def build_gwc_volume_normalized(ref_fea, tgt_fea, maxdisp, num_groups):
+    b, c, h, w = ref_fea.shape
+    vol = ref_fea.new_zeros((b, num_groups, maxdisp, h, w))
+    for idx, d, lc, rc in _hypotheses(w, range(maxdisp)):
+        vol[:, :, idx, :, lc] = groupwise_correlation_normalized(ref_fea[..., lc], tgt_fea[..., rc], num_groups)
+    return vol.contiguous()
+
+
+def coex_cost_volume(x, y, maxdisp, group=1):
+    """CoExCostVolume(maxdisp, group)(x, y): (B, group, maxdisp + 1, H, W); cost[b, g, d, h, w] = sum_k x[.., w] * y[.., w - d]
+    with zero padding on the left (cost_volume.py:9-29: left pad, unfold windows of maxdisp+1 columns, flip)."""
+    b, c, h, w = x.shape
+    n = maxdisp + 1
+    yp = torch.nn.functional.pad(y, (maxdisp, 0, 0, 0))
+    win = torch.nn.functional.unfold(yp, (1, n), 1, 0, 1).reshape(b, group, c // group, n, h, w)
+    cost = (x.reshape(b, group, c // group, 1, h, w) * win).sum(2)
+    return torch.flip(cost, dims=[2])
+
+
+def build_corr_volume(img_left, img_right, max_disp):
+    """cost_volume.py:95-105.  The reference's condition is ``(i > 0) & (i < W)``: hypotheses beyond the image width fall
+    into the else branch and correlate the two images WITHOUT a shift (kept as is -- parity, not repair)."""
+    b, c, h, w = img_left.shape
+    vol = img_left.new_zeros((b, max_disp, h, w))
+    for i in range(max_disp):
+        if 0 < i < w:
+            vol[:, i, :, i:] = (img_left[:, :, :, i:] * img_right[:, :, :, :w - i]).mean(dim=1)
+        else:
+            vol[:, i, :, :] = (img_left * img_right).mean(dim=1)
+    return vol.contiguous()

@@ -11,6 +11,9 @@
   psmnet_cost_processor.py:203-214 + psmnet_disp_processor.py:64-73
   (align_corners=True)
 * ``epe_per_image``         stereo/evaluation/metric_per_image.py:32-41
+* ``disparity_regression_interval`` / ``disparity_regression_values``  the strided and explicit-hypothesis expectations of
+  IGEV++ (stereo/modeling/models/igevpp/submodule.py:147-151) and CasStereo (casnet/submodule.py:22-24): SURVEY.md section
+  8f row 4, restated ahead of their kernels
 """
 import torch
 import torch.nn.functional as F
@@ -61,3 +64,19 @@ def epe_per_image(disp_pred, disp_gt, mask):
     valid = mask.sum(dim=[1, 2])
     epe = total / valid
     return torch.where(valid > 0, epe, torch.zeros_like(epe))
+
+
+# ------------------------------------------------------------------------------------ SURVEY.md section 8(f) row 4
+def disparity_regression_interval(prob, maxdisp, interval):
+    """IGEV++: hypotheses 0, interval, 2*interval, ... < maxdisp (igevpp/submodule.py:147-151)."""
+    if prob.dim() != 4:
+        raise AssertionError("expected (B, D, H, W)")
+    values = torch.arange(0, maxdisp, interval, dtype=prob.dtype, device=prob.device).view(1, maxdisp // interval, 1, 1)
+    return torch.sum(prob * values, 1, keepdim=True)
+
+
+def disparity_regression_values(prob, disp_values):
+    """CasStereo: per-pixel hypothesis planes disp_values (B, D, H, W) (casnet/submodule.py:22-24)."""
+    if prob.dim() != 4:
+        raise AssertionError("expected (B, D, H, W)")
+    return torch.sum(prob * disp_values, 1, keepdim=False)

@@ -128,3 +128,21 @@ def test_geo_lookup(name):
 def test_context_upsample():
     g = load_golden("context_upsample")
     assert torch.equal(ogeo.context_upsample(g["disp_low"], g["up_weights"], g["scale"]), g["out"])
+
+
+def test_row4_volume_and_regression_flavours():
+    """oracle restatements pinned against the reference ahead of their kernels."""
+    g = load_golden("gwc_normalized")
+    out = ocv.build_gwc_volume_normalized(g["left"], g["right"], g["maxdisp"], g["groups"])
+    assert torch.equal(out, g["out"]) and out.abs().max() <= 1.0 + 1e-6          # cosine similarities
+    g = load_golden("coex_volume")
+    assert torch.equal(ocv.coex_cost_volume(g["left"], g["right"], g["maxdisp"], g["group"]), g["out"])
+    assert g["out"].shape[2] == g["maxdisp"] + 1
+    g = load_golden("corr_volume_quirk")
+    out = ocv.build_corr_volume(g["left"], g["right"], g["maxdisp"])
+    assert torch.equal(out, g["out"])
+    w = g["left"].shape[-1]
+    assert torch.equal(out[:, w], out[:, 0])                                     # hypotheses d >= W correlate the unshifted images
+    g = load_golden("regression_flavours")
+    assert torch.equal(oreg.disparity_regression_interval(g["prob"], g["maxdisp"], g["interval"]), g["out_interval"])
+    assert torch.equal(oreg.disparity_regression_values(g["prob"], g["values"]), g["out_values"])

@@ -250,6 +250,40 @@ def lookups():
     save("context_upsample", disp_low=low, up_weights=wts, scale=4, out=ref)
 
 
+def flavours():
+    """the remaining volume / regression flavours (oracle pinned ahead of the kernels)."""
+    import torch.nn.functional as F
+    rcv = shim.load("stereo.modeling.cost_volume.cost_volume")
+    import types
+    for missing in ("trimesh", "imageio", "open3d", "transformations"):     # imported at module level by foundationstereo/Utils.py,
+        if missing not in sys.modules:                                      # never dereferenced by the two functions used here
+            try:
+                __import__(missing)
+            except Exception:
+                sys.modules[missing] = types.ModuleType(missing)
+    rfs = shim.load("stereo.modeling.models.foundationstereo.core.submodule")
+    rpp = shim.load("stereo.modeling.models.igevpp.submodule")
+    rcas = shim.load("stereo.modeling.models.casnet.submodule")
+    l, r = rnd(80, 2, 24, 3, 17), rnd(81, 2, 24, 3, 17)
+    ref = rfs.build_gwc_volume(l, r, 9, 4)
+    must_equal(ref, ocv.build_gwc_volume_normalized(l, r, 9, 4), "normalised gwc volume")
+    save("gwc_normalized", left=l, right=r, maxdisp=9, groups=4, out=ref)
+    ref = rcv.CoExCostVolume(6, group=3)(l, r)
+    must_equal(ref, ocv.coex_cost_volume(l, r, 6, 3), "CoEx volume")
+    save("coex_volume", left=l, right=r, maxdisp=6, group=3, out=ref)
+    ls, rs = rnd(82, 1, 5, 2, 6), rnd(83, 1, 5, 2, 6)
+    ref = rcv.build_corr_volume(ls, rs, 9)                          # 9 > W = 6: exercises the unshifted else-branch
+    must_equal(ref, ocv.build_corr_volume(ls, rs, 9), "corr volume (d >= W quirk)")
+    save("corr_volume_quirk", left=ls, right=rs, maxdisp=9, out=ref)
+    prob = F.softmax(rnd(84, 2, 12, 3, 5, scale=2.0), dim=1)
+    ref = rpp.disparity_regression(prob, 48, 4)
+    must_equal(ref, oreg.disparity_regression_interval(prob, 48, 4), "interval regression")
+    vals = rnd(85, 2, 12, 3, 5).abs() * 30
+    ref2 = rcas.disparity_regression(prob, vals)
+    must_equal(ref2, oreg.disparity_regression_values(prob, vals), "explicit-hypothesis regression")
+    save("regression_flavours", prob=prob, maxdisp=48, interval=4, out_interval=ref, values=vals, out_values=ref2)
+
+
 if __name__ == "__main__":
     if not shim.available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the authoring container")
@@ -259,4 +293,5 @@ if __name__ == "__main__":
     modules()
     models()
     lookups()
+    flavours()
     print("all oracle restatements bit-equal to the reference; golden vectors written to", OUT)
