@@ -146,3 +146,16 @@ def test_row4_volume_and_regression_flavours():
     g = load_golden("regression_flavours")
     assert torch.equal(oreg.disparity_regression_interval(g["prob"], g["maxdisp"], g["interval"]), g["out_interval"])
     assert torch.equal(oreg.disparity_regression_values(g["prob"], g["values"]), g["out_values"])
+
+
+def test_lightstereo_aggregation():
+    """the restated MobileNetV2-block hourglass + strip attention reproduces the reference output."""
+    from oracle import lightstereo as olight
+    g = load_golden("lightstereo_aggregation")
+    m = olight.Aggregation(in_channels=12, left_att=True, blocks=[1, 2, 2], expanse_ratio=4, backbone_channels=[10, 14, 18]).eval()
+    sd = si.seeded_state_dict(m.state_dict(), seed=g["seed"])
+    assert abs(checksum(sd) - g["sd_checksum"]) <= 1e-6 * g["sd_checksum"]
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out = m(g["x"], [g["f0"], g["f1"], g["f2"]])[0]
+    assert torch.equal(out, g["out"]) and out.std() > 1e-3

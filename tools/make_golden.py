@@ -25,6 +25,7 @@ from oracle import _reference_shim as shim                      # noqa: E402
 from oracle import aggregation as oagg                          # noqa: E402
 from oracle import cost_volume as ocv                           # noqa: E402
 from oracle import geo_lookup as ogeo                           # noqa: E402
+from oracle import lightstereo as olight                        # noqa: E402
 from oracle import models as omodels                            # noqa: E402
 from oracle import regression as oreg                           # noqa: E402
 from oracle import seeded_init as si                            # noqa: E402
@@ -250,6 +251,25 @@ def lookups():
     save("context_upsample", disp_low=low, up_weights=wts, scale=4, out=ref)
 
 
+def lightstereo():
+    """LightStereo's 2D aggregation (cfgs/lightstereo: in_channels 48, blocks [4, 8, 14], expanse 4
+    in LightStereo-M; a reduced [1, 2, 2] stack with every block kind keeps the fixture small)."""
+    ragg = shim.load("stereo.modeling.models.lightstereo.aggregation")
+    with torch.no_grad():
+        args = dict(in_channels=12, left_att=True, blocks=[1, 2, 2], expanse_ratio=4, backbone_channels=[10, 14, 18])
+        ref, mine = ragg.Aggregation(**args).eval(), olight.Aggregation(**args).eval()
+        assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+        sd = si.seeded_state_dict(ref.state_dict(), seed=5)
+        ref.load_state_dict(sd), mine.load_state_dict(sd)
+        x = rnd(86, 2, 12, 8, 20)
+        feats = [rnd(87, 2, 10, 8, 20), rnd(88, 2, 14, 4, 10), rnd(89, 2, 18, 2, 5)]
+        y = ref(x, feats)[0]
+        must_equal(y, mine(x, feats)[0], "LightStereo aggregation")
+        if not y.std() > 1e-3:
+            raise SystemExit("degenerate LightStereo fixture (std %g)" % y.std())
+        save("lightstereo_aggregation", x=x, f0=feats[0], f1=feats[1], f2=feats[2], out=y, seed=5, sd_checksum=checksum(sd))
+
+
 def flavours():
     """the remaining volume / regression flavours (oracle pinned ahead of the kernels)."""
     import torch.nn.functional as F
@@ -294,4 +314,5 @@ if __name__ == "__main__":
     models()
     lookups()
     flavours()
+    lightstereo()
     print("all oracle restatements bit-equal to the reference; golden vectors written to", OUT)
