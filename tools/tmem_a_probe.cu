@@ -81,9 +81,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 constexpr int N = 96, K = 32;
 constexpr uint32_t A_COL = 256;      // A tile lives in TMEM columns [256, 288)
 
-// mode 0: correctness (A from TMEM);  mode 1: rate with A from shared memory;  mode 2: rate with A from TMEM
-__global__ void __launch_bounds__(128) probe(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, int mode,
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// MODE 0: correctness (A from TMEM);  MODE 1: rate with A from shared memory;  MODE 2: rate with A from TMEM.
+// The issue loop is warp-uniform with an elected lane, as in the product kernels (an `if (t == 0)` body makes ptxas wrap every
+// descriptor in R2UR broadcast loops and the measurement becomes issue-bound: 117 clk/MMA in the first version of this probe).
+template <int MODE>
+__global__ void __launch_bounds__(128) probe(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d,
                                              long long* cycles) {
+  constexpr int mode = MODE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sa = smem;                    // 128 rows x 128 B, SWIZZLE_128B
@@ -125,29 +135,30 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ a, const 
   const uint32_t idesc = idesc_tf32(128, N);
   const uint64_t da = desc_sw128(smem_u32(sa)), db = desc_sw128(smem_u32(sb));
   if (warp == 0) {
-    long long t0 = 0, t1 = 0;
+    long long t0 = 0;
     if (mode == 0) {
-      if (t == 0) {
+      if (elect_one()) {
+#pragma unroll
         for (int ks = 0; ks < K / 8; ++ks) mma_ts(tmem, tmem + A_COL + ks * 8, db + 2 * ks, idesc, ks > 0);
         commit(bar);
       }
     } else {
-      if (t == 0) {
-        t0 = clock64();
-        for (int it = 0; it < 2000; ++it)
+      t0 = clock64();
+      for (int it = 0; it < 2000; ++it) {
+        if (elect_one()) {
+#pragma unroll
           for (int ks = 0; ks < K / 8; ++ks) {
             if (mode == 1) mma_ss(tmem, da + 2 * ks, db + 2 * ks, idesc, 1);
             else mma_ts(tmem, tmem + A_COL + ks * 8, db + 2 * ks, idesc, 1);
           }
-        commit(bar);
+        }
+        __syncwarp();
       }
+      if (elect_one()) commit(bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    if (t == 0 && mode != 0) {
-      t1 = clock64();
-      *cycles = t1 - t0;
-    }
+    if (t == 0 && mode != 0) *cycles = clock64() - t0;
   }
   fence_before();
   __syncthreads();
@@ -160,6 +171,60 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ a, const 
       for (int i = 0; i < 16; ++i) d[t * N + c0 + i] = v[i];
     }
   }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- exploratory: where does tcgen05.cp put shared-memory bytes?  smem holds float(i) at float index i; after
+// `tcgen05.cp.cta_group::1.<shape> [tmem], desc` every thread reads its lane's first 8 columns back and a few lanes are
+// printed, for several descriptor settings (swizzle mode, leading / stride byte offsets).  Picks the layout for staging A
+// tiles with ONE bulk copy per tile instead of per-thread tcgen05.st (and instead of 3 smem reads per k-step by the MMA).
+__global__ void __launch_bounds__(128) cp_probe(int shape, uint64_t desc_hi_bits, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* src = reinterpret_cast<float*>(smem);                       // 16 KB = 4096 floats
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, t = threadIdx.x;
+  for (int i = t; i < 4096; i += 128) src[i] = (float)i;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *slot;
+  {   // clear the destination columns so untouched cells are recognisable (-1)
+    float m1[8] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
+    tmem_st8(tmem + ((uint32_t)(warp * 32) << 16), m1);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (t == 0) {
+    const uint64_t desc = (uint64_t)((smem_u32(src) & 0x3FFFF) >> 4) | desc_hi_bits;
+    if (shape == 0) asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem), "l"(desc) : "memory");
+    else asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tmem), "l"(desc) : "memory");
+    commit(bar);
+  }
+  if (warp == 0) {
+    __syncwarp();
+    mbar_wait(bar, 0);
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  float v[16];
+  tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+  for (int i = 0; i < 8; ++i) out[t * 8 + i] = v[i];
   fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -187,8 +252,10 @@ int main() {
   CHECK(cudaMemcpy(da, ha, 128 * K * 4, cudaMemcpyHostToDevice));
   CHECK(cudaMemcpy(db, hb, N * K * 4, cudaMemcpyHostToDevice));
   const size_t smem = 1024 + 2 * 128 * 128 + 64;
-  CHECK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe<<<1, 128, smem>>>(da, db, dd, 0, dc);
+  CHECK(cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CHECK(cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CHECK(cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe<0><<<1, 128, smem>>>(da, db, dd, dc);
   CHECK(cudaDeviceSynchronize());
   CHECK(cudaMemcpy(hd, dd, 128 * N * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0;
@@ -202,10 +269,45 @@ int main() {
          hd[0], hd[1], hd[2], hd[3]);
   for (int mode = 1; mode <= 2; ++mode) {
     long long cyc = 0;
-    probe<<<1, 128, smem>>>(da, db, dd, mode, dc);
+    if (mode == 1) probe<1><<<1, 128, smem>>>(da, db, dd, dc);
+    else probe<2><<<1, 128, smem>>>(da, db, dd, dc);
     CHECK(cudaDeviceSynchronize());
     CHECK(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
     printf("rate  A from %s:  %.1f cycles per M128 x N%d x K8 MMA\n", mode == 1 ? "shared memory" : "tensor memory ", (double)cyc / 8000.0, N);
+  }
+  // ---- tcgen05.cp layout exploration
+  float* dout;
+  CHECK(cudaMalloc(&dout, 128 * 8 * 4));
+  float hout[128 * 8];
+  CHECK(cudaFuncSetAttribute(cp_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 16384 + 64));
+  struct Cfg { const char* name; int shape; uint64_t hi; };
+  const uint64_t V1 = (uint64_t)1 << 46;
+  auto lbo = [](uint64_t b) { return (uint64_t)(b >> 4) << 16; };
+  auto sbo = [](uint64_t b) { return (uint64_t)(b >> 4) << 32; };
+  const Cfg cfgs[] = {
+      {"128x256b swizzle=none LBO=16   SBO=256 ", 0, V1 | lbo(16) | sbo(256)},
+      {"128x256b swizzle=none LBO=128  SBO=256 ", 0, V1 | lbo(128) | sbo(256)},
+      {"128x256b swizzle=none LBO=256  SBO=128 ", 0, V1 | lbo(256) | sbo(128)},
+      {"128x256b swizzle=32B  LBO=16   SBO=256 ", 0, V1 | lbo(16) | sbo(256) | ((uint64_t)6 << 61)},
+      {"128x256b swizzle=128B LBO=16   SBO=1024", 0, V1 | lbo(16) | sbo(1024) | ((uint64_t)2 << 61)},
+      {"128x128b swizzle=none LBO=16   SBO=128 ", 1, V1 | lbo(16) | sbo(128)},
+      {"128x128b swizzle=128B LBO=16   SBO=1024", 1, V1 | lbo(16) | sbo(1024) | ((uint64_t)2 << 61)},
+  };
+  for (const Cfg& c : cfgs) {
+    cp_probe<<<1, 128, 1024 + 16384 + 64>>>(c.shape, c.hi, dout);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("cp %s: kernel failed: %s\n", c.name, cudaGetErrorString(e));
+      return 1;                                   // a fault poisons the context: stop here, rerun with the entry removed
+    }
+    CHECK(cudaMemcpy(hout, dout, sizeof(hout), cudaMemcpyDeviceToHost));
+    printf("cp %s: float index found at (lane, col 0..7)\n", c.name);
+    const int lanes[] = {0, 1, 2, 7, 8, 9, 31, 32, 64, 127};
+    for (int l : lanes) {
+      printf("   lane %3d:", l);
+      for (int i = 0; i < 8; ++i) printf(" %6.0f", hout[l * 8 + i]);
+      printf("\n");
+    }
   }
   return 0;
 }
