@@ -150,6 +150,13 @@ def disparity_regression(x, maxdisp, keepdim=True):
     return softargmin(x, maxdisp, keepdim=keepdim, normalize=False)
 
 
+def disparity_regression_interval(prob, maxdisp, interval):
+    """IGEV++'s strided expectation (igevpp/submodule.py:147-151): sum_k prob[:, k] * (k * interval) over the
+    maxdisp // interval hypotheses 0, interval, 2*interval, ...; prob is already normalised.  -> (B, 1, H, W)."""
+    assert len(prob.shape) == 4
+    return softargmin(prob, maxdisp // interval, keepdim=True, start=0.0, step=float(interval), normalize=False)
+
+
 def faster_soft_argmin(cost_volume, max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True):
     """FasterSoftArgmin.forward, psmnet/psmnet_disp_processor.py:51-74 -> (B, H, W)."""
     if cost_volume.dim() != 4:

@@ -438,3 +438,12 @@ def test_tc_kernels_partial_blocks_many_items(ops):
         got = ops.conv3d_k3_tc(ops.to_ndhwc(x), ops.pack_tc_weight(wt), sc, sh, res, ops.ACT_RELU, out_ndhwc=False, res_ndhwc=False)
     torch.cuda.synchronize()
     assert ((got - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8(f) row 4 (first piece)
+def test_disparity_regression_interval_golden(ops):
+    """IGEV++'s strided expectation on the soft-argmin kernel (normalize off, step = interval) vs the reference output."""
+    g = load_golden("regression_flavours")
+    out = ops.disparity_regression_interval(dev(g["prob"]), g["maxdisp"], g["interval"])
+    assert out.shape == g["out_interval"].shape
+    assert_close(out, g["out_interval"], 1e-5 * g["maxdisp"], "interval regression")
