@@ -44,6 +44,16 @@ int osb_abi_version(void);
 const char* osb_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports it). */
 uint64_t osb_launch_count(void);
+/* 3xTF32 operand-split policy of the tensor-core convolutions (process-wide; returns the previous value):
+ *   1 (default)  hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi)   -- unbiased
+ *   0            hi = x truncated by the MMA itself, lo = x - trunc(x)                      -- round 1, biased towards zero;
+ *                kept only so the parity bisect (tools/bisect_parity.py) can reproduce it.
+ * Weights must be packed with the same policy (openstereo_b200/ops.py: pack_tc_weight). */
+int osb_set_tf32_split(int mode);
+/* Expected round-towards-zero loss per accumulating tcgen05.mma, undone by the conv epilogues (csrc/tc_common.cuh: rz_kappa;
+ * DESIGN.md section 4.3).  Process-wide; returns the previous value; 0 switches the correction off.  The default is the
+ * constant measured on B200 (profiles/r2_rz_kappa.md); the setter exists for that calibration. */
+float osb_set_rz_kappa(float kappa);
 
 /* ---------------------------------------------------------------- cost-volume constructors --- */
 

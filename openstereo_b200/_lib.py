@@ -57,6 +57,10 @@ def _load():
     lib.osb_abi_version.restype = ctypes.c_int
     lib.osb_last_error.restype = ctypes.c_char_p
     lib.osb_launch_count.restype = ctypes.c_uint64
+    lib.osb_set_tf32_split.argtypes = [ctypes.c_int]
+    lib.osb_set_tf32_split.restype = ctypes.c_int
+    lib.osb_set_rz_kappa.argtypes = [ctypes.c_float]
+    lib.osb_set_rz_kappa.restype = ctypes.c_float
     for name, argtypes in SIGNATURES.items():
         try:
             fn = getattr(lib, name)

@@ -17,6 +17,34 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_tf32_split{1};
+int tf32_split_mode() { return g_tf32_split.load(std::memory_order_relaxed); }
+
+static std::atomic<float> g_rz_kappa{1.57e-8f};   // measured on B200: profiles/r2_rz_kappa.md
+float rz_kappa() { return g_rz_kappa.load(std::memory_order_relaxed); }
+
+int device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return dev;
+}
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  const int dev = device_index();
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = 148;
+  }
+  cache[dev & 63].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
@@ -72,4 +100,14 @@ extern "C" {
 int osb_abi_version(void) { return 1; }
 const char* osb_last_error(void) { return osb::g_error; }
 uint64_t osb_launch_count(void) { return osb::g_launches.load(std::memory_order_relaxed); }
+float osb_set_rz_kappa(float kappa) {
+  const float old = osb::g_rz_kappa.load(std::memory_order_relaxed);
+  if (kappa >= 0.f && kappa < 1e-6f) osb::g_rz_kappa.store(kappa, std::memory_order_relaxed);
+  return old;
+}
+int osb_set_tf32_split(int mode) {
+  const int old = osb::g_tf32_split.load(std::memory_order_relaxed);
+  if (mode == 0 || mode == 1) osb::g_tf32_split.store(mode, std::memory_order_relaxed);
+  return old;
+}
 }

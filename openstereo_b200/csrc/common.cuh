@@ -13,6 +13,14 @@ namespace osb {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> OSB_OK / OSB_ECUDA (+message)
+int device_index();                   // current CUDA device (0 when the query fails)
+int sm_count();                       // multiprocessors of the CURRENT device (cached per device)
+// Per-device "already configured" flag: cudaFuncSetAttribute is per device, a process may drive several
+// (DataParallel, model.to('cuda:1')); a plain `static bool` would configure only the first one.
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool& here() { return done[device_index() & 63]; }
+};
 
 #define OSB_REQUIRE(cond, ...)          \
   do {                                  \

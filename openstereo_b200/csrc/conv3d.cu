@@ -534,10 +534,10 @@ template <int S, int TCO, int NCG, int TD, int TH, int CI>
 static int launch_conv_k3(ConvParams& p, cudaStream_t stream) {
   using C = ConvCfg<S, TCO, NCG, TD, TH, CI>;
   auto kernel = conv3d_k3_kernel<S, TCO, NCG, TD, TH, CI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     if (int rc = set_smem(kernel, C::SMEM, "conv3d_k3")) return rc;
-    configured = true;
+    configured.here() = true;
   }
   p.tiles_w = (p.Wo + C::TW - 1) / C::TW;
   p.tiles_h = (p.Ho + TH - 1) / TH;
@@ -553,10 +553,10 @@ template <int KS, int CI>
 static int launch_deconv(ConvParams& p, cudaStream_t stream) {
   using C = DeconvCfg<KS, CI>;
   auto kernel = deconv3d_kernel<KS, CI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     if (int rc = set_smem(kernel, C::SMEM, "deconv3d")) return rc;
-    configured = true;
+    configured.here() = true;
   }
   p.tiles_w = (p.Wo + C::TW - 1) / C::TW;
   p.tiles_h = (p.Ho + C::TH - 1) / C::TH;
@@ -673,14 +673,14 @@ int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const 
   OSB_REQUIRE(blocks < (1ll << 31), "conv3d_k3_c1_ndhwc: too many tiles");
   constexpr size_t smem = ((size_t)(C1_TD + 2) * (C1_TH + 2) * (C1_TW + 2) * (32 + 4) + 27 * 32) * sizeof(float);
   auto kernel = conv3d_k3_c1_ndhwc_kernel<32>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv3d_k3_c1_ndhwc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = true;
+    configured.here() = true;
   }
   kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(x_ndhwc, w_taps, scale, shift, y, D, H, W, tiles_w, tiles_h, tiles_d);
   count_launch();

@@ -54,6 +54,8 @@ struct TcParams {
   float* y;
   int B, D, H, Cin, Cout;
   int act;
+  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
+  float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -238,8 +240,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       for (int j = 0; j < 8; ++j) {
         const int m = vcol + 16 * j;                  // tile row = image column
         const int off = m * 128 + ((c16 ^ (m & 7)) << 4);   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-        *reinterpret_cast<float4*>(hi + off) = v[j];
-        *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+        float4 vh, vl;
+        tf32_split4(v[j], p.split, vh, vl);
+        *reinterpret_cast<float4*>(hi + off) = vh;
+        *reinterpret_cast<float4*>(lo + off) = vl;
       }
       fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_ready[s]);
@@ -273,6 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const int b = it / (p.hblocks * p.D);
       const int h0 = hb * TC_TILES;
       const int ntiles = min(TC_TILES, p.H - h0);
+      // MMAs each P_kw accumulator received: (existing kd planes) x chunks x 3 kh x k-steps x 3 split terms
+      const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (d + 1 < p.D)) * nchunk * 3 * (TC_KC / 8) * 3);
       // D[m] = P0[m-1] + P1[m] + P2[m+1], tile by tile as the MMA warp releases them
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_relaxed(&acc_full[t], itc & 1);
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);
           left = (lane == 0) ? xl[i] : left;          // m-1 lives in the previous quadrant (zero at the image edge)
           right = (lane == 31) ? xr[i] : right;       // m+1 lives in the next quadrant
-          out[i] = (left + __uint_as_float(raw[1][i])) + right;
+          out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
         }
         if (p.out_ndhwc && (!p.residual || p.res_ndhwc)) {       // coalesced channels-last path (BN/residual/act inside)
           static_assert(COUT == 32, "one 32-channel chunk per voxel");
@@ -428,20 +434,16 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
   const size_t smem = 1024 + 2 * (size_t)TC_STAGES * TC_ROW_BYTES + 3 * 2 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
                       3 * COUT * 4 + TP_BYTES;
   auto kernel = conv3d_tc_kernel<COUT>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv3d_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = true;
+    configured.here() = true;
   }
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    (void)cudaGetLastError();
-    sms = 148;
-  }
+  const int sms = sm_count();
   const int grid = p.items < sms ? p.items : sms;   // persistent: one CTA per SM (it owns all 512 TMEM columns)
   kernel<<<grid, TC_THREADS, smem, stream>>>(p);
   count_launch();
@@ -497,6 +499,7 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float
   TcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.Cout = Cout, p.act = act;
+  p.split = tf32_split_mode(), p.kappa = rz_kappa();
   p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;

@@ -22,6 +22,8 @@ struct TcdcParams {
   float* y;
   int B, D, H, Cin;        // INPUT extent D x H x W; output is 2D x 2H x 2W
   int act;
+  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
+  float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -219,8 +221,10 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int off = swz_offset<KC>(v0 + VPL * j, c);
-        *reinterpret_cast<float4*>(hi + off) = v[j];
-        *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+        float4 vh, vl;
+        tf32_split4(v[j], p.split, vh, vl);
+        *reinterpret_cast<float4*>(hi + off) = vh;
+        *reinterpret_cast<float4*>(lo + off) = vl;
       }
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
@@ -262,6 +266,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
       const ItemDc w = decode_dc<C>(p, it);
       const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
+      // tap pairs of this parity class: (1 or 2 kd) x (1 or 2 kh); each adds chunks x k-steps x 3 MMAs (tc_common.cuh: rz_kappa)
+      const float corr = 1.f + p.kappa * (float)(((w.od & 1) + 1) * (w.ph + 1) * nchunk * C::KSTEPS * 3);
       for (int t = 0; t < ntiles; ++t) {
         const int j = w.j0 + t * C::R + rr;
         const bool live = j < p.H;
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           for (int i = 0; i < 32; ++i) {
             float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
             right = (lane == 31) ? xr[i] : right;                                        // zero beyond the last input column
-            ev[i] = __uint_as_float(raw[0][i]);
-            od_[i] = __uint_as_float(raw[1][i]) + right;
+            ev[i] = __uint_as_float(raw[0][i]) * corr;
+            od_[i] = (__uint_as_float(raw[1][i]) + right) * corr;
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride
@@ -417,24 +423,20 @@ template <int COUT, int KC, int W, int TILES>
 static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
   using C = TcdcCfg<COUT, KC, W, TILES>;
   auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv3d_tcg: cannot reserve %zu bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = true;
+    configured.here() = true;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
   const long long items = (long long)p.B * (2 * p.D) * 2 * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcdc: too many work items");
   p.items = (int)items;
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    (void)cudaGetLastError();
-    sms = 148;
-  }
+  const int sms = sm_count();
   const int grid = p.items < sms ? p.items : sms;
   kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
   count_launch();
@@ -470,6 +472,7 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const flo
   TcdcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.split = tf32_split_mode(), p.kappa = rz_kappa();
   cudaStream_t s = (cudaStream_t)stream;
   if (W == 32) return launch_tcdc<64, 16, 32, 2>(p, s);
   return launch_tcdc<32, 16, 64, 5>(p, s);

@@ -23,6 +23,8 @@ struct TcgParams {
   float* y;
   int B, D, H, Cin;
   int act;
+  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
+  float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -216,8 +218,10 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int off = swz_offset<KC>(v0 + VPL * j, c);
-        *reinterpret_cast<float4*>(hi + off) = v[j];
-        *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+        float4 vh, vl;
+        tf32_split4(v[j], p.split, vh, vl);
+        *reinterpret_cast<float4*>(hi + off) = vh;
+        *reinterpret_cast<float4*>(lo + off) = vl;
       }
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
       const int b = it / (p.hblocks * p.D);
       const int h0 = hb * C::HBLK;
       const int ntiles = min(TILES, (p.H - h0 + C::R - 1) / C::R);
+      const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (d + 1 < p.D)) * nchunk * 3 * C::KSTEPS * 3);   // tc_common.cuh: rz_kappa
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
             float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), DIL);
             left = (lane < DIL) ? xl[i] : left;       // column w-DIL (zero at the image edge)
             right = (lane >= 32 - DIL) ? xr[i] : right;   // column w+DIL
-            out[i] = (left + __uint_as_float(raw[1][i])) + right;
+            out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
@@ -391,24 +396,20 @@ template <int COUT, int KC, int W, int TILES, int DIL = 1>
 static int launch_tcg(TcgParams& p, cudaStream_t stream) {
   using C = TcgCfg<COUT, KC, W, TILES, DIL>;
   auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv3d_tcg: cannot reserve %zu bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = true;
+    configured.here() = true;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
   const long long items = (long long)p.B * p.D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcg: too many work items");
   p.items = (int)items;
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    (void)cudaGetLastError();
-    sms = 148;
-  }
+  const int sms = sm_count();
   const int grid = p.items < sms ? p.items : sms;
   kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
   count_launch();
@@ -430,6 +431,7 @@ int launch_tcg_dispatch(const float* x, const float* w, const float* scale, cons
   TcgParams p{};
   p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.split = tf32_split_mode(), p.kappa = rz_kappa();
   if (Cin % 16 != 0 || Cin < 16) return -1;
   if (W == 64 && Cout == 64) return launch_tcg<64, 16, 64, 2>(p, stream);
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
@@ -445,6 +447,7 @@ int launch_tcg_dilated2(const float* x, const float* w, const float* scale, cons
   TcgParams p{};
   p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = 1, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.split = tf32_split_mode(), p.kappa = rz_kappa();
   if (Cin % 16 != 0 || Cin < 16) return -1;
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1, 2>(p, stream);
   return -1;

@@ -22,6 +22,8 @@ struct Tcs2Params {
   float* y;
   int B, D, H, Cin;        // INPUT extent D x H x (2*WO); output is D/2 x H/2 x WO
   int act;
+  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
+  float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -200,8 +202,10 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int off = swz_offset<KC>(v0 + VPL * j, c);
-        *reinterpret_cast<float4*>(hi + off) = v[j];
-        *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(v[j].x), tf32_lo(v[j].y), tf32_lo(v[j].z), tf32_lo(v[j].w));
+        float4 vh, vl;
+        tf32_split4(v[j], p.split, vh, vl);
+        *reinterpret_cast<float4*>(hi + off) = vh;
+        *reinterpret_cast<float4*>(lo + off) = vl;
       }
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       const int b = it / (p.hblocks * Do);
       const int h0 = hb * C::HBLK;
       const int ntiles = min(TILES, (Ho - h0 + C::R - 1) / C::R);
+      // input planes 2d-1, 2d, 2d+1: the first is missing for d = 0 (tc_common.cuh: rz_kappa)
+      const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (2 * d + 1 < p.D)) * nchunk * 3 * C::KSTEPS * 3);
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           for (int i = 0; i < 32; ++i) {
             float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[1][i]), 1);   // P0 of output column ow-1
             left = (lane == 0) ? xl[i] : left;                                        // zero at ow = 0 (left padding)
-            out[i] = (left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i]);
+            out[i] = ((left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i])) * corr;
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
@@ -375,24 +381,20 @@ template <int COUT, int KC, int W, int TILES>
 static int launch_tcs2(Tcs2Params& p, cudaStream_t stream) {
   using C = Tcs2Cfg<COUT, KC, W, TILES>;
   auto kernel = conv3d_tcs2_kernel<COUT, KC, W, TILES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) {
       set_error("conv3d_tcg: cannot reserve %zu bytes of shared memory: %s", C::SMEM, cudaGetErrorString(e));
       return OSB_ECUDA;
     }
-    configured = true;
+    configured.here() = true;
   }
   p.hblocks = (p.H / 2 + C::HBLK - 1) / C::HBLK;
   const long long items = (long long)p.B * (p.D / 2) * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcs2: too many work items");
   p.items = (int)items;
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    (void)cudaGetLastError();
-    sms = 148;
-  }
+  const int sms = sm_count();
   const int grid = p.items < sms ? p.items : sms;
   kernel<<<grid, C::THREADS, C::SMEM, stream>>>(p);
   count_launch();
@@ -429,6 +431,7 @@ int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const float* w_split, const fl
   Tcs2Params p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.split = tf32_split_mode(), p.kappa = rz_kappa();
   cudaStream_t s = (cudaStream_t)stream;
   if (W == 128 && Cout == 64) return launch_tcs2<64, 16, 64, 2>(p, s);
   if (W == 64 && Cout == 64) return launch_tcs2<64, 16, 32, 2>(p, s);

@@ -75,7 +75,33 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ float tf32_lo(float a) { return a - __uint_as_float(__float_as_uint(a) & 0xffffe000u); }
+// 3xTF32 operand split.  A kind::tf32 MMA reads only the top 19 bits of an fp32 operand (truncation), so the split is done
+// here, before the operand reaches shared memory:
+//   mode 0 (round 1, kept for the bisect): hi = x (hardware truncates), lo = x - trunc(x); both truncations and the dropped
+//           lo*lo term shrink every product towards zero -- a BIAS of up to 2^-19 per product that adds up coherently;
+//   mode 1: hi = rna_tf32(x), lo = rna_tf32(x - hi): both parts are exact TF32 values, the hardware truncation is a no-op, and
+//           the residual (|x - hi - lo| <= 2^-23 |x|, lo*lo <= 2^-22 |x||y|) is zero-mean.
+__device__ __forceinline__ float tf32_rna(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void tf32_split4(const float4 v, int mode, float4& hi, float4& lo) {
+  if (mode == 0) {
+    hi = v;
+    lo = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                     v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+  } else {
+    hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+    lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+  }
+}
+int tf32_split_mode();      // api.cu: process-wide split policy (osb_set_tf32_split)
+
+// The TMEM accumulator of tcgen05.mma rounds TOWARDS ZERO (tools/tc_probe.cu acc, profiles/r2_acc_probe.log: accumulating the same
+// positive product block n times loses n * 2^-24 of the sum, where round-to-nearest would lose ~sqrt(n) * 2^-25).  Each MMA
+// therefore shrinks the running sum by ~c * ulp, and because E[partial sum after i of n MMAs | final] = (i/n) * final, an
+// accumulator that received n MMAs comes out as final * (1 - kappa * n) plus zero-mean noise.  The shrink is coherent from
+// layer to layer (round 1: -4e-5 on the GwcNet logits, 2.3e-3 px EPE), the noise is not -- so the epilogue undoes the EXPECTED
+// loss: raw sum * (1 + kappa * n), n = MMAs issued into that accumulator for this work item.  kappa is measured
+// (tools/parity_bisect.py --layers: every kernel variant agrees within 10 %); osb_set_rz_kappa() overrides it for calibration.
+float rz_kappa();           // api.cu
 
 
 // K-major SWIZZLE_64B descriptor base (64-byte rows, 512-byte 8-row atoms)

@@ -260,18 +260,6 @@ __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ 
   }
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = 148;
-    }
-  }
-  return n;
-}
-
 static int launch_volume(const float* ref_g, const float* tgt_g, const float* ref_c, const float* tgt_c, float* out,
                          int B, int Cg, int Cc, int H, int W, int D, int G, int mask_left, cudaStream_t stream) {
   OSB_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, "volume: empty shape B=%d H=%d W=%d D=%d", B, H, W, D);
@@ -318,7 +306,8 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   static const KernelFn kernels[4] = {volume_kernel<false, false>, volume_kernel<false, true>, volume_kernel<true, false>,
                                       volume_kernel<true, true>};
   KernelFn kernel = kernels[variant];
-  static size_t configured[4] = {0, 0, 0, 0};
+  static size_t configured_all[64][4] = {};                       // per device: cudaFuncSetAttribute is per device
+  size_t* configured = configured_all[device_index() & 63];
   if (smem > configured[variant]) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

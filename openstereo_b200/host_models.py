@@ -23,6 +23,9 @@ from . import ops
 from .aggregation import GwcAggregation, PSMAggregation
 
 
+USE_TC_BACKBONE = True      # the 2D extractor's 3x3 residual blocks on the tcgen05 kernels (False: everything 2D stays cuDNN)
+
+
 def _cfg_get(cfgs, key, default=None):
     if isinstance(cfgs, dict):
         return cfgs.get(key, default)
@@ -41,7 +44,7 @@ def _front_tc_ok(net, x):
     a 2D conv commutes with transposing the image, so the kernel sees (rows = W/2, columns = H/2 = 128) and the 3x3 weights
     with kh/kw swapped, as a one-plane 3D conv (the kd != 1 phases are skipped for D = 1)."""
     return (getattr(net, "_osb_folded", False) and x.is_cuda and x.dim() == 4 and x.shape[2] == 2 * ops.TC_WIDTH and x.shape[3] % 2 == 0
-            and _agg.USE_TENSOR_CORES and x.dtype == torch.float32 and ops.conv3d_tc_kc(32, 32, ops.TC_WIDTH) == 32)
+            and _agg.USE_TENSOR_CORES and USE_TC_BACKBONE and x.dtype == torch.float32 and ops.conv3d_tc_kc(32, 32, ops.TC_WIDTH) == 32)
 
 
 def _front_tc(net, x):
@@ -94,7 +97,7 @@ def _stage_tc(net, stage, x):
     first block that changes stride / channels (+ 1x1 downsample) stays cuDNN; the identity-shortcut 3x3 blocks run on the
     tcgen05 kernel when the feature map is 128 columns wide, channels-last in between, NCHW out of the last epilogue."""
     blocks = list(stage.children())
-    usable = getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES
+    usable = getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES and USE_TC_BACKBONE
     y, rest = x, blocks
     if not (usable and x.shape[3] == ops.TC_WIDTH and _block_tc_ok(blocks[0], x.shape[1])):
         y, rest = blocks[0](x), blocks[1:]
@@ -114,7 +117,7 @@ def _lastconv_tc_ok(net, x):
     """lastconv = conv3x3(320->128)+BN+ReLU, conv1x1(128->12) (gwcnet_backbone.py:62-67): cuDNN picks an FFT algorithm for the
     320-channel 3x3 (2.1 ms); on the tcgen05 kernel it is the layer3 conv with 20 K chunks."""
     convs = [m for m in net.lastconv.modules() if isinstance(m, nn.Conv2d)]
-    return (getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES
+    return (getattr(net, "_osb_folded", False) and x.is_cuda and x.dtype == torch.float32 and _agg.USE_TENSOR_CORES and USE_TC_BACKBONE
             and x.shape[3] == ops.TC_WIDTH and len(convs) == 2 and convs[0].kernel_size == (3, 3) and convs[0].stride == (1, 1)
             and convs[0].dilation == (1, 1) and convs[0].padding == (1, 1) and convs[1].kernel_size == (1, 1)
             and ops.conv2d_tc_kc(convs[0].in_channels, convs[0].out_channels, ops.TC_WIDTH, 1) != 0)

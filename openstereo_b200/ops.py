@@ -17,8 +17,20 @@ TC_WIDTH = 128      # image width (at 1/4 resolution) handled by the tensor-core
 TC_KC = 32          # input channels per K chunk of the tensor-core conv (128-byte K-major rows)
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_LAUNCH_DEVICE = [None]      # device index of the tensors of the launch being assembled (set by _stream, read by _call)
+
+
+def _stream(t):
+    """cudaStream_t of the CURRENT stream of the device `t` lives on (not of the current device: a model moved to cuda:1 without
+    torch.cuda.set_device(1) must still launch on device 1 -- the reference's aten ops are device-guarded the same way)."""
+    _LAUNCH_DEVICE[0] = t.device.index
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _same_device(*tensors):
+    devs = {t.device for t in tensors if t is not None}
+    if len(devs) > 1:
+        raise RuntimeError("openstereo_b200: operands live on different devices: %s" % sorted(str(d) for d in devs))
 
 
 # Optional live timing: CUDA events recorded on the launching stream around every entry-point call.
@@ -38,6 +50,14 @@ def profile_stop():
 
 
 def _call(name, *args):
+    dev = _LAUNCH_DEVICE[0]
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):                     # device guard: kernels launch where their operands live
+            return _call_on_current(name, *args)
+    return _call_on_current(name, *args)
+
+
+def _call_on_current(name, *args):
     if _PROFILE is None:
         return _lib.call(name, *args)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,12 +89,13 @@ def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
     ref, dt = _prep(refimg_fea, "refimg_fea")
     tgt, _ = _prep(targetimg_fea, "targetimg_fea")
     assert ref.dim() == 4 and ref.shape == tgt.shape
+    _same_device(ref, tgt)
     b, c, h, w = ref.shape
     assert c % num_groups == 0                       # cost_volume.py:61
     out = torch.empty((b, num_groups, maxdisp, h, w), dtype=torch.float32, device=ref.device)
     if out.numel():
         _call("osb_gwc_volume_fwd", ref.data_ptr(), tgt.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp,
-                  num_groups, _stream())
+                  num_groups, _stream(out))
     return out.to(dt)
 
 
@@ -83,11 +104,12 @@ def build_concat_volume(refimg_fea, targetimg_fea, maxdisp, mask_left=True):
     ref, dt = _prep(refimg_fea, "refimg_fea")
     tgt, _ = _prep(targetimg_fea, "targetimg_fea")
     assert ref.dim() == 4 and ref.shape == tgt.shape
+    _same_device(ref, tgt)
     b, c, h, w = ref.shape
     out = torch.empty((b, 2 * c, maxdisp, h, w), dtype=torch.float32, device=ref.device)
     if out.numel():
         _call("osb_concat_volume_fwd", ref.data_ptr(), tgt.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp,
-                  1 if mask_left else 0, _stream())
+                  1 if mask_left else 0, _stream(out))
     return out.to(dt)
 
 
@@ -104,10 +126,11 @@ def correlation_volume(left_feature, right_feature, max_disp):
     l, dt = _prep(left_feature, "left_feature")
     r, _ = _prep(right_feature, "right_feature")
     assert l.dim() == 4 and l.shape == r.shape
+    _same_device(l, r)
     b, c, h, w = l.shape
     out = torch.empty((b, max_disp, h, w), dtype=torch.float32, device=l.device)
     if out.numel():
-        _call("osb_corr_volume_fwd", l.data_ptr(), r.data_ptr(), out.data_ptr(), b, c, h, w, max_disp, _stream())
+        _call("osb_corr_volume_fwd", l.data_ptr(), r.data_ptr(), out.data_ptr(), b, c, h, w, max_disp, _stream(out))
     return out.to(dt)
 
 
@@ -119,13 +142,14 @@ def gwc_concat_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, maxdisp, num_groups):
     rc, _ = _prep(ref_cat, "ref_cat")
     tc, _ = _prep(tgt_cat, "tgt_cat")
     assert rg.shape == tg.shape and rc.shape == tc.shape and rg.shape[0] == rc.shape[0] and rg.shape[2:] == rc.shape[2:]
+    _same_device(rg, tg, rc, tc)
     b, cg, h, w = rg.shape
     cc = rc.shape[1]
     assert cg % num_groups == 0
     out = torch.empty((b, num_groups + 2 * cc, maxdisp, h, w), dtype=torch.float32, device=rg.device)
     if out.numel():
         _call("osb_gwc_concat_volume_fwd", rg.data_ptr(), tg.data_ptr(), rc.data_ptr(), tc.data_ptr(),
-                  out.data_ptr(), b, cg, cc, h, w, maxdisp, num_groups, _stream())
+                  out.data_ptr(), b, cg, cc, h, w, maxdisp, num_groups, _stream(out))
     return out.to(dt)
 
 
@@ -139,7 +163,7 @@ def softargmin(cost, maxdisp, keepdim=True, alpha=1.0, start=0.0, step=1.0, norm
     out = torch.empty((b, h, w), dtype=torch.float32, device=c.device)
     if out.numel():
         _call("osb_softargmin_fwd", c.data_ptr(), out.data_ptr(), b, d, h, w, float(alpha), float(start),
-                  float(step), 1 if normalize else 0, _stream())
+                  float(step), 1 if normalize else 0, _stream(out))
     out = out.to(dt)
     return out.unsqueeze(1) if keepdim else out
 
@@ -177,7 +201,7 @@ def upsample_softargmin(cost, maxdisp, out_h, out_w, align_corners=False):
     out = torch.empty((b, out_h, out_w), dtype=torch.float32, device=c.device)
     if out.numel():
         _call("osb_upsample_softargmin_fwd", c.data_ptr(), out.data_ptr(), b, dl, hl, wl, maxdisp, out_h, out_w,
-                  1 if align_corners else 0, _stream())
+                  1 if align_corners else 0, _stream(out))
     return out.to(dt)
 
 
@@ -190,7 +214,7 @@ def epe_partial(disp_pred, disp_gt, maxdisp):
     b = p.shape[0]
     out = torch.empty((b, 2), dtype=torch.float32, device=p.device)
     _call("osb_epe_partial_fwd", p.data_ptr(), g.data_ptr(), out.data_ptr(), b, p.shape[1] * p.shape[2],
-              float(maxdisp), _stream())
+              float(maxdisp), _stream(out))
     return out
 
 
@@ -231,7 +255,7 @@ def conv3d_k3(x, w_packed, scale=None, shift=None, residual=None, gate=None, str
     if gate is not None:
         assert gate.shape == (b, cout, ho, wo) and gate.is_contiguous()
     _call("osb_conv3d_k3_bn_act_fwd", x.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-              _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, stride, act, _stream())
+              _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, stride, act, _stream(y))
     return y
 
 
@@ -244,7 +268,7 @@ def deconv3d(x, w_packed, scale=None, shift=None, residual=None, kernel=3, act=A
     if residual is not None:
         assert residual.shape == y.shape and residual.is_contiguous()
     _call("osb_deconv3d_bn_act_fwd", x.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-              y.data_ptr(), b, cin, cout, d, h, w, kernel, act, _stream())
+              y.data_ptr(), b, cin, cout, d, h, w, kernel, act, _stream(y))
     return y
 
 
@@ -264,7 +288,7 @@ def conv3d_1x1(x0, w_packed, scale=None, shift=None, residual=None, gate=None, a
     cout = w_packed.shape[-1]
     y = torch.empty((b, cout, d, h, w), dtype=torch.float32, device=x0.device)
     _call("osb_conv3d_1x1_bn_act_fwd", x0.data_ptr(), _ptr(x1), c0, w_packed.data_ptr(), _ptr(scale), _ptr(shift),
-              _ptr(residual), _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, act, 1 if sigmoid_out else 0, _stream())
+              _ptr(residual), _ptr(gate), y.data_ptr(), b, cin, cout, d, h, w, act, 1 if sigmoid_out else 0, _stream(y))
     return y.squeeze(2) if squeeze else y
 
 
@@ -278,15 +302,45 @@ def conv3d_tc_kc(cin, cout, w, stride=1):
     return int(_lib.lib.osb_conv3d_tc_kc(int(cin), int(cout), int(w), int(stride)))
 
 
+_TF32_SPLIT = 1      # must match the library's policy (osb_set_tf32_split); 1 = round-to-nearest (unbiased), 0 = round 1's truncation
+
+
+def set_tf32_split(mode):
+    """Select the 3xTF32 operand-split policy of the tensor-core convolutions, library and weight packing together
+    (include/openstereo_b200.h: osb_set_tf32_split).  Weights packed before the call must be re-packed (new engine)."""
+    global _TF32_SPLIT
+    assert mode in (0, 1)
+    _lib.lib.osb_set_tf32_split(int(mode))
+    _TF32_SPLIT = int(mode)
+
+
+def set_rz_kappa(kappa):
+    """Override the accumulator round-towards-zero correction constant of the tensor-core convs (include/openstereo_b200.h:
+    osb_set_rz_kappa); returns the previous value.  Calibration / bisect only."""
+    return float(_lib.lib.osb_set_rz_kappa(float(kappa)))
+
+
+def tf32_split(w):
+    """fp32 tensor -> (hi, lo), both exactly representable in TF32 (low 13 mantissa bits zero) under the default policy:
+    hi = w rounded to nearest (ties away, like cvt.rna.tf32.f32), lo = (w - hi) rounded to nearest.  |w - hi - lo| <= 2^-23 |w|
+    with zero mean.  Policy 0 reproduces round 1: hi = w truncated, lo = w - hi left for the MMA to truncate (biased)."""
+    w = w.contiguous()
+    if _TF32_SPLIT == 0:
+        hi = (w.view(torch.int32) & -8192).view(torch.float32)
+        return hi, w - hi
+    hi = ((w.view(torch.int32) + 4096) & -8192).view(torch.float32)
+    lo = w - hi
+    return hi, ((lo.view(torch.int32) + 4096) & -8192).view(torch.float32)
+
+
 def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2)):
-    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] fp32.
-    hi = the value with its low 13 mantissa bits cleared (what a kind::tf32 MMA reads), lo = value - hi (exact)."""
+    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] fp32,
+    hi/lo = tf32_split(weight)."""
     w = weight.detach().float()
     cout, cin = w.shape[:2]
     kc = TC_KC if kc is None else kc
     assert kc in (16, 32) and cin % kc == 0 and tuple(w.shape[2:]) == (3, 3, 3)
-    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    lo = w - hi
+    hi, lo = tf32_split(w)
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
     both = both[..., list(kw_order)]                                   # stride-2 kernel wants kw slices as (1, 0, 2)
     both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (2, co, chunk, ci, kd, kh, kw)
@@ -299,7 +353,7 @@ def to_ndhwc(x):
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
     b, c, d, h, w = x.shape
     y = torch.empty((b, d, h, w, c), dtype=torch.float32, device=x.device)
-    _call("osb_ncdhw_to_ndhwc", x.data_ptr(), y.data_ptr(), b, c, d, h, w, _stream())
+    _call("osb_ncdhw_to_ndhwc", x.data_ptr(), y.data_ptr(), b, c, d, h, w, _stream(y))
     return y
 
 
@@ -316,7 +370,7 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
         want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
     _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
 
@@ -338,7 +392,7 @@ def conv3d_k3_s2_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act
         want = (b, do, ho, wo, cout) if res_ndhwc else (b, cout, do, ho, wo)
         assert tuple(residual.shape) == want and residual.is_contiguous()
     _call("osb_conv3d_k3_s2_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
 
@@ -364,7 +418,7 @@ def deconv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=
         want = (b, 2 * d, 2 * h, 2 * w, cout) if res_ndhwc else (b, cout, 2 * d, 2 * h, 2 * w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
     _call("osb_deconv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream())
+          y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
 
@@ -375,7 +429,7 @@ def conv1x1_ndhwc(x_ndhwc, w_packed, scale=None, shift=None, act=ACT_NONE):
     assert x_ndhwc.shape[-1] == cin
     y = torch.empty(x_ndhwc.shape[:-1] + (cout,), dtype=torch.float32, device=x_ndhwc.device)
     _call("osb_conv1x1_ndhwc_fwd", x_ndhwc.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(),
-          x_ndhwc.numel() // cin, cin, cout, act, _stream())
+          x_ndhwc.numel() // cin, cin, cout, act, _stream(y))
     return y
 
 
@@ -392,7 +446,7 @@ def conv3d_k3_c1_ndhwc(x_ndhwc, w_taps, scale=None, shift=None):
     assert w_taps.shape == (27, cin) and w_taps.is_contiguous()
     y = torch.empty((b, 1, d, h, w), dtype=torch.float32, device=x_ndhwc.device)
     _call("osb_conv3d_k3_c1_ndhwc_fwd", x_ndhwc.data_ptr(), w_taps.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(), b, cin, d, h, w,
-          _stream())
+          _stream(y))
     return y
 
 
@@ -405,7 +459,7 @@ def avgpool_pairs(x, axis):
     n = x.shape[axis]
     outer, inner = math.prod(x.shape[:axis]), math.prod(x.shape[axis + 1:])
     y = torch.empty(x.shape[:axis] + (n // 2,) + x.shape[axis + 1:], dtype=torch.float32, device=x.device)
-    _call("osb_avgpool_pairs_fwd", x.data_ptr(), y.data_ptr(), outer, n, inner, _stream())
+    _call("osb_avgpool_pairs_fwd", x.data_ptr(), y.data_ptr(), outer, n, inner, _stream(y))
     return y
 
 
@@ -427,7 +481,7 @@ def geo_lookup(geo_levels, corr_levels, disp, coords, radius):
     gp = [geo_levels[i].data_ptr() if i < levels else None for i in range(4)]
     cp = [corr_levels[i].data_ptr() if i < levels else None for i in range(4)]
     _call("osb_geo_lookup_fwd", *gp, *cp, disp.data_ptr(), coords.data_ptr(), out.data_ptr(), b, c, d, h, w, w2, levels, radius,
-          _stream())
+          _stream(out))
     return out
 
 
@@ -438,7 +492,7 @@ def context_upsample(disp_low, up_weights, scale_factor=4):
     assert tuple(up_weights.shape) == (b, 9, h * scale_factor, w * scale_factor)
     disp_low, up_weights = disp_low.contiguous().float(), up_weights.contiguous().float()
     out = torch.empty((b, h * scale_factor, w * scale_factor), dtype=torch.float32, device=disp_low.device)
-    _call("osb_context_upsample_fwd", disp_low.data_ptr(), up_weights.data_ptr(), out.data_ptr(), b, h, w, scale_factor, _stream())
+    _call("osb_context_upsample_fwd", disp_low.data_ptr(), up_weights.data_ptr(), out.data_ptr(), b, h, w, scale_factor, _stream(out))
     return out
 
 
@@ -459,5 +513,5 @@ def conv2d_k3_tc(x_nhwc, w_split, scale=None, shift=None, residual=None, act=ACT
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == y.numel()
     _call("osb_conv2d_k3_tc_fwd", x_nhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, cin,
-          cout, h, w, dilation, act, int(out_nhwc), int(res_nhwc), _stream())
+          cout, h, w, dilation, act, int(out_nhwc), int(res_nhwc), _stream(y))
     return y

@@ -7,46 +7,73 @@ needs its own rebinding:
 * GwcNet      bound methods on ``CostProcessor`` (gwcnet_cost_processor.py:58-64) and the ``DispProcessor``
               forward (gwcnet_disp_processor.py:83-140)                    -> per-instance ``forward`` override
 * PSMNet      ``cat_fms`` captured by functools.partial at construction (psmnet_cost_processor.py:227-232),
-              aggregator + FasterSoftArgmin modules                          -> ``CostProcessor.forward`` / ``DispProcessor.forward``
-* StereoBase  functions imported INTO the module namespace (stereobase_gru.py:5-6) and the ``cost_agg``
-              Hourglass + ``classifier``                                    -> module-global rebinding + ``cost_agg.forward``
+              aggregator + FasterSoftArgmin modules                          -> ``CostProcessor.forward`` / ``FasterSoftArgmin.forward``
+* StereoBase  functions imported INTO the module namespace (stereobase_gru.py:5-6,10-11) and the ``cost_agg``
+              Hourglass                                                      -> per-INSTANCE copies of the methods that use those names,
+                                                                                with a private globals dict (the module itself, and
+                                                                                therefore every other StereoBase instance, is untouched)
 
 Parameters stay where they are (the engines read them through the reference's attribute names), so
 ``state_dict()`` / ``load_state_dict()`` and checkpoints are untouched.
 
-Behaviour outside the accelerated envelope: by default (strict=True) a patched module RAISES when it is in
-training mode or is fed non-CUDA tensors -- there is no silent CPU path in this package.  strict=False instead
-hands such calls back to the reference's own original Python method (useful for tools/train.py).
+When is a call accelerated?  Only when it is a CUDA inference call: every tensor on a CUDA device, the module in eval
+mode, and autograd not recording (``torch.no_grad()`` as in trainer_template.py:260-283, or no operand requires grad).
+The kernels have no backward, so anything else must NOT reach them silently:
+  strict=True  (default) such a call RAISES -- there is no CPU / autograd path in this package;
+  strict=False           such a call runs the reference's own original Python code, gradients intact (tools/train.py).
 """
-import sys
 import types
 
 import torch
 
 from . import ops
-from .aggregation import GwcAggregation, PSMAggregation, StereoBaseAggregation, StereoBaseCostHead
+from .aggregation import GwcAggregation, PSMAggregation, StereoBaseAggregation
 from .geo import CombinedGeoEncodingVolume
 
 
-def _accelerable(module, *tensors):
-    return (not module.training) and all(t.is_cuda for t in tensors)
+def _tensors(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, (list, tuple)):
+            yield from _tensors(a)
+        elif isinstance(a, dict):
+            yield from _tensors(a.values())
+
+
+def _recording(*args):
+    """True when autograd would record an op on these operands (the kernels would silently cut the graph)."""
+    return torch.is_grad_enabled() and any(t.requires_grad for t in _tensors(args))
+
+
+def _accelerable(module, *args):
+    ts = list(_tensors(args))
+    return (module is None or not module.training) and bool(ts) and all(t.is_cuda for t in ts) and not _recording(*ts)
 
 
 def _refuse(what):
-    raise RuntimeError("openstereo_b200: %s is patched for CUDA inference only "
-                       "(model.eval() on a CUDA device); use patch(model, strict=False) to delegate "
+    raise RuntimeError("openstereo_b200: %s is patched for CUDA inference only (model.eval() on a CUDA device, under "
+                       "torch.no_grad() or with no operand requiring grad); use patch(model, strict=False) to delegate "
                        "training / CPU calls to the reference implementation" % what)
 
 
 def _patch_gwcnet(model, strict):
     cp, dp = model.CostProcessor, model.DispProcessor
-    cp_orig, dp_orig = cp.forward, dp.forward
+    cp_orig, dp_orig = cp.forward, dp.forward                                 # the reference's bound methods
+    gwc_orig, cat_orig = cp.build_gwc_volume, cp.build_concat_volume
     engine = GwcAggregation(dp)
 
     def cost_forward(self, inputs):
         lf, rf = inputs["ref_feature"], inputs["tgt_feature"]
-        if not _accelerable(self, lf["gwc_feature"]):
-            return cp_orig(inputs) if not strict else _refuse("GwcVolumeCostProcessor")
+        if not _accelerable(self, lf, rf):
+            if strict:
+                _refuse("GwcVolumeCostProcessor")
+            saved = self.build_gwc_volume, self.build_concat_volume            # the reference's forward calls these two
+            self.build_gwc_volume, self.build_concat_volume = gwc_orig, cat_orig
+            try:
+                return cp_orig(inputs)
+            finally:
+                self.build_gwc_volume, self.build_concat_volume = saved
         d = self.maxdisp // self.downsample
         if self.use_concat_volume:
             vol = ops.gwc_concat_volume(lf["gwc_feature"], rf["gwc_feature"], lf["concat_feature"],
@@ -63,105 +90,134 @@ def _patch_gwcnet(model, strict):
 
     cp.forward = types.MethodType(cost_forward, cp)
     dp.forward = types.MethodType(disp_forward, dp)
-    # the two volume builders stay callable on their own, with the reference's method signatures
-    gwc_orig, cat_orig = cp.build_gwc_volume, cp.build_concat_volume          # the reference's bound methods
 
+    # the two volume builders stay callable on their own, with the reference's method signatures
     def build_gwc(ref, tgt):
-        if ref.is_cuda or strict:                                              # strict: ops raises on CPU tensors
+        if _accelerable(None, ref, tgt):
             return ops.build_gwc_volume(ref, tgt, cp.maxdisp // cp.downsample, cp.num_groups)
-        return gwc_orig(ref, tgt)
+        return gwc_orig(ref, tgt) if not strict else _refuse("build_gwc_volume")
 
     def build_concat(ref, tgt):
-        if ref.is_cuda or strict:
+        if _accelerable(None, ref, tgt):
             return ops.build_concat_volume(ref, tgt, cp.maxdisp // cp.downsample)
-        return cat_orig(ref, tgt)
+        return cat_orig(ref, tgt) if not strict else _refuse("build_concat_volume")
 
     cp.build_gwc_volume, cp.build_concat_volume = build_gwc, build_concat
     return model
 
 
+class FusedCost:
+    """What the patched PSMCostProcessor hands to PSMDispProcessor in place of a (B, 192, H, W) cost tensor: the fused tail
+    (trilinear x4 + softmax + expectation in one kernel) already produced the disparity and the full-resolution cost is never
+    materialised.  The patched FasterSoftArgmin recognises it; any other consumer gets a loud AttributeError/TypeError
+    instead of a silently wrong tensor."""
+    __slots__ = ("disp",)
+
+    def __init__(self, disp):
+        self.disp = disp
+
+
 def _patch_psmnet(model, strict):
     cp, dp = model.CostProcessor, model.DispProcessor
-    cp_orig, dp_orig = cp.forward, dp.forward
+    cp_orig = cp.forward
     engine = PSMAggregation(cp.aggregator)
     max_disp = cp.aggregator.max_disp
+    cat_orig = cp.cat_func                                          # functools.partial(cat_fms, ...) of the reference
 
     def cost_forward(self, inputs):
         lf, rf = inputs["ref_feature"], inputs["tgt_feature"]
-        if not _accelerable(self, lf):
-            return cp_orig(inputs) if not strict else _refuse("PSMCostProcessor")
+        if not _accelerable(self, lf, rf):
+            if strict:
+                _refuse("PSMCostProcessor")
+            saved, self.cat_func = self.cat_func, cat_orig
+            try:
+                return cp_orig(inputs)
+            finally:
+                self.cat_func = saved
         raw = ops.cat_fms(lf, rf, max_disp=int(max_disp // 4), start_disp=0, dilation=1)
         d1, d2, d3 = engine(raw)
-        # the fused tail already produced disparities; the (B,192,H,W) costs are never materialised
-        return {"cost1": None, "cost2": None, "cost3": None, "_osb_disps": [d1, d2, d3]}
-
-    def disp_forward(self, inputs):
-        if "_osb_disps" in inputs and inputs["_osb_disps"] is not None:
-            return list(inputs["_osb_disps"])
-        return dp_orig(inputs)
+        return {"cost1": FusedCost(d1), "cost2": FusedCost(d2), "cost3": FusedCost(d3)}
 
     cp.forward = types.MethodType(cost_forward, cp)
-    dp.forward = types.MethodType(disp_forward, dp)
-    cat_orig = cp.cat_func                                          # functools.partial(cat_fms, ...) of the reference
 
     def cat_func(l, r):
-        if l.is_cuda or strict:                                     # strict: ops raises on CPU tensors
+        if _accelerable(None, l, r):
             return ops.cat_fms(l, r, max_disp=int(max_disp // 4), start_disp=0, dilation=1)
-        return cat_orig(l, r)
+        return cat_orig(l, r) if not strict else _refuse("cat_fms")
 
     cp.cat_func = cat_func
     sa = dp.disp_processor                                          # FasterSoftArgmin: keep the frozen Conv3d parameter
     sa_orig = sa.forward
 
     def sa_forward(self, cost):
-        if cost.is_cuda or strict:
+        if isinstance(cost, FusedCost):
+            return cost.disp
+        if _accelerable(None, cost):
             return ops.faster_soft_argmin(cost, self.max_disp, self.start_disp, self.dilation, self.alpha, self.normalize)
-        return sa_orig(cost)
+        return sa_orig(cost) if not strict else _refuse("FasterSoftArgmin")
 
     sa.forward = types.MethodType(sa_forward, sa)
     return model
 
 
+def _rebind_methods(model, overrides):
+    """Give `model` private copies of the methods of its class that use any name in `overrides` as a module global: same code
+    object, closure and defaults, but a globals dict with the overrides applied.  The module namespace and the class are not
+    modified, so other instances (patched or not) are unaffected."""
+    for name, fn in vars(type(model)).items():
+        if isinstance(fn, types.FunctionType) and set(fn.__code__.co_names) & set(overrides):
+            g = dict(fn.__globals__)
+            g.update(overrides)
+            copy = types.FunctionType(fn.__code__, g, fn.__name__, fn.__defaults__, fn.__closure__)
+            copy.__kwdefaults__ = fn.__kwdefaults__
+            setattr(model, name, types.MethodType(copy, model))
+
+
 def _patch_stereobase(model, strict):
-    mod = sys.modules[type(model).__module__]                       # stereo.modeling.models.stereobase.stereobase_gru
+    g = type(model).forward.__globals__                             # stereo.modeling.models.stereobase.stereobase_gru namespace
     hg = model.cost_agg
     hg_orig = hg.forward
     agg = StereoBaseAggregation(hg)
-    head = StereoBaseCostHead(model.classifier)
-    originals = {n: getattr(mod, n) for n in ("build_gwc_volume", "build_concat_volume", "disparity_regression")}
+    orig = {n: g[n] for n in ("build_gwc_volume", "build_concat_volume", "disparity_regression", "CombinedGeoEncodingVolume",
+                              "context_upsample")}
 
     def gwc(ref, tgt, maxdisp, groups):
-        return ops.build_gwc_volume(ref, tgt, maxdisp, groups) if ref.is_cuda else originals["build_gwc_volume"](ref, tgt, maxdisp, groups)
+        if _accelerable(model, ref, tgt):
+            return ops.build_gwc_volume(ref, tgt, maxdisp, groups)
+        return orig["build_gwc_volume"](ref, tgt, maxdisp, groups) if not strict else _refuse("build_gwc_volume")
 
     def concat(ref, tgt, maxdisp):
-        return ops.build_concat_volume(ref, tgt, maxdisp) if ref.is_cuda else originals["build_concat_volume"](ref, tgt, maxdisp)
+        if _accelerable(model, ref, tgt):
+            return ops.build_concat_volume(ref, tgt, maxdisp)
+        return orig["build_concat_volume"](ref, tgt, maxdisp) if not strict else _refuse("build_concat_volume")
 
     def regression(x, maxdisp):
-        return ops.disparity_regression(x, maxdisp) if x.is_cuda else originals["disparity_regression"](x, maxdisp)
-
-    mod.build_gwc_volume, mod.build_concat_volume, mod.disparity_regression = gwc, concat, regression
+        if _accelerable(model, x):
+            return ops.disparity_regression(x, maxdisp)
+        return orig["disparity_regression"](x, maxdisp) if not strict else _refuse("disparity_regression")
 
     # SURVEY.md section 8(f) rows 1 and 3: the per-GRU-iteration lookup and the convex up-sampling (stereobase_gru.py:172-209)
-    geo_orig, up_orig = mod.CombinedGeoEncodingVolume, mod.context_upsample
-
     def geo_factory(fmap1, fmap2, volume, num_levels=2, radius=4):
-        cls = CombinedGeoEncodingVolume if volume.is_cuda else geo_orig
+        fast = _accelerable(model, fmap1, fmap2, volume)
+        if not fast and strict:
+            _refuse("CombinedGeoEncodingVolume")
+        cls = CombinedGeoEncodingVolume if fast else orig["CombinedGeoEncodingVolume"]
         return cls(fmap1, fmap2, volume, num_levels=num_levels, radius=radius)
 
     def upsample(disp_low, up_weights, scale_factor=4):
-        if disp_low.is_cuda:
+        if _accelerable(model, disp_low, up_weights):
             return ops.context_upsample(disp_low, up_weights, scale_factor).to(disp_low.dtype)
-        return up_orig(disp_low, up_weights, scale_factor)
+        return orig["context_upsample"](disp_low, up_weights, scale_factor) if not strict else _refuse("context_upsample")
 
-    mod.CombinedGeoEncodingVolume, mod.context_upsample = geo_factory, upsample
+    _rebind_methods(model, {"build_gwc_volume": gwc, "build_concat_volume": concat, "disparity_regression": regression,
+                            "CombinedGeoEncodingVolume": geo_factory, "context_upsample": upsample})
 
     def hg_forward(self, x, features, return_multi=False):
-        if return_multi or not _accelerable(self, x):
+        if return_multi or not _accelerable(self, x, features):
             return hg_orig(x, features, return_multi) if not strict else _refuse("StereoBase Hourglass")
         return agg(x, features).to(x.dtype)
 
     hg.forward = types.MethodType(hg_forward, hg)
-    model._osb_cost_head = head                                     # fused classifier + softmax + regression
     return model
 
 

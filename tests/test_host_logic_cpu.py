@@ -14,17 +14,36 @@ def rnd(seed, *shape, scale=1.0):
 
 
 @pytest.mark.parametrize("kc,order", [(32, (0, 1, 2)), (16, (0, 1, 2)), (16, (1, 0, 2)), (16, (1, 2, 0))])
-def test_pack_tc_weight_split_is_exact(kc, order):
+def test_pack_tc_weight_split(kc, order):
+    """hi and lo are both exact TF32 values (the MMA's own truncation is then a no-op), hi is the nearest TF32 to w, and
+    hi + lo reproduces w to 2^-23 relative with no sign preference (round 1 truncated: every product shrank towards zero)."""
     cout, cin = 8, 64
     w = rnd(1, cout, cin, 3, 3, 3) * torch.logspace(-3, 3, cin).view(1, cin, 1, 1, 1)      # wide dynamic range
     p = ops.pack_tc_weight(w, kc, kw_order=order)
     assert p.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and p.is_contiguous()
     hi, lo = p[0], p[1]
-    assert ((hi.view(torch.int32) & 0x1FFF) == 0).all()                     # what a kind::tf32 MMA reads is exactly hi
+    assert ((hi.view(torch.int32) & 0x1FFF) == 0).all() and ((lo.view(torch.int32) & 0x1FFF) == 0).all()
     # un-permute: [kd][chunk][kh][kw*cout + co][ci] -> (co, ci, kd, kh, kw) in the requested kw order
-    back = (hi.double() + lo.double()).view(3, cin // kc, 3, 3, cout, kc).permute(4, 1, 5, 0, 2, 3).reshape(cout, cin, 3, 3, 3)
-    assert torch.equal(back.float(), w[..., list(order)])                    # hi + lo == w bit for bit
-    assert (lo.abs() <= hi.abs() * 2.0 ** -10 + 1e-45).all()                 # lo is the dropped 13 mantissa bits
+    unperm = lambda t: t.double().view(3, cin // kc, 3, 3, cout, kc).permute(4, 1, 5, 0, 2, 3).reshape(cout, cin, 3, 3, 3)
+    want = w[..., list(order)].double()
+    resid = unperm(hi) + unperm(lo) - want
+    assert (resid.abs() <= want.abs() * 2.0 ** -23).all()
+    assert abs((resid * want.sign()).sum().item()) <= 0.05 * resid.abs().sum().item()     # zero-mean, not a shrink
+    assert ((unperm(hi) - want).abs() <= want.abs() * 2.0 ** -11).all()                    # round to nearest (truncation: 2^-10)
+    assert (lo.abs() <= hi.abs() * 2.0 ** -11 * (1 + 2.0 ** -10)).all()
+
+
+def test_tf32_split_legacy_truncation_mode():
+    """Policy 0 (round 1, kept for tools/parity_bisect.py): hi = truncation, lo = exact remainder, always the sign of w."""
+    w = rnd(9, 4096)
+    old = ops._TF32_SPLIT
+    ops._TF32_SPLIT = 0
+    try:
+        hi, lo = ops.tf32_split(w)
+    finally:
+        ops._TF32_SPLIT = old
+    assert torch.equal((hi.double() + lo.double()).float(), w) and ((hi.view(torch.int32) & 0x1FFF) == 0).all()
+    assert (lo * w >= 0).all()
 
 
 def test_pack_deconv_and_head_weights():

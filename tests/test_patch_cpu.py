@@ -64,3 +64,39 @@ def test_patch_rejects_unknown():
         patch("not a module")
     with pytest.raises(NotImplementedError, match="no hot-path drop-in"):
         patch(torch.nn.Linear(2, 2))
+
+
+def test_patch_strict_false_keeps_autograd():
+    """strict=False must hand every call autograd is recording back to the reference's own code -- gradients have to
+    reach the Backbone through the volume builders (the kernels have no backward and detach their inputs)."""
+    from openstereo_b200.patch import patch
+    m = patch(_gwcnet(), strict=False)
+    x = _inputs(64, 128, 5)
+    out = m(dict(x))["disp_pred"]
+    assert out.requires_grad
+    out.mean().backward()
+    grads = [p.grad for n, p in m.named_parameters() if n.startswith("Backbone.")]
+    assert all(g is not None for g in grads) and any(g.abs().sum() > 0 for g in grads)
+    cfg = shim.load_cfg("cfgs/psmnet/psmnet_sceneflow.yaml").MODEL
+    p = shim.load("stereo.modeling.models.psmnet.psmnet").PSMNet(cfg).eval()
+    p.load_state_dict(si.seeded_state_dict(p.state_dict(), seed=1, scale=si.PSMNET_SCALE, keep=si.PSMNET_KEEP))
+    patch(p, strict=False)
+    out = p(dict(_inputs(256, 256, 6)))["disp_pred"]
+    out.mean().backward()
+    assert any(q.grad is not None and q.grad.abs().sum() > 0 for n, q in p.named_parameters() if n.startswith("Backbone."))
+
+
+def test_stereobase_rebinding_is_per_instance():
+    """The StereoBase drop-in must not rebind the reference module's globals (every other instance would change behaviour):
+    patched instances get private method copies with their own globals."""
+    from openstereo_b200 import patch as P
+    ns = {}
+    exec("def helper(x):\n    return x + 1\n\nclass Net:\n    def forward(self, x):\n        return helper(x)\n"
+         "    def other(self, x):\n        return x * 2\n", ns)
+    a, b = ns["Net"](), ns["Net"]()
+    P._rebind_methods(a, {"helper": lambda x: x + 100})
+    assert a.forward(1) == 101 and b.forward(1) == 2 and ns["helper"](1) == 2       # module namespace and class untouched
+    assert "other" not in vars(a)                                                    # only methods that use the name are copied
+    sb = shim.load("stereo.modeling.models.stereobase.stereobase_gru")
+    names = set(sb.StereoBase.forward.__code__.co_names) | set(sb.StereoBase.upsample_disp.__code__.co_names)
+    assert {"build_gwc_volume", "build_concat_volume", "disparity_regression", "CombinedGeoEncodingVolume", "context_upsample"} <= names

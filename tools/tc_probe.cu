@@ -223,7 +223,7 @@ static float tf32_trunc(float a) {
   return a;
 }
 
-int main() {
+int main(int argc, char** argv) {
   CK(cudaSetDevice(0));
   void* fnp = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -260,6 +260,46 @@ int main() {
     CK(cudaMemcpy(hO, dO, 128 * 64 * 4, cudaMemcpyDeviceToHost));
   };
 
+  // ---- test 5 (./tc_probe acc): how does the TMEM accumulator round?  The same K = 32 product block is accumulated `reps` times
+  // into one accumulator (4 MMAs of K = 8 each per rep).  With all-positive operands the exact answer is reps * (A.B); round-to-
+  // nearest accumulation leaves a zero-mean error growing like sqrt(#MMAs) * 2^-25, truncation (RZ) a NEGATIVE bias growing like
+  // #MMAs * 2^-25.  Second pass: random-sign operands (error relative to the RMS magnitude of the result).
+  if (argc > 1 && !strcmp(argv[1], "acc")) {
+    for (int pass = 0; pass < 2; ++pass) {
+      float* hA2 = (float*)malloc(kRowsA * 32 * 4);
+      for (int i = 0; i < kRowsA * 32; ++i) hA2[i] = pass == 0 ? fabsf(hA[i]) + 0.25f : hA[i];
+      for (int i = 0; i < NB * 32; ++i) hB[i] = 0.f;
+      for (int i = 0; i < 32 * 32; ++i) hB[i] = pass == 0 ? fabsf(W[i]) + 0.25f : W[i];
+      CK(cudaMemcpy(dA, hA2, kRowsA * 32 * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dB, hB, NB * 32 * 4, cudaMemcpyHostToDevice));
+      for (int reps : {1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048}) {
+        Params p{};
+        p.mode = 2, p.N = 32, p.reps = reps;
+        run(p);
+        double sum_rel = 0, max_rel = 0, rms = 0;
+        for (int m = 0; m < 128; ++m)
+          for (int n = 0; n < 32; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 32; ++k) ref += (double)tf32_trunc(hA2[m * 32 + k]) * (double)tf32_trunc(hB[n * 32 + k]);
+            rms += ref * ref;
+          }
+        rms = sqrt(rms / (128 * 32));
+        for (int m = 0; m < 128; ++m)
+          for (int n = 0; n < 32; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 32; ++k) ref += (double)tf32_trunc(hA2[m * 32 + k]) * (double)tf32_trunc(hB[n * 32 + k]);
+            const double denom = pass == 0 ? ref * reps : rms * reps;
+            const double rel = ((double)hO[m * 64 + n] - ref * reps) / denom;
+            sum_rel += (pass == 0) ? rel : rel * (ref > 0 ? 1.0 : -1.0);      // signed towards/away from zero
+            max_rel = fmax(max_rel, fabs(rel));
+          }
+        printf("acc %s reps=%4d (%5d MMAs): mean signed rel err %+.3e (x 2^-24 = %+.2f), max |rel| %.3e\n",
+               pass == 0 ? "positive" : "random  ", reps, 4 * reps, sum_rel / (128 * 32), sum_rel / (128 * 32) / 5.96e-8, max_rel);
+      }
+      free(hA2);
+    }
+    return 0;
+  }
   // ---- test 1 + 2: 1xTF32 GEMM with row offsets / base_offset candidates
   for (int i = 0; i < NB * 32; ++i) hB[i] = 0.f;
   for (int i = 0; i < 32 * 32; ++i) hB[i] = W[i];
