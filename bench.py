@@ -13,13 +13,17 @@ Reported in one JSON line (rank 0):
   value      pairs/s, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public model call with PINNED HOST inputs: H2D copy of the images + ground truth
              and D2H read-back of the per-image EPE inside the timed region, every step
-  roofline   the cost-volume kernel named by the metric (HBM-bound), timed live with CUDA events around its launch
-             inside the timed steps, against MEASURED_PEAKS.json hbm_gbs
-  roofline_dominant  the kernel family that dominates the hot path (3x3x3 Conv3d / ConvTranspose3d on tcgen05, 3xTF32),
-             same live timing; roofline_cuda_core = the fp32 layers still on CUDA cores
-  cpu_baseline  the oracle port of the reference (same aten CPU kernels) on the host cores, bounded sample
---impl reference times that oracle port as the reference arm (the reference is pure Python/PyTorch and cannot travel;
-oracle/__init__.py explains the provenance).
+  roofline   the DOMINANT kernel family of the step (3x3x3 Conv3d / ConvTranspose3d on tcgen05, split-operand fp32-accurate
+             MMAs; tensor-bound), timed live with CUDA events around every launch inside the timed steps
+  roofline_volume  the cost-volume kernel the metric names (HBM-bound) against MEASURED_PEAKS.json hbm_gbs and the 8 TB/s nominal;
+             roofline_cuda_core = the fp32 layers still on CUDA cores
+  cpu_baseline  the UNMODIFIED reference GwcNet (oracle/_ref, staged by oracle/make_ref.py; kind "reference") on the host
+             cores, bounded sample -- the oracle port (kind "port") only when the staged reference is absent
+  parity_epe_px  mean |disparity - reference| of one pair of the timed batch: this library on the GPU vs that CPU forward
+  dropin     the same step through the reference's OWN GwcNet class + openstereo_b200.patch.patch() (what a maintainer gets)
+  comparators  the unmodified reference on the same B200 (cuDNN fp32, TF32 off) and its Triton gwc kernel
+               (fast_foundationstereo/core/submodule.py:443-478) against this library's gwc volume kernel
+--impl reference times the reference's own CPU implementation as the reference arm.
 """
 import argparse
 import json
@@ -37,6 +41,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "stereo_pairs_per_sec_gwcnet_256x512_d192"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 8 from `ncu --set full` captures of this command
+# (profiles/README.md names the capture each figure comes from); None = not captured for the current kernel version
+NCU_TRAFFIC = {"volume_kernel": 919946496, "conv3d_tc_kernel": 765931264}
 CFG = {"MAX_DISP": 192, "USE_CONCAT_VOLUME": True, "CONCAT_CHANNELS": 12, "DOWNSAMPLE": 4, "NUM_GROUPS": 40}
 H, W = 256, 512
 
@@ -167,36 +174,57 @@ def barrier(world):
         dist.barrier()
 
 
-def oracle_model():
-    from oracle import models as omodels                           # CPU oracle: cpu_baseline / reference arm only
+def reference_available():
+    try:
+        from oracle import _reference_shim as shim
+        return shim.available()
+    except Exception:
+        return False
+
+
+def reference_model():
+    """-> (model, kind).  The UNMODIFIED reference GwcNet built by its own class from its own cfgs/gwcnet/gwcnet_sceneflow.yaml
+    (oracle/_ref on the GPU box: byte copies staged by oracle/make_ref.py), kind "reference"; the oracle port (same aten calls,
+    bit-equal: tests/test_oracle_pins_reference.py), kind "port", only when no reference tree is present.  Same synthetic weights
+    as the timed model (identical state_dict keys).  Checker / baseline legs only."""
+    if reference_available():
+        from oracle import _reference_shim as shim
+        cfg = shim.load_cfg("cfgs/gwcnet/gwcnet_sceneflow.yaml").MODEL
+        assert (cfg.MAX_DISP, cfg.NUM_GROUPS, cfg.CONCAT_CHANNELS) == (CFG["MAX_DISP"], CFG["NUM_GROUPS"], CFG["CONCAT_CHANNELS"])
+        m = shim.load("stereo.modeling.models.gwcnet.gwcnet").GwcNet(cfg).eval()
+        return synthetic_weights(m), "reference"
+    from oracle import models as omodels
     m = omodels.GwcNet(CFG["MAX_DISP"], CFG["USE_CONCAT_VOLUME"], CFG["CONCAT_CHANNELS"], CFG["DOWNSAMPLE"],
                        CFG["NUM_GROUPS"]).eval()
-    return synthetic_weights(m)
+    return synthetic_weights(m), "port"
 
 
-def time_cpu(model, pairs_per_step, steps, warmup):
-    gen = torch.Generator().manual_seed(0)
-    x = {"left": torch.randn(pairs_per_step, 3, H, W, generator=gen), "right": torch.randn(pairs_per_step, 3, H, W, generator=gen)}
+def time_cpu(model, pairs_per_step, steps, warmup, x=None):
+    """-> (seconds for `steps` forwards, last output).  x defaults to seeded synthetic pairs."""
+    if x is None:
+        gen = torch.Generator().manual_seed(0)
+        x = {"left": torch.randn(pairs_per_step, 3, H, W, generator=gen), "right": torch.randn(pairs_per_step, 3, H, W, generator=gen)}
+    out = None
     with torch.no_grad():
         for _ in range(warmup):
             model(dict(x))
         t0 = time.perf_counter()
         for _ in range(steps):
-            model(dict(x))
+            out = model(dict(x))["disp_pred"]
         dt = time.perf_counter() - t0
-    return dt
+    return dt, out
 
 
 def run_reference(args):
-    """Reference arm: the oracle port of the reference's CPU path with every host thread, rank 0 only."""
+    """Reference arm: the reference's own CPU path (unmodified GwcNet from oracle/_ref) with every host thread, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = usable_cores()
     torch.set_num_threads(cores)
-    model = oracle_model()
+    model, kind = reference_model()
     pairs = 1                                                       # bounded sample: one pair of the B=8 batch per step
-    dt = time_cpu(model, pairs, args.steps, min(args.warmup, 2))
+    dt, _ = time_cpu(model, pairs, args.steps, min(args.warmup, 2))
     value = pairs * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -204,8 +232,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "GwcNet cfgs/gwcnet_sceneflow 256x512 D=192 (configs[1]); CPU step = 1 pair sample",
                    "global_batch": pairs, "parallelism": "cpu-threads"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d forward(s) of 1 pair, oracle port of the reference (same aten CPU kernels)" % args.steps},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
+                         "sample": "%d forward(s) of 1 pair; %s" % (args.steps, "unmodified reference GwcNet class (oracle/_ref)"
+                                                                   if kind == "reference" else "oracle port of the reference")},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -319,19 +348,14 @@ def run_ours(args):
     step_ms = ms / args.steps
     vol_ms, vol_n, vol_total = kernel_stats("osb_gwc_concat_volume_fwd")
     vol_bytes = 4 * (2 * B * (320 + 12) * 64 * 128 + B * 64 * 48 * 64 * 128)
-    roofline = None
+    roof_vol = None
     if vol_ms:
         ach = vol_bytes / vol_ms / 1e6
-        roofline = {"kernel": "volume_kernel (gwc+concat fused, osb_gwc_concat_volume_fwd)", "bound": "hbm",
-                    "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                    "frac_of_8TBs_nominal": round(ach / 8000.0, 4), "peak_source": peak_src,
-                    "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4),
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture of the same
-                    # command (profiles/r1_ncu_summary_final.md, r1_volume_final): 174.2 MB read (= the algorithmic input)
-                    # + 745.8 MB written (the rest of the 805.3 MB output is still dirty in the 126 MB L2 at kernel end)
-                    "traffic": 919946496 if B == 8 else None,
-                    "share_of_step": round(vol_total / ms, 4)}
-    # ---- 3D aggregation (SURVEY.md section 8a rows a4-a6): MACs per pair of GwcNet-gc at D'=48, H'=64, W'=128
+        roof_vol = {"kernel": "volume_kernel (gwc+concat fused)", "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak,
+                    "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
+                    "peak_source": peak_src, "alg_bytes_per_launch": vol_bytes, "ms_per_launch": round(vol_ms, 4),
+                    "traffic": NCU_TRAFFIC.get("volume_kernel") if B == 8 else None, "share_of_step": round(vol_total / ms, 4)}
+    # ---- 3D aggregation (SURVEY.md section 8a row a6): MACs per pair of GwcNet-gc at D'=48, H'=64, W'=128
     vox = 48 * 64 * 128
     macs = {
         # stem dres0a (64->32) + dres0b, dres1a, dres1b, classif3a (32->32) at full resolution; 3 x (conv2, conv4)
@@ -345,8 +369,7 @@ def run_ours(args):
         # classif3b 32->1 head
         "osb_conv3d_k3_c1_ndhwc_fwd": vox * 27 * 32,
         # 2D backbone residual blocks on the same kernels (two images per pair): 8 front convs 32->32 @128x256, 30 layer2 convs
-        # 64->64, 4 layer3 + 6 dilated layer4 convs 128->128 @64x128 (gwcnet_backbone.py:38-60)
-        # + lastconv's 320->128 3x3
+        # 64->64, 4 layer3 + 6 dilated layer4 convs 128->128 @64x128 (gwcnet_backbone.py:38-60) + lastconv's 320->128 3x3
         "osb_conv2d_k3_tc_fwd": 2 * 9 * (8 * 128 * 256 * 32 * 32 + 30 * 64 * 128 * 64 * 64 + 10 * 64 * 128 * 128 * 128
                                          + 64 * 128 * 320 * 128),
     }
@@ -357,8 +380,9 @@ def run_ours(args):
             bf16_peak = float(json.load(f).get("bf16_tflops_sustained"))
     except Exception:
         bf16_peak = 1400.0
-    tf32_peak = bf16_peak / 2.0                                     # dense tf32 = half the bf16 rate
-    roof_dom = None
+    mma_kind = ops.tc_operand_kind()                                # "tf32" (3xTF32) or "f16" (3xFP16 split)
+    tc_peak = bf16_peak / (2.0 if mma_kind == "tf32" else 1.0)      # dense tf32 = half the 16-bit rate
+    roofline = None
     tc_total = sum(kernel_stats(n)[2] for n in tc_names)
     if tc_total > 0:
         per = {}
@@ -369,18 +393,14 @@ def run_ours(args):
                           "useful_tflops": round(2 * macs[n] * B * args.steps / (tot / 1e3) / 1e12, 1)}
         ran = [n for n in tc_names if kernel_stats(n)[2] > 0]
         useful = 2 * sum(macs[n] for n in ran) * B * args.steps / (tc_total / 1e3) / 1e12
-        roof_dom = {"kernel": "tcgen05 conv family: conv3d_tc_kernel / conv3d_tcg_kernel (3x3x3 s1), conv3d_tcs2_kernel (s2), "
-                              "conv3d_tcdc_kernel (transposed), incl. the backbone's 3x3 residual blocks as one-plane volumes "
-                              "(osb_conv2d_k3_tc_fwd); kind::tf32 with the 3xTF32 split",
-                    "bound": "tensor", "achieved": round(3 * useful, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
-                    "frac": round(3 * useful / tf32_peak, 4), "useful_fp32_equivalent_tflops": round(useful, 1),
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense tf32 rate); achieved counts the 3 MMAs "
-                                   "issued per fp32-accurate product",
+        roofline = {"kernel": "tcgen05 conv family (conv3d_tc / tcg / tcs2 / tcdc kernels: 3x3x3 s1, s2, transposed; the backbone's 3x3 "
+                              "blocks as one-plane volumes), kind::%s, 3 split-operand MMAs per fp32-accurate product" % mma_kind,
+                    "bound": "tensor", "achieved": round(3 * useful, 1), "peak": round(tc_peak, 1), "unit": "TFLOP/s",
+                    "frac": round(3 * useful / tc_peak, 4), "useful_fp32_equivalent_tflops": round(useful, 1),
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained%s; achieved counts the 3 issued MMAs"
+                                   % (" / 2 (dense tf32)" if mma_kind == "tf32" else " (dense 16-bit)"),
                     "alg_flops_per_step": 2 * sum(macs[n] for n in ran) * B, "share_of_step": round(tc_total / ms, 4),
-                    "per_kernel": per,
-                    # conv3d_tc_kernel<32> (32->32 stem layer), ncu --set full: 403.2 MB read + 362.8 MB written per launch =
-                    # its algorithmic 402.7 + 402.7 MB (profiles/r1_ncu_summary_final.md, r1_conv3d_tc_final)
-                    "traffic": 765931264 if B == 8 else None}
+                    "traffic": NCU_TRAFFIC.get("conv3d_tc_kernel") if B == 8 else None, "per_kernel": per}
     cc_names = ["osb_conv3d_k3_bn_act_fwd", "osb_deconv3d_bn_act_fwd", "osb_conv3d_1x1_bn_act_fwd", "osb_conv1x1_ndhwc_fwd",
                 "osb_conv3d_k3_c1_ndhwc_fwd"]
     cc_total = sum(kernel_stats(n)[2] for n in cc_names)
@@ -389,25 +409,35 @@ def run_ours(args):
     if cc_total > 0:
         cc_flops = 2 * (agg_macs - (sum(macs[n] for n in tc_names[:3]) if tc_total > 0 else 0)) * B
         ach = cc_flops * args.steps / (cc_total / 1e3) / 1e12
-        roof_cc = {"kernel": "fp32 CUDA-core layers left in the aggregation (classif3b 32->1 head conv3d_k3_c1_ndhwc_kernel, channels-last "
-                             "1x1 redir convs; everything else when the tensor-core variants do not cover a shape)",
-                   "bound": "fp32_fma", "achieved": round(ach, 2), "peak": round(fp32_peak, 1), "unit": "TFLOP/s",
-                   "frac": round(ach / fp32_peak, 4), "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
+        roof_cc = {"kernel": "fp32 CUDA-core layers left in the aggregation", "bound": "fp32_fma", "achieved": round(ach, 2),
+                   "peak": round(fp32_peak, 1), "unit": "TFLOP/s", "frac": round(ach / fp32_peak, 4),
+                   "peak_source": "derived 148 SM x 128 lanes x 2 x %.0f MHz" % sm_max,
                    "alg_flops_per_step": cc_flops, "share_of_step": round(cc_total / ms, 4), "traffic": None}
     shares = {}
     for name, ev in prof.items():
         shares[name] = round(sum(a.elapsed_time(b) for a, b in ev) / ms, 4)
 
-    cpu = None
+    # ---- checker / baseline legs (rank 0, N = 1 only): the reference on the host cores, parity of one timed pair against it,
+    # the reference's own class through patch(), the reference on this GPU, its Triton gwc kernel.
+    cpu, parity, dropin, comparators = None, None, None, None
     if world == 1 and not args.no_cpu_baseline:
         cores = usable_cores()
         torch.set_num_threads(cores)
-        cm = oracle_model()
+        cm, kind = reference_model()
         n = 4
-        dt = time_cpu(cm, 1, n, 1)
-        cpu = {"value": round(n / dt, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": "%d forwards of 1 pair (of the B=%d batch) through the oracle port of the reference GwcNet "
-                         "(same aten CPU kernels), %d threads" % (n, B, cores)}
+        x1 = {"left": host_left[0][:1].clone(), "right": host_right[0][:1].clone()}       # pair 0 of the first timed batch
+        dt, want = time_cpu(cm, 1, n, 1, x=x1)
+        cpu = {"value": round(n / dt, 4), "unit": "pairs/s", "cores": cores, "kind": kind,
+               "sample": "%d forwards of 1 pair (pair 0 of the B=%d batch) through %s, %d threads"
+                         % (n, B, "the unmodified reference GwcNet class (oracle/_ref)" if kind == "reference"
+                            else "the oracle port of the reference", cores)}
+        with torch.no_grad():
+            got = model({"left": dev_left[0], "right": dev_right[0]})["disp_pred"][:1].cpu()  # the timed B=8 batch, image 0
+        parity = {"epe_px": float("%.3e" % (got - want).abs().mean().item()), "bar_px": 1e-3, "against": kind + " on CPU",
+                  "disparity_std_px": round(want.std().item(), 2), "pair": "image 0 of timed batch 0 (inside the B=%d forward)" % B}
+        del cm
+    if world == 1 and not args.no_comparators and reference_available():
+        dropin, comparators = run_comparators(args, dev, B, dev_left, dev_right, dev_gt, value)
 
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -415,19 +445,92 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "GwcNet cfgs/gwcnet/gwcnet_sceneflow.yaml, batch %d/GPU @256x512 D=192 (BASELINE configs[1])" % B,
                    "global_batch": B * world, "parallelism": "dp%d batch-shard, 1 all_gather of per-image EPE" % world,
+                   "model_path": "openstereo_b200.host_models.GwcNet (state_dict-compatible mirror; `dropin` = the reference's class + patch())",
                    "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); per-step activations ~6 GB" % (rot, rot * 2 * B * 3 * H * W * 4 / 1e6),
                    "weights": "synthetic seeded init (no checkpoints ship with the reference)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "h2d_bytes_per_step": (2 * B * 3 * H * W + B * H * W) * 4, "d2h_bytes_per_step": B * 2 * 4},
         "gpu_launches": launches,
-        "roofline": roofline, "roofline_dominant": roof_dom, "roofline_cuda_core": roof_cc, "kernel_share_of_step": shares,
-        "cpu_baseline": cpu, "mean_epe_vs_synthetic_gt": round(epe, 3),
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "parity_epe_px": parity["epe_px"] if parity else None,
+        "dropin": dropin, "comparators": comparators,
+        "roofline_volume": roof_vol, "roofline_cuda_core": roof_cc, "kernel_share_of_step": shares,
+        "mean_epe_vs_synthetic_gt": round(epe, 3),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def run_comparators(args, dev, B, dev_left, dev_right, dev_gt, mirror_value):
+    """N = 1 legs that need the staged reference (oracle/_ref).  Each is CUDA-event timed after warm-up, resident inputs, same
+    synthetic weights and batches as the main arm.
+      dropin                     the reference's own GwcNet class + patch(): pairs/s and its ratio to the mirror's value
+      reference_gpu_cudnn_fp32   the UNMODIFIED reference forward on this B200 (cuDNN fp32, TF32 off) -- SURVEY.md section 8d's GPU bar
+      triton_gwc                 the reference's Triton gwc kernel (normalize=False, / K to match build_gwc_volume's mean)
+                                 against osb_gwc_volume_fwd at the config-2 shape (8, 320, 64, 128), D' = 48, G = 40"""
+    from oracle import _reference_shim as shim
+    from openstereo_b200 import ops
+    from openstereo_b200.patch import patch
+    rot = len(dev_left)
+
+    def timed_model(m, steps, warm):
+        with torch.no_grad():
+            for i in range(warm):
+                m({"left": dev_left[i % rot], "right": dev_right[i % rot]})
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(steps):
+                d = m({"left": dev_left[i % rot], "right": dev_right[i % rot]})["disp_pred"]
+                ops.epe_partial(d.float().contiguous(), dev_gt[i % rot], CFG["MAX_DISP"])
+            b.record()
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, d
+
+    dropin, comp = None, {}
+    try:
+        ref, _ = reference_model()
+        ref = ref.to(dev)
+        ms_ref, d_ref = timed_model(ref, 3, 2)
+        comp["reference_gpu_cudnn_fp32"] = {"value": round(B / (ms_ref / 1e3), 2), "unit": "pairs/s", "ms_per_step": round(ms_ref, 2),
+                                            "what": "unmodified reference GwcNet forward on this GPU, B=%d, cuDNN fp32, allow_tf32=False" % B}
+        patch(ref)                                                  # same instance, now on this library's kernels
+        ms_pat, d_pat = timed_model(ref, args.steps, 3)
+        dropin = {"value": round(B / (ms_pat / 1e3), 3), "unit": "pairs/s", "ms_per_step": round(ms_pat, 4),
+                  "path": "reference GwcNet class (oracle/_ref) + openstereo_b200.patch.patch(model)",
+                  "ratio_to_mirror": round(B / (ms_pat / 1e3) / mirror_value, 4),
+                  "epe_vs_reference_on_this_gpu_px": float("%.3e" % (d_pat - d_ref).abs().mean().item())}
+        del ref
+    except Exception as exc:                                        # a comparator must never take the bench line down
+        comp["reference_gpu_cudnn_fp32"] = comp.get("reference_gpu_cudnn_fp32") or {"error": repr(exc)[:200]}
+    try:
+        sub = shim.load("stereo.modeling.models.fast_foundationstereo.core.submodule")
+        g = torch.Generator(device=dev).manual_seed(5)
+        lf, rf = torch.randn(B, 320, 64, 128, device=dev, generator=g), torch.randn(B, 320, 64, 128, device=dev, generator=g)
+
+        def timeit(fn, n=10):
+            for _ in range(3):
+                out = fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n, out
+
+        ms_tr, v_tr = timeit(lambda: sub.build_gwc_volume_triton(lf, rf, 48, 40, normalize=False))
+        ms_us, v_us = timeit(lambda: ops.build_gwc_volume(lf, rf, 48, 40))
+        comp["triton_gwc"] = {"reference_triton_ms": round(ms_tr, 4), "this_library_ms": round(ms_us, 4), "speedup": round(ms_tr / ms_us, 2),
+                              "max_abs_diff": float("%.2e" % (v_tr / 8.0 - v_us).abs().max().item()),
+                              "what": "build_gwc_volume_triton(normalize=False) [sum over K=8; /8 for the mean] vs osb_gwc_volume_fwd, "
+                                      "(%d,320,64,128) D'=48 G=40" % B}
+    except Exception as exc:
+        comp["triton_gwc"] = {"error": repr(exc)[:200]}
+    return dropin, comp
 
 
 def main():
@@ -439,6 +542,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--rotate", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

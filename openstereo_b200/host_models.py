@@ -129,6 +129,32 @@ def _lastconv_tc(net, x):
     return convs[1](_tc2d(net, convs[0], t, ops.ACT_RELU, last=True))             # 3x3 + ReLU on tensor cores, 1x1 on cuDNN
 
 
+def gwc_extract(net, x):
+    """feature_extraction.forward of gwcnet_backbone.py:80-93 on any module with its attribute names (this file's mirror or a
+    BN-folded copy of the reference's own class): identical graph, the 3x3 residual blocks on the tcgen05 kernels where a
+    variant serves the shape, everything else through the module's own layers (cuDNN)."""
+    x = _front_tc(net, x) if _front_tc_ok(net, x) else net.layer1(net.firstconv(x))
+    l2 = _stage_tc(net, net.layer2, x)
+    l3 = _stage_tc(net, net.layer3, l2)
+    l4 = _stage_tc(net, net.layer4, l3)
+    gwc = torch.cat((l2, l3, l4), dim=1)
+    out = {"gwc_feature": gwc}
+    if net.concat_feature:
+        out["concat_feature"] = _lastconv_tc(net, gwc) if _lastconv_tc_ok(net, gwc) else net.lastconv(gwc)
+    return out
+
+
+def psm_extract(net, x):
+    """PSMNet._forward of psmnet_backbone.py:82-116 on any module with its attribute names (see gwc_extract)."""
+    o2 = _front_tc(net, x) if _front_tc_ok(net, x) else net.layer1(net.firstconv(x))
+    o4_0 = _stage_tc(net, net.layer2, o2)
+    o8 = _stage_tc(net, net.layer4, _stage_tc(net, net.layer3, o4_0))
+    size = (o8.size()[2], o8.size()[3])
+    up = [F.interpolate(getattr(net, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
+    cat = torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1)
+    return _lastconv_tc(net, cat) if _lastconv_tc_ok(net, cat) else net.lastconv(cat)
+
+
 class _ResBlock(nn.Module):
     """conv-bn-relu, conv-bn, += identity (no trailing relu): gwcnet_backbone.py:13-35, psmnet/submodule.py:219-243."""
 
@@ -171,15 +197,7 @@ class _GwcFeatureExtraction(nn.Module):
                                           nn.Conv2d(128, concat_channels, kernel_size=1, padding=0, stride=1, bias=False))
 
     def forward(self, x):
-        x = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
-        l2 = _stage_tc(self, self.layer2, x)
-        l3 = _stage_tc(self, self.layer3, l2)
-        l4 = _stage_tc(self, self.layer4, l3)
-        gwc = torch.cat((l2, l3, l4), dim=1)
-        out = {"gwc_feature": gwc}
-        if self.concat_feature:
-            out["concat_feature"] = _lastconv_tc(self, gwc) if _lastconv_tc_ok(self, gwc) else self.lastconv(gwc)
-        return out
+        return gwc_extract(self, x)
 
 
 def _fold_conv_bn(module):
@@ -188,7 +206,12 @@ def _fold_conv_bn(module):
     original module keeps the parameters (state_dict unchanged); the folded copy is runtime-only."""
     import copy
     from torch.nn.utils.fusion import fuse_conv_bn_eval
-    fused = copy.deepcopy(module).eval()
+    inst_fwd = module.__dict__.pop("forward", None)              # a patch()-installed per-instance forward is not part of the net
+    try:
+        fused = copy.deepcopy(module).eval()
+    finally:
+        if inst_fwd is not None:
+            module.__dict__["forward"] = inst_fwd
 
     def walk(m):
         for name, child in list(m.named_children()):
@@ -266,19 +289,13 @@ class _PsmBackbone(nn.Module):
                                       nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, dilation=1, bias=False))
 
     def _forward(self, x):
-        o2 = _front_tc(self, x) if _front_tc_ok(self, x) else self.layer1(self.firstconv(x))
-        o4_0 = _stage_tc(self, self.layer2, o2)
-        o8 = _stage_tc(self, self.layer4, _stage_tc(self, self.layer3, o4_0))
-        size = (o8.size()[2], o8.size()[3])
-        up = [F.interpolate(getattr(self, "branch%d" % i)(o8), size, mode="bilinear", align_corners=True) for i in (1, 2, 3, 4)]
-        cat = torch.cat((o4_0, o8, up[3], up[2], up[1], up[0]), 1)
-        return _lastconv_tc(self, cat) if _lastconv_tc_ok(self, cat) else self.lastconv(cat)
+        return psm_extract(self, x)
 
     def forward(self, inputs):
         if getattr(self, "_rt", None) is None:
             object.__setattr__(self, "_rt", _FoldedRuntime(self))
         net = self if self.training else self._rt.get()
-        both = net._forward(torch.cat((inputs["left"], inputs["right"]), 0))
+        both = psm_extract(net, torch.cat((inputs["left"], inputs["right"]), 0))
         b = inputs["left"].shape[0]
         return {"ref_feature": both[:b], "tgt_feature": both[b:]}
 

@@ -302,6 +302,11 @@ def conv3d_tc_kc(cin, cout, w, stride=1):
     return int(_lib.lib.osb_conv3d_tc_kc(int(cin), int(cout), int(w), int(stride)))
 
 
+def tc_operand_kind():
+    """MMA kind of the tensor-core convolutions: "tf32" (3xTF32 split) or "f16" (3xFP16 split)."""
+    return "tf32"
+
+
 _TF32_SPLIT = 1      # must match the library's policy (osb_set_tf32_split); 1 = round-to-nearest (unbiased), 0 = round 1's truncation
 
 

@@ -57,7 +57,38 @@ def _refuse(what):
                        "training / CPU calls to the reference implementation" % what)
 
 
-def _patch_gwcnet(model, strict):
+def _patch_backbone(bb, net, extract, split):
+    """2D feature extractor (gwcnet_backbone.py:96-107 / psmnet_backbone.py:118-126; not a SURVEY section-8 row, but inside the
+    measured forward): CUDA inference calls run a BN-folded twin of `net` whose identity-shortcut 3x3 residual blocks use the
+    tcgen05 conv kernels where a variant serves the shape (host_models.gwc_extract / psm_extract; every other layer is the
+    module's own cuDNN conv), left and right images in ONE batched pass (the weights are shared).  Parameters stay in `net`;
+    the twin is rebuilt when they change.  Any other call (CPU, training, autograd recording) runs the reference's forward."""
+    from . import host_models
+    rt = host_models._FoldedRuntime(net)
+    orig = bb.forward
+
+    def forward(self, inputs):
+        left, right = inputs["left"], inputs["right"]
+        if not (_accelerable(self, left, right) and left.dtype == torch.float32 and left.shape == right.shape):
+            return orig(inputs)
+        both = extract(rt.get(), torch.cat((left, right), 0))
+        return split(both, left.shape[0])
+
+    bb.forward = types.MethodType(forward, bb)
+
+
+def _split_dict(both, b):
+    return {"ref_feature": {k: v[:b] for k, v in both.items()}, "tgt_feature": {k: v[b:] for k, v in both.items()}}
+
+
+def _split_tensor(both, b):
+    return {"ref_feature": both[:b], "tgt_feature": both[b:]}
+
+
+def _patch_gwcnet(model, strict, backbone=True):
+    if backbone:
+        from .host_models import gwc_extract
+        _patch_backbone(model.Backbone, model.Backbone.feature_extraction, gwc_extract, _split_dict)
     cp, dp = model.CostProcessor, model.DispProcessor
     cp_orig, dp_orig = cp.forward, dp.forward                                 # the reference's bound methods
     gwc_orig, cat_orig = cp.build_gwc_volume, cp.build_concat_volume
@@ -117,7 +148,10 @@ class FusedCost:
         self.disp = disp
 
 
-def _patch_psmnet(model, strict):
+def _patch_psmnet(model, strict, backbone=True):
+    if backbone:
+        from .host_models import psm_extract
+        _patch_backbone(model.Backbone, model.Backbone, psm_extract, _split_tensor)
     cp, dp = model.CostProcessor, model.DispProcessor
     cp_orig = cp.forward
     engine = PSMAggregation(cp.aggregator)
@@ -173,7 +207,7 @@ def _rebind_methods(model, overrides):
             setattr(model, name, types.MethodType(copy, model))
 
 
-def _patch_stereobase(model, strict):
+def _patch_stereobase(model, strict, backbone=True):
     g = type(model).forward.__globals__                             # stereo.modeling.models.stereobase.stereobase_gru namespace
     hg = model.cost_agg
     hg_orig = hg.forward
@@ -224,8 +258,10 @@ def _patch_stereobase(model, strict):
 _PATCHERS = {"GwcNet": _patch_gwcnet, "PSMNet": _patch_psmnet, "StereoBase": _patch_stereobase}
 
 
-def patch(model, strict=True):
-    """Rebind the hot path of a reference model instance in place and return it."""
+def patch(model, strict=True, backbone=True):
+    """Rebind the hot path of a reference model instance in place and return it.  backbone=True (default) also routes the
+    GwcNet / PSMNet 2D extractor's residual blocks to the tcgen05 conv kernels in CUDA inference calls (_patch_backbone);
+    backbone=False leaves the extractor entirely to the reference's cuDNN code."""
     if not isinstance(model, torch.nn.Module):
         raise TypeError("patch() expects an nn.Module")
     name = type(model).__name__
@@ -233,6 +269,6 @@ def patch(model, strict=True):
         raise NotImplementedError("patch(): no hot-path drop-in for %s (supported: %s)" % (name, sorted(_PATCHERS)))
     if getattr(model, "_osb_patched", False):
         return model
-    _PATCHERS[name](model, strict)
+    _PATCHERS[name](model, strict, backbone)
     model._osb_patched = True
     return model
