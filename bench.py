@@ -493,11 +493,15 @@ def run_comparators(args, dev, B, dev_left, dev_right, dev_gt, mirror_value):
     try:
         ref, _ = reference_model()
         ref = ref.to(dev)
-        ms_ref, d_ref = timed_model(ref, 3, 2)
+        ms_ref, _ = timed_model(ref, 3, 2)
+        with torch.no_grad():
+            d_ref = ref({"left": dev_left[0], "right": dev_right[0]})["disp_pred"]
         comp["reference_gpu_cudnn_fp32"] = {"value": round(B / (ms_ref / 1e3), 2), "unit": "pairs/s", "ms_per_step": round(ms_ref, 2),
                                             "what": "unmodified reference GwcNet forward on this GPU, B=%d, cuDNN fp32, allow_tf32=False" % B}
         patch(ref)                                                  # same instance, now on this library's kernels
-        ms_pat, d_pat = timed_model(ref, args.steps, 3)
+        ms_pat, _ = timed_model(ref, args.steps, 3)
+        with torch.no_grad():
+            d_pat = ref({"left": dev_left[0], "right": dev_right[0]})["disp_pred"]
         dropin = {"value": round(B / (ms_pat / 1e3), 3), "unit": "pairs/s", "ms_per_step": round(ms_pat, 4),
                   "path": "reference GwcNet class (oracle/_ref) + openstereo_b200.patch.patch(model)",
                   "ratio_to_mirror": round(B / (ms_pat / 1e3) / mirror_value, 4),
@@ -509,6 +513,8 @@ def run_comparators(args, dev, B, dev_left, dev_right, dev_gt, mirror_value):
         sub = shim.load("stereo.modeling.models.fast_foundationstereo.core.submodule")
         g = torch.Generator(device=dev).manual_seed(5)
         lf, rf = torch.randn(B, 320, 64, 128, device=dev, generator=g), torch.randn(B, 320, 64, 128, device=dev, generator=g)
+        # the reference's wrapper views permute(0,2,3,1) as (B*H, W, C): it expects channels_last features (as its own backbone emits)
+        lf_cl, rf_cl = lf.contiguous(memory_format=torch.channels_last), rf.contiguous(memory_format=torch.channels_last)
 
         def timeit(fn, n=10):
             for _ in range(3):
@@ -522,7 +528,7 @@ def run_comparators(args, dev, B, dev_left, dev_right, dev_gt, mirror_value):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n, out
 
-        ms_tr, v_tr = timeit(lambda: sub.build_gwc_volume_triton(lf, rf, 48, 40, normalize=False))
+        ms_tr, v_tr = timeit(lambda: sub.build_gwc_volume_triton(lf_cl, rf_cl, 48, 40, normalize=False))
         ms_us, v_us = timeit(lambda: ops.build_gwc_volume(lf, rf, 48, 40))
         comp["triton_gwc"] = {"reference_triton_ms": round(ms_tr, 4), "this_library_ms": round(ms_us, 4), "speedup": round(ms_tr / ms_us, 2),
                               "max_abs_diff": float("%.2e" % (v_tr / 8.0 - v_us).abs().max().item()),

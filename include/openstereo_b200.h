@@ -44,15 +44,16 @@ int osb_abi_version(void);
 const char* osb_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports it). */
 uint64_t osb_launch_count(void);
-/* 3xTF32 operand-split policy of the tensor-core convolutions (process-wide; returns the previous value):
- *   1 (default)  hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi)   -- unbiased
- *   0            hi = x truncated by the MMA itself, lo = x - trunc(x)                      -- round 1, biased towards zero;
- *                kept only so the parity bisect (tools/bisect_parity.py) can reproduce it.
- * Weights must be packed with the same policy (openstereo_b200/ops.py: pack_tc_weight). */
-int osb_set_tf32_split(int mode);
+/* fp16 range guard of the tensor-core convolutions.  They compute every fp32 product as three kind::f16 MMAs on operands split
+ * into fp16 (hi, lo) pairs (csrc/tc_common.cuh): activations are staged as x * 16, so |x| must stay below 65504 / 16 = 4094
+ * (weights are pre-scaled per output channel on the host and cannot overflow).  Conversions saturate and every loader thread
+ * that met a larger value increments a sticky per-device counter.  osb_tc_overflow_count copies it to *count (host memory),
+ * optionally resets it, and synchronises `stream`; osb_tc_overflow_flag returns its device address (for an asynchronous read). */
+int osb_tc_overflow_count(osb_stream_t stream, int reset, unsigned int* count);
+const unsigned int* osb_tc_overflow_flag(void);
 /* Expected round-towards-zero loss per accumulating tcgen05.mma, undone by the conv epilogues (csrc/tc_common.cuh: rz_kappa;
  * DESIGN.md section 4.3).  Process-wide; returns the previous value; 0 switches the correction off.  The default is the
- * constant measured on B200 (profiles/r2_rz_kappa.md); the setter exists for that calibration. */
+ * constant measured on B200 (profiles/r2_parity_bisect.md); the setter exists for that calibration. */
 float osb_set_rz_kappa(float kappa);
 
 /* ---------------------------------------------------------------- cost-volume constructors --- */
@@ -143,29 +144,30 @@ int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const 
 /* ------------------------------------------------------- tensor-core (tcgen05) variant of the 3x3x3 conv ----- */
 
 /* Same operator as osb_conv3d_k3_bn_act_fwd (stride 1) for the full-resolution layers, computed on the 5th-gen tensor
- * cores with 3xTF32 operand splitting (fp32-accurate, see csrc/conv3d_tc.cu, conv3d_tcg.cu).  Supported shapes:
- * osb_conv3d_tc_supported / osb_conv3d_tc_kc.  x is CHANNELS-LAST (B,D,H,W,Cin); w_split is the host-split weight tensor
- * [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] (ops.pack_tc_weight); y and residual are NCDHW or NDHWC
- * according to out_ndhwc / res_ndhwc. */
+ * cores with 3xFP16 operand splitting (fp32-accurate, see csrc/tc_common.cuh, conv3d_tc.cu, conv3d_tcg.cu).  Supported shapes:
+ * osb_conv3d_tc_supported / osb_conv3d_tc_kc.  x is CHANNELS-LAST (B,D,H,W,Cin) fp32; w_split is the host-split fp16 weight
+ * tensor [3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc hi | kc lo] of w * 2^e_c (ops.pack_tc_weight; e_c per output channel);
+ * `scale` (REQUIRED here, Cout floats) must already contain the exact inverse 2^-(e_c + 4) times the folded-BN scale
+ * (TcWeight.eff_scale).  y and residual are fp32, NCDHW or NDHWC according to out_ndhwc / res_ndhwc. */
 int osb_conv3d_tc_supported(int Cin, int Cout, int W, int stride);
 /* K chunk (16 or 32 input channels per operand tile) the weight tensor must be packed with; 0 = unsupported shape.
  * Variants: W=128/Cout=32 (kc 32); W=64/Cout=64, W=32/Cout=64|128 (kc 16, M tile = 128/W image rows). */
 int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
-int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* Stride-2 variant (the down-sampling convs of the hourglasses): x (B,D,H,W,Cin) channels-last with even D,H,W ->
  * y (B,Cout,D/2,H/2,W/2) or channels-last.  w_split like above but with the kw slices stored in the order (1,0,2)
  * (ops.pack_tc_weight(..., kw_order=(1,0,2))), 16-channel K chunks.  Supported: W=128/Cout=64, W=64/Cout=64|128. */
 int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W);
-int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                             const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                             int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* ConvTranspose3d(k=3, stride=2, padding=1, output_padding=1) on the tensor cores: x (B,D,H,W,Cin) channels-last ->
  * y (B,Cout,2D,2H,2W) or channels-last.  w_split = ops.pack_tc_deconv_weight(weight): the (Cin,Cout,3,3,3) parameter split
- * hi/lo, 16-channel K chunks, kw slices stored as (1,2,0).  Supported: W=32/Cout=64 (conv5), W=64/Cout=32 (conv6). */
+ * hi/lo (fp16), 16-channel K chunks, kw slices stored as (1,2,0).  Supported: W=32/Cout=64 (conv5), W=64/Cout=32 (conv6). */
 int osb_deconv3d_tc_supported(int Cin, int Cout, int W);
-int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                            int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* Channels-last 1x1x1 conv + folded BN + activation (the redir branches when the aggregation runs channels-last):
@@ -183,7 +185,7 @@ int osb_conv3d_k3_c1_ndhwc_fwd(const float* x_ndhwc, const float* w_taps, const 
  * at kd = 1, y (B,H,W,Cout) or (B,Cout,H,W).  dilation 1 = osb_conv3d_k3_tc_fwd with D = 1; dilation 2: W = 128, Cout = 128.
  * osb_conv2d_tc_kc returns the K chunk of the serving kernel (0 = unsupported). */
 int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation);
-int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const float* w_split, const float* scale, const float* shift, const float* residual,
+int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const void* w_split, const float* scale, const float* shift, const float* residual,
                          float* y, int B, int Cin, int Cout, int H, int W, int dilation, int act, int out_nhwc, int res_nhwc,
                          osb_stream_t stream);
 /* ---- GRU-iteration lookups of IGEV / StereoBase ------------------------------------

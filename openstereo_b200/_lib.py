@@ -57,8 +57,10 @@ def _load():
     lib.osb_abi_version.restype = ctypes.c_int
     lib.osb_last_error.restype = ctypes.c_char_p
     lib.osb_launch_count.restype = ctypes.c_uint64
-    lib.osb_set_tf32_split.argtypes = [ctypes.c_int]
-    lib.osb_set_tf32_split.restype = ctypes.c_int
+    lib.osb_tc_overflow_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint)]
+    lib.osb_tc_overflow_count.restype = ctypes.c_int
+    lib.osb_tc_overflow_flag.argtypes = []
+    lib.osb_tc_overflow_flag.restype = ctypes.c_void_p
     lib.osb_set_rz_kappa.argtypes = [ctypes.c_float]
     lib.osb_set_rz_kappa.restype = ctypes.c_float
     for name, argtypes in SIGNATURES.items():

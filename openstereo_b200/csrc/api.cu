@@ -17,11 +17,28 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static std::atomic<int> g_tf32_split{1};
-int tf32_split_mode() { return g_tf32_split.load(std::memory_order_relaxed); }
-
-static std::atomic<float> g_rz_kappa{1.57e-8f};   // measured on B200: profiles/r2_rz_kappa.md
+static std::atomic<float> g_rz_kappa{1.57e-8f};   // measured on B200: profiles/r2_parity_bisect.md
 float rz_kappa() { return g_rz_kappa.load(std::memory_order_relaxed); }
+
+// Sticky fp16-range counter of the tensor-core convolutions (tc_common.cuh): one zero-initialised unsigned int per device,
+// allocated on first use, incremented by every loader thread that staged a value beyond +-65504 / TC_ACT_SCALE.
+static std::atomic<unsigned int*> g_overflow[64];
+unsigned int* tc_overflow_flag() {
+  const int dev = device_index() & 63;
+  unsigned int* p = g_overflow[dev].load(std::memory_order_acquire);
+  if (p) return p;
+  unsigned int* fresh = nullptr;
+  if (cudaMalloc(&fresh, sizeof(unsigned int)) != cudaSuccess || cudaMemset(fresh, 0, sizeof(unsigned int)) != cudaSuccess) {
+    set_error("tc_overflow_flag: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  unsigned int* expected = nullptr;
+  if (!g_overflow[dev].compare_exchange_strong(expected, fresh, std::memory_order_acq_rel)) {
+    (void)cudaFree(fresh);
+    return expected;
+  }
+  return fresh;
+}
 
 int device_index() {
   int dev = 0;
@@ -105,9 +122,20 @@ float osb_set_rz_kappa(float kappa) {
   if (kappa >= 0.f && kappa < 1e-6f) osb::g_rz_kappa.store(kappa, std::memory_order_relaxed);
   return old;
 }
-int osb_set_tf32_split(int mode) {
-  const int old = osb::g_tf32_split.load(std::memory_order_relaxed);
-  if (mode == 0 || mode == 1) osb::g_tf32_split.store(mode, std::memory_order_relaxed);
-  return old;
+int osb_tc_overflow_count(osb_stream_t stream, int reset, unsigned int* count) {
+  using namespace osb;
+  OSB_REQUIRE(count, "tc_overflow_count: null pointer");
+  unsigned int* flag = tc_overflow_flag();
+  if (!flag) return OSB_ECUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(count, flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && reset) e = cudaMemsetAsync(flag, 0, sizeof(unsigned int), st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("tc_overflow_count: %s", cudaGetErrorString(e));
+    return OSB_ECUDA;
+  }
+  return OSB_OK;
 }
+const unsigned int* osb_tc_overflow_flag(void) { return osb::tc_overflow_flag(); }
 }

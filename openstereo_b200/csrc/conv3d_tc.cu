@@ -1,12 +1,9 @@
 // Tensor-core (tcgen05 / TMEM) implicit-GEMM Conv3d 3x3x3, stride 1, pad 1, for the full-resolution layers of the
-// hourglass aggregation (W = 128 output columns = one UMMA M tile).  fp32-accurate through 3xTF32 operand splitting:
-//
-//      a*b  ~=  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi ,   x_hi = x with the low 13 mantissa bits cleared, x_lo = x - x_hi
-//
-// (the kind::tf32 MMA reads only the top 19 bits of each fp32 operand, so a_hi is the raw value; a_lo is produced while
-// the operand is staged; b_hi / b_lo are split once on the host).  Measured on B200 with tools/tc_probe.cu: max error
-// 2.6e-6 against an fp64 reference where an fp32 FMA chain has 1.7e-6 and plain TF32 5.2e-3 -- i.e. this path keeps the
-// north star's 1e-3 px EPE bar that plain TF32/BF16 tensor-core math breaks.
+// hourglass aggregation (W = 128 output columns = one UMMA M tile).  fp32-accurate through 3xFP16 operand splitting
+// (tc_common.cuh):   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi   on tcgen05.mma.kind::f16, fp32 accumulation in TMEM.
+// Activations are split while they are staged (fp32 in HBM -> [hi | lo] fp16 rows in shared memory); weights are split
+// and pre-scaled once on the host.  Plain TF32 / BF16 / FP16 operands break the north star's 1e-3 px EPE bar
+// (2.2e-2 px for TF32); the split keeps it (tests/test_zz_fullsize_gpu.py).
 //
 // Replaces the same reference modules as conv3d.cu (convbn_3d + ReLU of gwcnet/hourglass.py:5-16,
 // gwcnet_disp_processor.py:40-81; conv3d_bn(_relu) psmnet/submodule.py:68-83,160-177) for layers with W == 128.
@@ -20,16 +17,18 @@
 //     that small-N tf32 MMAs hit (tools/tc_probe.cu: N=32, 64 and 96 all take 54-56 cycles).
 //   * kh taps: output row t of the block needs input rows t-1, t, t+1: input rows stream through a shared-memory ring
 //     and each staged row feeds up to three accumulator tiles.
+//   * an operand row is 128 bytes = [32 channels hi | 32 channels lo] fp16, SWIZZLE_128B; a K = 16 MMA step is 32 bytes, so
+//     the hi k-steps sit at descriptor offsets +0, +2 and the lo ones at +4, +6 (16-byte units) of the SAME tile.
 //   * kd taps and 32-channel Cin chunks are phases of one work item; the three kh weight slices of a phase are
 //     refilled just in time (slice kh is free after row 4+kh of a phase and needed again at row kh of the next one).
 // Work item = (image b, output plane d, block of 5 output rows); 5 accumulator tiles x 96 columns = 480 TMEM columns.
 //
 // Operand staging.  A first version fed the ring with TMA (cp.async.bulk.tensor, SWIZZLE_64B boxes of 64-byte rows;
 // kept as profiles/r1_conv3d_tc_tma_variant.cu.txt): correct, but ncu showed the TMA unit request-rate bound (~9 cycles
-// per 64-byte row, 7 B/clk/SM) and the tensor pipe only 34 % busy (profiles/r1_ncu_summary.md).  Here the loader warps
-// read coalesced float4 from global/L2, write the hi tile and the lo tile with the 128-byte swizzle applied by hand,
-// and publish them to the tensor core through fence.proxy.async + mbarrier -- the lo split costs nothing extra and
-// arbitrary gathers (stride 2, multi-row tiles) become possible.
+// per 64-byte row, 7 B/clk/SM) and the tensor pipe only 34 % busy (profiles/r1_ncu_summary.md) -- and fp32 data needs
+// the split anyway.  Here the loader warps read coalesced float4 from global/L2, convert to the hi/lo fp16 pair, write
+// both halves of the row with the 128-byte swizzle applied by hand (two conflict-free STS.64) and publish the tile to the
+// tensor core through fence.proxy.async + mbarrier; arbitrary gathers (stride 2, multi-row tiles) come for free.
 //
 // Warp roles (352 threads, 1 CTA/SM, persistent): warp 0 = MMA issuer (+ TMEM allocator), warps 1-4 = A-row loaders,
 // warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warps 9-10 = weight-slice loaders.
@@ -38,24 +37,24 @@
 namespace osb {
 
 constexpr int TC_W = 128;          // image width handled (UMMA M)
-constexpr int TC_KC = 32;          // input channels per phase (128-byte K-major rows, SWIZZLE_128B)
+constexpr int TC_KC = 32;          // input channels per phase: 128-byte K-major rows [32 hi | 32 lo] fp16, SWIZZLE_128B
 constexpr int TC_TILES = 5;        // output rows (accumulator tiles) per work item
 constexpr int TC_ROWS = TC_TILES + 2;
-constexpr int TC_STAGES = 4;       // A-row ring depth
-constexpr int TC_ROW_BYTES = TC_W * TC_KC * 4;     // 16384: one staged input row (hi or lo)
+constexpr int TC_STAGES = 6;       // A-row ring depth
+constexpr int TC_ROW_BYTES = TC_W * TC_KC * 4;     // 16384: one staged input row (hi and lo halves of every voxel)
 constexpr int TC_THREADS = 352;
 
 struct TcParams {
   const float* x;          // (B, D, H, W, Cin) channels-last
-  const float* w;          // [2 (hi,lo)][3 kd][Cin/32][3 kh][3*Cout][32]
+  const void* w;           // fp16 [3 kd][Cin/32][3 kh][3*Cout][32 hi | 32 lo]  (ops.pack_tc_weight)
   const float* scale;
   const float* shift;
   const float* residual;
   float* y;
   int B, D, H, Cin, Cout;
   int act;
-  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
+  unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -63,17 +62,15 @@ struct TcParams {
 template <int COUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
   constexpr int N3 = 3 * COUT;                      // kw-stacked MMA N
-  constexpr int B_SLICE = N3 * TC_KC * 4;           // one kh weight slice, hi or lo (12288 B for Cout = 32)
+  constexpr int B_SLICE = N3 * TC_KC * 4;           // one kh weight slice, rows [hi | lo] (12288 B for Cout = 32)
   static_assert(B_SLICE % 1024 == 0, "weight slices must stay 1024-byte aligned");
   static_assert(TC_TILES * N3 <= 512, "accumulators exceed TMEM");
-  constexpr int A_HI = 0;
-  constexpr int A_LO = A_HI + TC_STAGES * TC_ROW_BYTES;
-  constexpr int B_OFF = A_LO + TC_STAGES * TC_ROW_BYTES;       // [3 kh][hi | lo]
-  constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
+  constexpr int A_OFF = 0;
+  constexpr int B_OFF = A_OFF + TC_STAGES * TC_ROW_BYTES;      // [3 kh]
+  constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* a_hi = smem + A_HI;
-  uint8_t* a_lo = smem + A_LO;
+  uint8_t* a_buf = smem + A_OFF;
   uint8_t* b_buf = smem + B_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
@@ -125,7 +122,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   // ---------------------------------------------------------------------------------------------- MMA issuer
   if (warp == 0) {
     {
-      const uint32_t idesc = idesc_tf32(128, N3);
+      const uint32_t idesc = idesc_f16(128, N3);
+      constexpr uint32_t LO = TcK<TC_KC>::LO_OFF;     // descriptor offset of the lo half of an operand row
       const uint64_t dbase = desc_sw128_base();
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 bytes).
       const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
@@ -147,8 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
               mbar_wait(&a_ready[s], par);
               if (r < 3) mbar_wait(&b_full[r], phc & 1);       // slice kh = r is first needed by row r (tile 0)
               tc_fence_after();
-              const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
-              const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
+              const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
                 const int t = r - kh;                 // output row tile fed by input row r through tap kh (compile time)
@@ -161,14 +158,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
                 }
                 if (t < ntiles) {
                   const uint32_t acc = tmem + t * N3;
-                  const uint64_t dbh0 = dbase | (uint64_t)(b16 + kh * (2 * B_SLICE / 16));
-                  const uint64_t dbl0 = dbh0 + B_SLICE / 16;
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + kh * (B_SLICE / 16));
                   if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                      mma_tf32(acc, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
-                      mma_tf32(acc, dah0 + 2 * ks, dbl0 + 2 * ks, idesc, 1);
-                      mma_tf32(acc, dah0 + 2 * ks, dbh0 + 2 * ks, idesc, 1);
+                    for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
+                      mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                      mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc, 1);
+                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
                     }
                   }
                   __syncwarp();
@@ -190,7 +186,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   // ---------------------------------------------------------------------------------------------- A-row loaders
   else if (warp < 5) {
     const int lt = threadIdx.x - 32;                 // 0..127
-    const int vcol = lt >> 3, c16 = lt & 7;          // this thread's voxel (mod 16) and 16-byte chunk of the 128-byte row
+    const int vsel = lt >> 3, c16 = lt & 7;          // this thread's voxel (mod 16) and fp32 16-byte chunk of the 32-channel slice
+    // voxel order inside a half-warp alternates bit 2 of the column so that the STS.64 pairs of stage_f16_split hit disjoint banks
+    const int vcol = ((vsel & 1) << 2) | ((vsel >> 1) & 3) | (vsel & 8);
+    float amax = 0.f;
     const size_t row_stride = (size_t)TC_W * p.Cin;  // floats per image row
     // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run TWO rows ahead of
     // the stores (software pipeline in registers) so that a full L2/HBM round trip is always in flight.
@@ -234,17 +233,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     auto store_row = [&](const float4 (&v)[8]) {
       const uint32_t s = rowc % TC_STAGES, par = (rowc / TC_STAGES) & 1;
       mbar_wait_relaxed(&a_empty[s], par ^ 1);        // the MMAs that read this slot last time have completed
-      uint8_t* hi = a_hi + s * TC_ROW_BYTES;
-      uint8_t* lo = a_lo + s * TC_ROW_BYTES;
+      uint8_t* tile = a_buf + s * TC_ROW_BYTES;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int m = vcol + 16 * j;                  // tile row = image column
-        const int off = m * 128 + ((c16 ^ (m & 7)) << 4);   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-        float4 vh, vl;
-        tf32_split4(v[j], p.split, vh, vl);
-        *reinterpret_cast<float4*>(hi + off) = vh;
-        *reinterpret_cast<float4*>(lo + off) = vl;
-      }
+      for (int j = 0; j < 8; ++j) stage_f16_split<TC_KC>(tile, vcol + 16 * j, c16, v[j], amax);   // tile row = image column
       fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_ready[s]);
       ++rowc;
@@ -265,6 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       has_b = has_a && advance(ld);
       if (has_b) load_row(ld, vb);
     }
+    tc_report_overflow(p.overflow, amax);
   }
   // ---------------------------------------------------------------------------------------------- epilogue
   else if (warp < 9) {
@@ -278,7 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const int h0 = hb * TC_TILES;
       const int ntiles = min(TC_TILES, p.H - h0);
       // MMAs each P_kw accumulator received: (existing kd planes) x chunks x 3 kh x k-steps x 3 split terms
-      const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (d + 1 < p.D)) * nchunk * 3 * (TC_KC / 8) * 3);
+      const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (d + 1 < p.D)) * nchunk * 3 * TcK<TC_KC>::KSTEPS * 3);
       // D[m] = P0[m-1] + P1[m] + P2[m+1], tile by tile as the MMA warp releases them
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_relaxed(&acc_full[t], itc & 1);
@@ -368,7 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   // ---------------------------------------------------------------------------------------------- weight-slice loaders
   else {
     const int wt = threadIdx.x - 9 * 32;             // 0..63
-    constexpr int F4_PER_HALF = B_SLICE / 16;        // 768 float4 per (kh, hi|lo)
+    constexpr int CHUNKS = B_SLICE / 16;             // 768 16-byte chunks per kh slice
+    const uint4* wsrc = reinterpret_cast<const uint4*>(p.w);
     uint32_t phc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int d = (it / p.hblocks) % p.D;
@@ -377,24 +370,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         if (din < 0 || din >= p.D) continue;
         for (int ch = 0; ch < nchunk; ++ch, ++phc) {
           for (int kh = 0; kh < 3; ++kh) {
-            // global slice (half, kd, ch, kh): N3 rows x 32 floats, row-major
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)(N3 * TC_KC);
-            const size_t half_stride = (size_t)3 * nchunk * 3 * N3 * TC_KC;
-            float4 v[2][F4_PER_HALF / 64];
+            // global slice (kd, ch, kh): N3 rows x 128 bytes, row-major
+            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)CHUNKS;
+            uint4 v[CHUNKS / 64];
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int j = 0; j < F4_PER_HALF / 64; ++j)
-                v[half][j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
+            for (int j = 0; j < CHUNKS / 64; ++j) v[j] = __ldg(wsrc + slice + wt + 64 * j);
             mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);   // last reader (row 4+kh of the previous phase) is done
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int j = 0; j < F4_PER_HALF / 64; ++j) {
-                const int f = wt + 64 * j;            // float4 index inside the slice: row n = f / 8, chunk = f % 8
-                const int n = f >> 3, c = f & 7;
-                *reinterpret_cast<float4*>(b_buf + (kh * 2 + half) * B_SLICE + n * 128 + ((c ^ (n & 7)) << 4)) = v[half][j];
-              }
+            for (int j = 0; j < CHUNKS / 64; ++j) {
+              const int f = wt + 64 * j;              // chunk index inside the slice: row n = f / 8, chunk = f % 8
+              const int n = f >> 3, c = f & 7;
+              *reinterpret_cast<uint4*>(b_buf + kh * B_SLICE + n * 128 + ((c ^ (n & 7)) << 4)) = v[j];
+            }
             fence_proxy_async();
             mbar_arrive(&b_full[kh]);
           }
@@ -431,7 +418,7 @@ __global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __rest
 template <int COUT>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   constexpr int N3 = 3 * COUT;
-  const size_t smem = 1024 + 2 * (size_t)TC_STAGES * TC_ROW_BYTES + 3 * 2 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_ROW_BYTES + 3 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
                       3 * COUT * 4 + TP_BYTES;
   auto kernel = conv3d_tc_kernel<COUT>;
   static PerDeviceFlag configured;
@@ -450,9 +437,9 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
   return check_launch("conv3d_tc_kernel");
 }
 
-int launch_tcg_dispatch(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
-int launch_tcg_dilated2(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+int launch_tcg_dilated2(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
 
 }  // namespace osb
@@ -482,7 +469,7 @@ int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int
   return check_launch("ncdhw_to_ndhwc_kernel");
 }
 
-int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
   using namespace osb;
@@ -499,7 +486,8 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float
   TcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.Cout = Cout, p.act = act;
-  p.split = tf32_split_mode(), p.kappa = rz_kappa();
+  p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  OSB_REQUIRE(p.overflow, "conv3d_k3_tc: cannot allocate the overflow flag");
   p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;
@@ -514,7 +502,7 @@ int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation) {
   return 0;
 }
 
-int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const float* w_split, const float* scale, const float* shift, const float* residual,
+int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const void* w_split, const float* scale, const float* shift, const float* residual,
                          float* y, int B, int Cin, int Cout, int H, int W, int dilation, int act, int out_nhwc, int res_nhwc,
                          osb_stream_t stream) {
   using namespace osb;

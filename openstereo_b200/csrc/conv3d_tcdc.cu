@@ -2,7 +2,7 @@
 //   conv5 128->64 / 64->64 (1/16 -> 1/8 res) and conv6 64->32 (1/8 -> 1/4 res): gwcnet/hourglass.py:35-41,
 //   psmnet/psmnet_cost_processor.py:99-106 (deconv3d_bn).
 // Per dimension an output index o gathers  o even (=2m): tap k=1 from input m;  o odd (=2m+1): k=0 from m+1 and k=2 from m.
-// Same machinery as conv3d_tcg.cu / conv3d_tcs2.cu (3xTF32 split, LDG-staged swizzled operands, warp-specialised
+// Same machinery as conv3d_tcg.cu / conv3d_tcs2.cu (3xFP16 split, LDG-staged swizzled operands, warp-specialised
 // persistent CTA).  An accumulator tile holds the output rows of ONE parity class: plane od, rows oh = 2j + ph for
 // R = 128/Win consecutive j, all 2*Win output columns.  For each valid tap pair (kd, kh) the operand tile is the R input
 // rows j (+1 for k=0) of input plane id, un-shifted in w, and one MMA with the kw slices stacked along N gives
@@ -15,15 +15,15 @@ namespace osb {
 
 struct TcdcParams {
   const float* x;          // (B, D, H, W, Cin) channels-last
-  const float* w;          // [2 (hi,lo)][3 kd][Cin/KC][3 kh][3*Cout][KC]
+  const void* w;           // fp16 [3 kd][Cin/KC][3 kh][3*Cout][KC hi | KC lo]  (ops.pack_tc_weight)
   const float* scale;
   const float* shift;
   const float* residual;
   float* y;
   int B, D, H, Cin;        // INPUT extent D x H x W; output is 2D x 2H x 2W
   int act;
-  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
+  unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -31,16 +31,17 @@ struct TcdcParams {
 template <int COUT, int KC, int W, int TILES>     // W = INPUT width
 struct TcdcCfg {
   static constexpr int R = 128 / W;                         // input rows (= output rows of one parity) per M tile
-  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row
+  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row: [KC fp16 hi | KC fp16 lo]
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = 3 * COUT;
-  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
-  static constexpr int STAGES = (COUT >= 128) ? 3 : 4;   // the Cout = 128 weight slices leave room for 3
+  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
+  static constexpr int STAGES = 4;                          // one loader warp per ring slot
   static constexpr int HBLK = TILES * R;                    // output rows per work item
-  static constexpr int KSTEPS = KC / 8;
+  static constexpr int KSTEPS = KC / 16;                    // K = 16 fp16 channels per MMA
+  static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
   static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
-  static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
+  static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
+  static constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
@@ -80,8 +81,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   using C = TcdcCfg<COUT, KC, W, TILES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* a_hi = smem + C::A_OFF;
-  uint8_t* a_lo = a_hi + C::STAGES * C::UNIT_BYTES;
+  uint8_t* a_buf = smem + C::A_OFF;
   uint8_t* b_buf = smem + C::B_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
 
   // ---------------------------------------------------------------------------------------------- MMA issuer
   if (warp == 0) {
-    const uint32_t idesc = idesc_tf32(128, C::N3);
+    const uint32_t idesc = idesc_f16(128, C::N3);
     const uint64_t dbase = (KC == 32) ? desc_sw128_base() : desc_sw64_base();
     const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
     uint32_t unitc = 0, itc = 0;
@@ -161,16 +161,14 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               }
               if (t < ntiles) {
                 if (elect_one()) {
-                  const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
-                  const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+                  const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
                   const uint32_t acc = tmem + t * C::N3;
-                  const uint64_t dbh0 = dbase | (uint64_t)(b16 + (kh * 2 * C::B_SLICE) / 16);
-                  const uint64_t dbl0 = dbh0 + C::B_SLICE / 16;
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + (kh * C::B_SLICE) / 16);
 #pragma unroll
                   for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                    mma_tf32(acc, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
-                    mma_tf32(acc, dah0 + 2 * ks, dbl0 + 2 * ks, idesc, 1);
-                    mma_tf32(acc, dah0 + 2 * ks, dbh0 + 2 * ks, idesc, 1);
+                    mma_f16(acc, da0 + C::LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                    mma_f16(acc, da0 + 2 * ks, db0 + C::LO + 2 * ks, idesc, 1);
+                    mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
                   }
                 }
                 __syncwarp();
@@ -197,11 +195,13 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   // bodies took the kernel to 254 KB of code).
   else if (warp < 5) {
     const int lw = warp - 1;
-    constexpr int CPR = C::ROWB / 16;                // 16-byte chunks per operand row (8 or 4)
+    static_assert(KC == 16, "lane_voxel / unit-row mapping below is written for 64-byte operand rows");
+    constexpr int CPR = KC / 4;                      // fp32 16-byte chunks per voxel of the K chunk
     constexpr int VPL = 32 / CPR;                    // voxels covered by one warp-wide LDG.128
     constexpr int NLD = 128 / VPL;                   // loads per lane per unit
     static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
-    const int v0 = lane / CPR, c = lane % CPR;
+    const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
+    float amax = 0.f;
     const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
     auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
@@ -216,16 +216,9 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* hi = a_hi + lw * C::UNIT_BYTES;
-      uint8_t* lo = a_lo + lw * C::UNIT_BYTES;
+      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
 #pragma unroll
-      for (int j = 0; j < NLD; ++j) {
-        const int off = swz_offset<KC>(v0 + VPL * j, c);
-        float4 vh, vl;
-        tf32_split4(v[j], p.split, vh, vl);
-        *reinterpret_cast<float4*>(hi + off) = vh;
-        *reinterpret_cast<float4*>(lo + off) = vl;
-      }
+      for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
     };
@@ -253,6 +246,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
         }
       }
     }
+    tc_report_overflow(p.overflow, amax);
   }
   // ---------------------------------------------------------------------------------------------- epilogue
   else if (warp < 9) {
@@ -392,19 +386,15 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
         for (int ch = 0; ch < nchunk; ++ch) {
           for (int kh = 0; kh < 3; ++kh) {
             if (!kh_valid(w.ph, kh)) continue;
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)(C::N3 * KC);
-            const size_t half_stride = (size_t)3 * nchunk * 3 * C::N3 * KC;
+            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)F4;
+            uint4 v[PER];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 v[PER];
+            for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(p.w) + slice + wt + 64 * j);
+            mbar_wait_relaxed(&b_empty[kh], (bph[kh] & 1) ^ 1);
 #pragma unroll
-              for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
-              if (half == 0) mbar_wait_relaxed(&b_empty[kh], (bph[kh] & 1) ^ 1);
-#pragma unroll
-              for (int j = 0; j < PER; ++j) {
-                const int f = wt + 64 * j;
-                *reinterpret_cast<float4*>(b_buf + (kh * 2 + half) * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
-              }
+            for (int j = 0; j < PER; ++j) {
+              const int f = wt + 64 * j;
+              *reinterpret_cast<uint4*>(b_buf + kh * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
             }
             fence_proxy_async();
             mbar_arrive(&b_full[kh]);
@@ -461,7 +451,7 @@ int osb_deconv3d_tc_supported(int Cin, int Cout, int W) {
   return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) ? 1 : 0;
 }
 
-int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const float* scale, const float* shift,
+int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                            int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
   using namespace osb;
@@ -472,7 +462,8 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const float* w_split, const flo
   TcdcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
-  p.split = tf32_split_mode(), p.kappa = rz_kappa();
+  p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
   cudaStream_t s = (cudaStream_t)stream;
   if (W == 32) return launch_tcdc<64, 16, 32, 2>(p, s);
   return launch_tcdc<32, 16, 64, 5>(p, s);

@@ -2,12 +2,12 @@
 // 128-row UMMA tile: an M tile is R = 128 / W consecutive image rows (W = 64 -> 2 rows, W = 32 -> 4 rows).
 //   conv2 64->64 @ 1/8 res, conv4 128->128 (GwcNet) / 64->64 (PSMNet) @ 1/16 res:
 //   gwcnet/hourglass.py:25-32, psmnet/psmnet_cost_processor.py:86-98.
-// Same scheme as conv3d_tc.cu (3xTF32 split, kw taps stacked along N and un-shifted in the epilogue, LDG-staged swizzled
+// Same scheme as conv3d_tc.cu (3xFP16 split, kw taps stacked along N and un-shifted in the epilogue, LDG-staged swizzled
 // operands, warp-specialised persistent CTA), generalised:
 //   * an A "unit" is R consecutive input rows starting at block row s; tap kh of output tile t reads the unit with
 //     s = t*R + kh - 1, so units are shared between taps/tiles whenever those starts coincide;
-//   * K chunks are 16 channels (64-byte rows, SWIZZLE_64B) so that the three kh weight slices of a phase fit in shared
-//     memory next to the ring for Cout = 64 / 128;
+//   * K chunks are 16 channels (64-byte rows [16 hi | 16 lo] fp16, SWIZZLE_64B: one K = 16 MMA step each) so that the three
+//     kh weight slices of a phase fit in shared memory next to the ring for Cout = 64 / 128;
 //   * for Cout = 128 the kw-stacked N = 384 exceeds the UMMA maximum and is issued as three N = 128 MMAs;
 //   * the epilogue's +-1 column shift never crosses an image-row boundary (tile rows are whole image rows).
 #include "tc_common.cuh"
@@ -16,15 +16,15 @@ namespace osb {
 
 struct TcgParams {
   const float* x;          // (B, D, H, W, Cin) channels-last
-  const float* w;          // [2 (hi,lo)][3 kd][Cin/KC][3 kh][3*Cout][KC]
+  const void* w;           // fp16 [3 kd][Cin/KC][3 kh][3*Cout][KC hi | KC lo]  (ops.pack_tc_weight)
   const float* scale;
   const float* shift;
   const float* residual;
   float* y;
   int B, D, H, Cin;
   int act;
-  int split;         // 3xTF32 split policy (tc_common.cuh: tf32_split4)
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
+  unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
 };
@@ -35,20 +35,21 @@ struct TcgCfg {
   // tap kh of output row t reads input row t + (kh-1)*DIL, the kw-stacked partial sums are un-shifted by DIL columns.
   static_assert(DIL == 1 || (W == 128 && DIL == 2 && COUT >= 64), "dilation 2 is instantiated for full-width rows only");
   static constexpr int R = 128 / W;                         // image rows per M tile
-  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row
+  static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row: [KC fp16 hi | KC fp16 lo]
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = 3 * COUT;
   static constexpr int NMMA = (N3 <= 256) ? 1 : 3;          // MMAs per (A unit, weight slice, k step)
   static constexpr int NPER = N3 / NMMA;
-  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice, hi or lo
-  static constexpr int STAGES = (COUT >= 128) ? 3 : 4;   // the Cout = 128 weight slices leave room for 3
+  static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
+  static constexpr int STAGES = 4;                          // one loader warp per ring slot
   static constexpr int S_FIRST = -DIL;                      // unit start rows run from S_FIRST to S_LAST (block-relative)
   static constexpr int S_LAST = (TILES - 1) * R + DIL;
   static constexpr int HBLK = TILES * R;                    // output rows per work item
-  static constexpr int KSTEPS = KC / 8;
+  static constexpr int KSTEPS = KC / 16;                    // K = 16 fp16 channels per MMA
+  static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
   static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = A_OFF + 2 * STAGES * UNIT_BYTES;
-  static constexpr int BAR_OFF = B_OFF + 3 * 2 * B_SLICE;
+  static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
+  static constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * DIL * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
@@ -68,8 +69,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
   using C = TcgCfg<COUT, KC, W, TILES, DIL>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* a_hi = smem + C::A_OFF;
-  uint8_t* a_lo = a_hi + C::STAGES * C::UNIT_BYTES;
+  uint8_t* a_buf = smem + C::A_OFF;
   uint8_t* b_buf = smem + C::B_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
 
   // ---------------------------------------------------------------------------------------------- MMA issuer
   if (warp == 0) {
-    const uint32_t idesc = idesc_tf32(128, C::NPER);
+    const uint32_t idesc = idesc_f16(128, C::NPER);
     const uint64_t dbase = (KC == 32) ? desc_sw128_base() : desc_sw64_base();
     const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
     uint32_t unitc = 0, phc = 0, itc = 0;
@@ -143,8 +143,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
             for (int kh = 0; kh < 3; ++kh)
               if (C::tile_of(s, kh) == 0) mbar_wait(&b_full[kh], phc & 1);      // slice kh is first needed by the unit feeding tile 0
             tc_fence_after();
-            const uint64_t dah0 = dbase | (uint64_t)((smem_u32(a_hi + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
-            const uint64_t dal0 = dbase | (uint64_t)((smem_u32(a_lo + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
+            const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               const int t = C::tile_of(s, kh);
@@ -160,13 +159,12 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
 #pragma unroll
                   for (int mm = 0; mm < C::NMMA; ++mm) {
                     const uint32_t acc = tmem + t * C::N3 + mm * C::NPER;
-                    const uint64_t dbh0 = dbase | (uint64_t)(b16 + (kh * 2 * C::B_SLICE + mm * C::NPER * C::ROWB) / 16);
-                    const uint64_t dbl0 = dbh0 + C::B_SLICE / 16;
+                    const uint64_t db0 = dbase | (uint64_t)(b16 + (kh * C::B_SLICE + mm * C::NPER * C::ROWB) / 16);
 #pragma unroll
                     for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                      mma_tf32(acc, dal0 + 2 * ks, dbh0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
-                      mma_tf32(acc, dah0 + 2 * ks, dbl0 + 2 * ks, idesc, 1);
-                      mma_tf32(acc, dah0 + 2 * ks, dbh0 + 2 * ks, idesc, 1);
+                      mma_f16(acc, da0 + C::LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                      mma_f16(acc, da0 + 2 * ks, db0 + C::LO + 2 * ks, idesc, 1);
+                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
                     }
                   }
                 }
@@ -194,11 +192,13 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
   // bodies took the kernel to 254 KB of code).
   else if (warp < 5) {
     const int lw = warp - 1;
-    constexpr int CPR = C::ROWB / 16;                // 16-byte chunks per operand row (8 or 4)
+    static_assert(KC == 16, "lane_voxel / unit-row mapping below is written for 64-byte operand rows");
+    constexpr int CPR = KC / 4;                      // fp32 16-byte chunks per voxel of the K chunk
     constexpr int VPL = 32 / CPR;                    // voxels covered by one warp-wide LDG.128
     constexpr int NLD = 128 / VPL;                   // loads per lane per unit
     static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
-    const int v0 = lane / CPR, c = lane % CPR;
+    const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
+    float amax = 0.f;
     const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
     auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
@@ -213,16 +213,9 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* hi = a_hi + lw * C::UNIT_BYTES;
-      uint8_t* lo = a_lo + lw * C::UNIT_BYTES;
+      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
 #pragma unroll
-      for (int j = 0; j < NLD; ++j) {
-        const int off = swz_offset<KC>(v0 + VPL * j, c);
-        float4 vh, vl;
-        tf32_split4(v[j], p.split, vh, vl);
-        *reinterpret_cast<float4*>(hi + off) = vh;
-        *reinterpret_cast<float4*>(lo + off) = vl;
-      }
+      for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
     };
@@ -249,6 +242,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
         }
       }
     }
+    tc_report_overflow(p.overflow, amax);
   }
   // ---------------------------------------------------------------------------------------------- epilogue
   else if (warp < 9) {
@@ -354,10 +348,11 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
   // ---------------------------------------------------------------------------------------------- weight-slice loaders
   else {
     const int wt = threadIdx.x - 9 * 32;             // 0..63
-    constexpr int F4 = C::B_SLICE / 16;              // float4 per (kh, hi|lo)
+    constexpr int F4 = C::B_SLICE / 16;              // 16-byte chunks per kh slice
     constexpr int PER = F4 / 64;                     // per thread
     constexpr int CPR = C::ROWB / 16;
     static_assert(F4 % 64 == 0, "weight slice must split evenly over 64 loader threads");
+    const uint4* wsrc = reinterpret_cast<const uint4*>(p.w);
     uint32_t phc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int d = (it / p.hblocks) % p.D;
@@ -366,19 +361,15 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
         if (din < 0 || din >= p.D) continue;
         for (int ch = 0; ch < nchunk; ++ch, ++phc) {
           for (int kh = 0; kh < 3; ++kh) {
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)(C::N3 * KC);
-            const size_t half_stride = (size_t)3 * nchunk * 3 * C::N3 * KC;
+            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)F4;
+            uint4 v[PER];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 v[PER];
+            for (int j = 0; j < PER; ++j) v[j] = __ldg(wsrc + slice + wt + 64 * j);
+            mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);
 #pragma unroll
-              for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p.w + half * half_stride + slice) + wt + 64 * j);
-              if (half == 0) mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);
-#pragma unroll
-              for (int j = 0; j < PER; ++j) {
-                const int f = wt + 64 * j;
-                *reinterpret_cast<float4*>(b_buf + (kh * 2 + half) * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
-              }
+            for (int j = 0; j < PER; ++j) {
+              const int f = wt + 64 * j;
+              *reinterpret_cast<uint4*>(b_buf + kh * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
             }
             fence_proxy_async();
             mbar_arrive(&b_full[kh]);
@@ -426,12 +417,13 @@ static int launch_tcg(TcgParams& p, cudaStream_t stream) {
 }
 
 // dispatcher used by conv3d_tc.cu's C entry point; returns -1 when the shape has no generic instantiation
-int launch_tcg_dispatch(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream) {
   TcgParams p{};
   p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
-  p.split = tf32_split_mode(), p.kappa = rz_kappa();
+  p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  if (!p.overflow) return OSB_ECUDA;
   if (Cin % 16 != 0 || Cin < 16) return -1;
   if (W == 64 && Cout == 64) return launch_tcg<64, 16, 64, 2>(p, stream);
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
@@ -442,12 +434,13 @@ int launch_tcg_dispatch(const float* x, const float* w, const float* scale, cons
 }
 
 // dilated (2) one-plane variant for the 2D backbone: same parameters with D == 1
-int launch_tcg_dilated2(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y,
+int launch_tcg_dilated2(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream) {
   TcgParams p{};
   p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = 1, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
-  p.split = tf32_split_mode(), p.kappa = rz_kappa();
+  p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  if (!p.overflow) return OSB_ECUDA;
   if (Cin % 16 != 0 || Cin < 16) return -1;
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1, 2>(p, stream);
   return -1;

@@ -34,12 +34,13 @@ __device__ __forceinline__ uint64_t desc_sw128_base() {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor of a dense kind::f16 MMA: fp16 A and B (formats 0), fp32 accumulator, both operands K-major.
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -75,24 +76,45 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
-// 3xTF32 operand split.  A kind::tf32 MMA reads only the top 19 bits of an fp32 operand (truncation), so the split is done
-// here, before the operand reaches shared memory:
-//   mode 0 (round 1, kept for the bisect): hi = x (hardware truncates), lo = x - trunc(x); both truncations and the dropped
-//           lo*lo term shrink every product towards zero -- a BIAS of up to 2^-19 per product that adds up coherently;
-//   mode 1: hi = rna_tf32(x), lo = rna_tf32(x - hi): both parts are exact TF32 values, the hardware truncation is a no-op, and
-//           the residual (|x - hi - lo| <= 2^-23 |x|, lo*lo <= 2^-22 |x||y|) is zero-mean.
-__device__ __forceinline__ float tf32_rna(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
-__device__ __forceinline__ void tf32_split4(const float4 v, int mode, float4& hi, float4& lo) {
-  if (mode == 0) {
-    hi = v;
-    lo = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
-                     v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-  } else {
-    hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-    lo = make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
-  }
+// 3xFP16 operand split (fp32-accurate products on the 16-bit tensor-core rate).
+//   x * s  =  hi + lo + r,   hi = fp16_rn(x*s),  lo = fp16_rn(x*s - hi),   |r| <= max(2^-22 |x*s|, 2^-25)
+// and every product is issued as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  on tcgen05.mma.kind::f16 with fp32 accumulation in TMEM
+// (the dropped lo*lo term is <= 2^-22 of the product; both roundings are to nearest, so the residual is zero-mean).  fp16
+// carries the same 11 significant bits as TF32, so the accuracy equals the 3xTF32 scheme this replaces (round 1 / early round 2)
+// while an MMA instruction covers K = 16 channels instead of 8: half the MMAs, half the operand bytes in shared memory --
+// the two resources that bounded the TF32 kernels.  What fp16 lacks is exponent range, hence the
+// power-of-two scales: activations are staged as x * TC_ACT_SCALE (|x| < 65504 / TC_ACT_SCALE = 4094 is representable; smaller
+// magnitudes keep 22 significant bits down to |x| ~ 2^-7 and an ABSOLUTE error of 2^-29 below that), weights are pre-scaled per
+// output channel on the host so that max |w| lands in [2^14, 2^15) (ops.pack_tc_weight), and the epilogue's folded-BN scale
+// carries the exact inverse 2^-(e_c + 4).  Conversions saturate (no inf/NaN poisoning) and a sticky device flag records any
+// |x * s| > 65504 (osb_tc_overflow_count; the Python engines check it and refuse to return silently wrong results).
+constexpr float TC_ACT_SCALE = 16.f;
+constexpr float TC_F16_MAX = 65504.f;
+// {lo 16 bits: fp16(a), hi 16 bits: fp16(b)}, round to nearest even, saturating to +-65504
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-int tf32_split_mode();      // api.cu: process-wide split policy (osb_set_tf32_split)
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t h) {
+  float2 f;
+  asm("{\n.reg .b16 l, u;\nmov.b32 {l, u}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, u;\n}\n" : "=f"(f.x), "=f"(f.y) : "r"(h));
+  return f;
+}
+// four fp32 channels -> 4 fp16 hi parts + 4 fp16 lo parts of x * TC_ACT_SCALE; amax tracks max |x * s| for the overflow flag
+__device__ __forceinline__ void f16_split4(const float4 v, uint2& hi, uint2& lo, float& amax) {
+  const float x0 = v.x * TC_ACT_SCALE, x1 = v.y * TC_ACT_SCALE, x2 = v.z * TC_ACT_SCALE, x3 = v.w * TC_ACT_SCALE;
+  amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3))));
+  hi.x = cvt_f16x2_sat(x0, x1);
+  hi.y = cvt_f16x2_sat(x2, x3);
+  const float2 h01 = f16x2_to_float2(hi.x), h23 = f16x2_to_float2(hi.y);
+  lo.x = cvt_f16x2_sat(x0 - h01.x, x1 - h01.y);
+  lo.y = cvt_f16x2_sat(x2 - h23.x, x3 - h23.y);
+}
+unsigned int* tc_overflow_flag();      // api.cu: device address of the sticky overflow counter of the CURRENT device
+__device__ __forceinline__ void tc_report_overflow(unsigned int* flag, float amax) {
+  if (amax > TC_F16_MAX) atomicAdd(flag, 1u);
+}
 
 // The TMEM accumulator of tcgen05.mma rounds TOWARDS ZERO (tools/tc_probe.cu acc, profiles/r2_acc_probe.log: accumulating the same
 // positive product block n times loses n * 2^-24 of the sum, where round-to-nearest would lose ~sqrt(n) * 2^-25).  Each MMA
@@ -120,6 +142,31 @@ __device__ __forceinline__ int swz_offset(int row, int c) {
   else return row * 64 + ((c ^ ((row >> 1) & 3)) << 4);                        // SWIZZLE_64B
 }
 
+
+// Stage four fp32 channels (fp32 16-byte chunk `q` of the KC-channel slice of operand row `row`) into a swizzled operand tile whose
+// K-major rows hold [KC fp16 hi | KC fp16 lo] = 4*KC bytes: hi part to 16-byte chunk q/2, lo part to chunk KC/8 + q/2, 8 bytes each.
+template <int KC>
+__device__ __forceinline__ void stage_f16_split(uint8_t* tile, int row, int q, const float4 v, float& amax) {
+  uint2 hi, lo;
+  f16_split4(v, hi, lo, amax);
+  const int sub = (q & 1) << 3;
+  *reinterpret_cast<uint2*>(tile + swz_offset<KC>(row, q >> 1) + sub) = hi;
+  *reinterpret_cast<uint2*>(tile + swz_offset<KC>(row, KC / 8 + (q >> 1)) + sub) = lo;
+}
+// Lane -> operand row inside a warp-wide load of VPL = 128 / KC voxels (KC/4 lanes each), permuted so that the two STS.64 of
+// stage_f16_split are bank-conflict free per half-warp: SWIZZLE_128B rows (KC = 32) must differ in bit 2, SWIZZLE_64B rows
+// (KC = 16) must be {r, r+1, r+4, r+5}.  Global loads stay whole 16-byte chunks of whole voxels either way.
+template <int KC>
+__device__ __forceinline__ int lane_voxel(int lane) {
+  if constexpr (KC == 32) return (((lane >> 3) & 1) << 2) | (lane >> 4);                       // 4 voxels: 0,4 | 1,5 (caller adds the rest)
+  else return ((lane >> 2) & 1) | (((lane >> 3) & 1) << 2) | ((lane >> 4) << 1);               // 8 voxels: 0,1,4,5 | 2,3,6,7
+}
+// MMAs issued per accumulator per staged (unit, weight slice): k-steps of 16 channels x 3 split terms
+template <int KC>
+struct TcK {
+  static constexpr int KSTEPS = KC / 16;
+  static constexpr int LO_OFF = KC / 8;           // descriptor start-address offset (16-byte units) of the lo half of a row
+};
 
 // ------------------------------------------------------------------------------- coalesced channels-last epilogue output
 // An epilogue thread owns ONE voxel and all of its channels.  Storing those directly makes every STG.128 of a warp touch

@@ -292,7 +292,7 @@ def conv3d_1x1(x0, w_packed, scale=None, shift=None, residual=None, gate=None, a
     return y.squeeze(2) if squeeze else y
 
 
-# --------------------------------------------------------------------------- tensor-core conv (tcgen05, 3xTF32)
+# --------------------------------------------------------------------------- tensor-core conv (tcgen05, 3xFP16 split)
 def conv3d_tc_supported(cin, cout, w, stride=1):
     return bool(_lib.lib.osb_conv3d_tc_supported(int(cin), int(cout), int(w), int(stride)))
 
@@ -303,20 +303,12 @@ def conv3d_tc_kc(cin, cout, w, stride=1):
 
 
 def tc_operand_kind():
-    """MMA kind of the tensor-core convolutions: "tf32" (3xTF32 split) or "f16" (3xFP16 split)."""
-    return "tf32"
+    """MMA kind of the tensor-core convolutions: "f16" (3xFP16 operand split, csrc/tc_common.cuh)."""
+    return "f16"
 
 
-_TF32_SPLIT = 1      # must match the library's policy (osb_set_tf32_split); 1 = round-to-nearest (unbiased), 0 = round 1's truncation
-
-
-def set_tf32_split(mode):
-    """Select the 3xTF32 operand-split policy of the tensor-core convolutions, library and weight packing together
-    (include/openstereo_b200.h: osb_set_tf32_split).  Weights packed before the call must be re-packed (new engine)."""
-    global _TF32_SPLIT
-    assert mode in (0, 1)
-    _lib.lib.osb_set_tf32_split(int(mode))
-    _TF32_SPLIT = int(mode)
+TC_ACT_SCALE_LOG2 = 4        # activations are staged as x * 2^4 (csrc/tc_common.cuh: TC_ACT_SCALE); |x| must stay below 4094
+TC_WEIGHT_TOP_LOG2 = 15      # per output channel, weights are scaled so that max |w| * 2^e lies in [2^14, 2^15)
 
 
 def set_rz_kappa(kappa):
@@ -325,32 +317,71 @@ def set_rz_kappa(kappa):
     return float(_lib.lib.osb_set_rz_kappa(float(kappa)))
 
 
-def tf32_split(w):
-    """fp32 tensor -> (hi, lo), both exactly representable in TF32 (low 13 mantissa bits zero) under the default policy:
-    hi = w rounded to nearest (ties away, like cvt.rna.tf32.f32), lo = (w - hi) rounded to nearest.  |w - hi - lo| <= 2^-23 |w|
-    with zero mean.  Policy 0 reproduces round 1: hi = w truncated, lo = w - hi left for the MMA to truncate (biased)."""
+def tc_overflow_count(device=None, reset=False):
+    """Number of loader threads (since the last reset) that staged an activation outside the fp16 range of the tensor-core
+    convolutions (|x| >= 4094).  Synchronises the current stream of `device`.  0 = every result is valid."""
+    import ctypes
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = ctypes.c_uint(0)
+    with torch.cuda.device(dev):
+        rc = _lib.lib.osb_tc_overflow_count(torch.cuda.current_stream(dev).cuda_stream, 1 if reset else 0, ctypes.byref(out))
+    if rc != 0:
+        raise RuntimeError("osb_tc_overflow_count: %s" % (_lib.lib.osb_last_error() or b"").decode())
+    return int(out.value)
+
+
+def f16_split(w):
+    """fp32 tensor (already scaled into the fp16 range) -> (hi, lo) fp16 with hi = rn(w), lo = rn(w - hi):
+    |w - hi - lo| <= 2^-22 |w| while lo stays a normal fp16 number (|w| >= 2^-3), 2^-25 absolute below that."""
     w = w.contiguous()
-    if _TF32_SPLIT == 0:
-        hi = (w.view(torch.int32) & -8192).view(torch.float32)
-        return hi, w - hi
-    hi = ((w.view(torch.int32) + 4096) & -8192).view(torch.float32)
-    lo = w - hi
-    return hi, ((lo.view(torch.int32) + 4096) & -8192).view(torch.float32)
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+class TcWeight:
+    """A conv weight packed for the tcgen05 kernels: `data` fp16 [3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc hi | kc lo] of
+    w * 2^e_c, and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply."""
+    __slots__ = ("data", "inv", "kc", "cout", "_eff")
+
+    def __init__(self, data, inv, kc, cout):
+        self.data, self.inv, self.kc, self.cout, self._eff = data, inv, kc, cout, None
+
+    def eff_scale(self, scale):
+        """Epilogue scale vector: folded-BN scale (or 1) times the exact power-of-two un-scaling of this weight."""
+        key = None if scale is None else (scale.data_ptr(), scale._version)
+        if self._eff is None or self._eff[0] != key:
+            eff = self.inv if scale is None else scale.float() * self.inv
+            self._eff = (key, eff.contiguous())
+        return self._eff[1]
 
 
 def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2)):
-    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> [2 (hi,lo)][3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc] fp32,
-    hi/lo = tf32_split(weight)."""
+    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> TcWeight (see there).  Per output channel the weights are scaled by the
+    power of two that puts max |w| into [2^14, 2^15) (exact; undone by TcWeight.inv), then split with f16_split."""
     w = weight.detach().float()
     cout, cin = w.shape[:2]
     kc = TC_KC if kc is None else kc
     assert kc in (16, 32) and cin % kc == 0 and tuple(w.shape[2:]) == (3, 3, 3)
-    hi, lo = tf32_split(w)
+    amax = w.abs().amax(dim=(1, 2, 3, 4))
+    _, ex = torch.frexp(amax)                                           # amax = m * 2^ex, m in [0.5, 1)
+    e = torch.where(amax > 0, TC_WEIGHT_TOP_LOG2 - ex, torch.zeros_like(ex)).clamp(-40, 40)
+    ws = torch.ldexp(w, e.view(-1, 1, 1, 1, 1))
+    hi, lo = f16_split(ws)
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
     both = both[..., list(kw_order)]                                   # stride-2 kernel wants kw slices as (1, 0, 2)
-    both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (2, co, chunk, ci, kd, kh, kw)
-    both = both.permute(0, 4, 2, 5, 6, 1, 3)                           # (2, kd, chunk, kh, kw, co, ci)
-    return both.reshape(2, 3, cin // kc, 3, 3 * cout, kc).contiguous()
+    both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (half, co, chunk, ci, kd, kh, kw)
+    both = both.permute(4, 2, 5, 6, 1, 0, 3)                           # (kd, chunk, kh, kw, co, half, ci)
+    data = both.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
+    inv = torch.ldexp(torch.ones_like(amax), -(e + TC_ACT_SCALE_LOG2))
+    return TcWeight(data, inv.contiguous(), kc, cout)
+
+
+def _tc_args(w_split, cin, kc, scale):
+    assert isinstance(w_split, TcWeight) and w_split.kc == kc
+    assert tuple(w_split.data.shape) == (3, cin // kc, 3, 3 * w_split.cout, 2 * kc) and w_split.data.dtype == torch.float16
+    assert w_split.data.is_contiguous() and w_split.data.is_cuda
+    return w_split.data.data_ptr(), w_split.eff_scale(scale)
 
 
 def to_ndhwc(x):
@@ -366,15 +397,16 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
     """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
-    cout = w_split.shape[4] // 3
+    cout = w_split.cout
     kc = conv3d_tc_kc(cin, cout, w)
-    assert kc and w_split.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and w_split.is_contiguous()
+    assert kc
+    wptr, scale = _tc_args(w_split, cin, kc, scale)
     shape = (b, d, h, w, cout) if out_ndhwc else (b, cout, d, h, w)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:
         want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
-    _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+    _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
@@ -388,15 +420,15 @@ def conv3d_k3_s2_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act
     w_split = pack_tc_weight(weight, 16, kw_order=(1, 0, 2))."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
-    cout = w_split.shape[4] // 3
-    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    cout = w_split.cout
+    wptr, scale = _tc_args(w_split, cin, 16, scale)
     do, ho, wo = d // 2, h // 2, w // 2
     shape = (b, do, ho, wo, cout) if out_ndhwc else (b, cout, do, ho, wo)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:
         want = (b, do, ho, wo, cout) if res_ndhwc else (b, cout, do, ho, wo)
         assert tuple(residual.shape) == want and residual.is_contiguous()
-    _call("osb_conv3d_k3_s2_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+    _call("osb_conv3d_k3_s2_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
@@ -406,7 +438,7 @@ def deconv3d_tc_supported(cin, cout, w):
 
 
 def pack_tc_deconv_weight(weight):
-    """(Cin, Cout, 3, 3, 3) ConvTranspose3d parameter -> hi/lo split, 16-channel chunks, kw slices ordered (1, 2, 0):
+    """(Cin, Cout, 3, 3, 3) ConvTranspose3d parameter -> TcWeight, 16-channel chunks, kw slices ordered (1, 2, 0):
     even output columns come from tap 1, odd ones from taps 2 (same input column) and 0 (next input column)."""
     return pack_tc_weight(weight.detach().float().permute(1, 0, 2, 3, 4).contiguous(), 16, kw_order=(1, 2, 0))
 
@@ -415,14 +447,14 @@ def deconv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=
     """ConvTranspose3d(k3, s2, p1, op1) + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
-    cout = w_split.shape[4] // 3
-    assert w_split.shape == (2, 3, cin // 16, 3, 3 * cout, 16) and w_split.is_contiguous()
+    cout = w_split.cout
+    wptr, scale = _tc_args(w_split, cin, 16, scale)
     shape = (b, 2 * d, 2 * h, 2 * w, cout) if out_ndhwc else (b, cout, 2 * d, 2 * h, 2 * w)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:
         want = (b, 2 * d, 2 * h, 2 * w, cout) if res_ndhwc else (b, cout, 2 * d, 2 * h, 2 * w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
-    _call("osb_deconv3d_k3_tc_fwd", x_ndhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+    _call("osb_deconv3d_k3_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 
@@ -511,12 +543,13 @@ def conv2d_k3_tc(x_nhwc, w_split, scale=None, shift=None, residual=None, act=ACT
     w_split = pack_tc_weight of the 3x3x3 weight that holds the 2D taps at kd = 1."""
     assert x_nhwc.is_cuda and x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and x_nhwc.dim() == 4
     b, h, w, cin = x_nhwc.shape
-    cout = w_split.shape[4] // 3
+    cout = w_split.cout
     kc = conv2d_tc_kc(cin, cout, w, dilation)
-    assert kc and w_split.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and w_split.is_contiguous()
+    assert kc
+    wptr, scale = _tc_args(w_split, cin, kc, scale)
     y = torch.empty((b, h, w, cout) if out_nhwc else (b, cout, h, w), dtype=torch.float32, device=x_nhwc.device)
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == y.numel()
-    _call("osb_conv2d_k3_tc_fwd", x_nhwc.data_ptr(), w_split.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, cin,
+    _call("osb_conv2d_k3_tc_fwd", x_nhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, cin,
           cout, h, w, dilation, act, int(out_nhwc), int(res_nhwc), _stream(y))
     return y

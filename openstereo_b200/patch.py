@@ -69,7 +69,8 @@ def _patch_backbone(bb, net, extract, split):
 
     def forward(self, inputs):
         left, right = inputs["left"], inputs["right"]
-        if not (_accelerable(self, left, right) and left.dtype == torch.float32 and left.shape == right.shape):
+        trainable = torch.is_grad_enabled() and any(q.requires_grad for q in net.parameters())   # the folded twin would cut them off
+        if trainable or not (_accelerable(self, left, right) and left.dtype == torch.float32 and left.shape == right.shape):
             return orig(inputs)
         both = extract(rt.get(), torch.cat((left, right), 0))
         return split(both, left.shape[0])

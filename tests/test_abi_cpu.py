@@ -39,7 +39,7 @@ def test_binding_signatures_match_header(native):
     """Arity and C types of every ctypes binding are checked against the prototypes in the header."""
     text = open(os.path.join(ROOT, "include", "openstereo_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    kinds = {"const float*": ctypes.c_void_p, "float*": ctypes.c_void_p, "int": ctypes.c_int, "float": ctypes.c_float,
+    kinds = {"const float*": ctypes.c_void_p, "float*": ctypes.c_void_p, "const void*": ctypes.c_void_p, "int": ctypes.c_int, "float": ctypes.c_float,
              "osb_stream_t": ctypes.c_void_p, "long long": ctypes.c_longlong}
     for name, argtypes in native.SIGNATURES.items():
         m = re.search(r"int\s+%s\s*\(([^)]*)\)" % name, text)

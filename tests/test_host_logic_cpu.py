@@ -1,4 +1,4 @@
-"""CPU: host-side logic of the product that needs no GPU -- operand packing for the tensor-core kernels (the 3xTF32 split must
+"""CPU: host-side logic of the product that needs no GPU -- operand packing for the tensor-core kernels (the 3xFP16 split must
 be exact), BN folding, the BN-folded backbone twins, state_dict compatibility of the host mirrors, and the gates that keep
 CPU tensors away from the CUDA-only paths."""
 import pytest
@@ -15,42 +15,47 @@ def rnd(seed, *shape, scale=1.0):
 
 @pytest.mark.parametrize("kc,order", [(32, (0, 1, 2)), (16, (0, 1, 2)), (16, (1, 0, 2)), (16, (1, 2, 0))])
 def test_pack_tc_weight_split(kc, order):
-    """hi and lo are both exact TF32 values (the MMA's own truncation is then a no-op), hi is the nearest TF32 to w, and
-    hi + lo reproduces w to 2^-23 relative with no sign preference (round 1 truncated: every product shrank towards zero)."""
+    """3xFP16 weight packing: per output channel a power-of-two scale puts max |w| into [2^14, 2^15) (no fp16 overflow, exact to
+    undo), hi = nearest fp16, lo = nearest fp16 of the remainder; hi + lo reproduces the scaled weight to 2^-22 relative (2^-25
+    absolute once lo is subnormal) with no sign preference, and `inv` is the exact inverse scale times 2^-4 (activation scale)."""
     cout, cin = 8, 64
-    w = rnd(1, cout, cin, 3, 3, 3) * torch.logspace(-3, 3, cin).view(1, cin, 1, 1, 1)      # wide dynamic range
+    w = rnd(1, cout, cin, 3, 3, 3) * torch.logspace(-2, 2, cin).view(1, cin, 1, 1, 1)      # wide dynamic range
+    w = w * torch.logspace(-6, 6, cout).view(cout, 1, 1, 1, 1)                               # and very different channel magnitudes
     p = ops.pack_tc_weight(w, kc, kw_order=order)
-    assert p.shape == (2, 3, cin // kc, 3, 3 * cout, kc) and p.is_contiguous()
-    hi, lo = p[0], p[1]
-    assert ((hi.view(torch.int32) & 0x1FFF) == 0).all() and ((lo.view(torch.int32) & 0x1FFF) == 0).all()
-    # un-permute: [kd][chunk][kh][kw*cout + co][ci] -> (co, ci, kd, kh, kw) in the requested kw order
-    unperm = lambda t: t.double().view(3, cin // kc, 3, 3, cout, kc).permute(4, 1, 5, 0, 2, 3).reshape(cout, cin, 3, 3, 3)
-    want = w[..., list(order)].double()
-    resid = unperm(hi) + unperm(lo) - want
-    assert (resid.abs() <= want.abs() * 2.0 ** -23).all()
+    assert isinstance(p, ops.TcWeight) and p.kc == kc and p.cout == cout
+    assert p.data.shape == (3, cin // kc, 3, 3 * cout, 2 * kc) and p.data.is_contiguous() and p.data.dtype == torch.float16
+    assert torch.isfinite(p.data.float()).all()
+    # un-permute: [kd][chunk][kh][kw*cout + co][half*kc + ci] -> (half, co, ci, kd, kh, kw) in the requested kw order
+    t = p.data.double().view(3, cin // kc, 3, 3, cout, 2, kc).permute(5, 4, 1, 6, 0, 2, 3).reshape(2, cout, cin, 3, 3, 3)
+    hi, lo = t[0], t[1]
+    scale = 2.0 ** -ops.TC_ACT_SCALE_LOG2 / p.inv.double()                                  # 2^e_c
+    assert torch.equal(torch.log2(scale), torch.log2(scale).round())                          # exact powers of two
+    want = w[..., list(order)].double() * scale.view(-1, 1, 1, 1, 1)
+    top = want.abs().amax(dim=(1, 2, 3, 4))
+    assert (top >= 2.0 ** 14).all() and (top < 2.0 ** 15).all()
+    resid = hi + lo - want
+    assert (resid.abs() <= torch.maximum(want.abs() * 2.0 ** -22, torch.tensor(2.0 ** -25, dtype=torch.float64))).all()
     assert abs((resid * want.sign()).sum().item()) <= 0.05 * resid.abs().sum().item()     # zero-mean, not a shrink
-    assert ((unperm(hi) - want).abs() <= want.abs() * 2.0 ** -11).all()                    # round to nearest (truncation: 2^-10)
-    assert (lo.abs() <= hi.abs() * 2.0 ** -11 * (1 + 2.0 ** -10)).all()
+    assert ((hi - want).abs() <= want.abs() * 2.0 ** -11).all()                            # round to nearest
+    # eff_scale folds the BN scale and is cached per scale tensor
+    bn = torch.rand(cout) + 0.5
+    assert torch.equal(p.eff_scale(bn), bn * p.inv) and p.eff_scale(bn) is p.eff_scale(bn)
+    assert torch.equal(p.eff_scale(None), p.inv)
 
 
-def test_tf32_split_legacy_truncation_mode():
-    """Policy 0 (round 1, kept for tools/parity_bisect.py): hi = truncation, lo = exact remainder, always the sign of w."""
-    w = rnd(9, 4096)
-    old = ops._TF32_SPLIT
-    ops._TF32_SPLIT = 0
-    try:
-        hi, lo = ops.tf32_split(w)
-    finally:
-        ops._TF32_SPLIT = old
-    assert torch.equal((hi.double() + lo.double()).float(), w) and ((hi.view(torch.int32) & 0x1FFF) == 0).all()
-    assert (lo * w >= 0).all()
+def test_f16_split_small_and_zero_channels():
+    hi, lo = ops.f16_split(torch.tensor([0.0, 1e-6, 1.0, 1000.123, -32767.9]))
+    assert torch.isfinite(hi.float()).all() and hi[0] == 0 and lo[0] == 0
+    p = ops.pack_tc_weight(torch.zeros(4, 32, 3, 3, 3), 32)                                 # an all-zero channel must not produce inf/nan
+    assert torch.isfinite(p.inv).all() and (p.data == 0).all()
 
 
 def test_pack_deconv_and_head_weights():
     w = rnd(2, 32, 16, 3, 3, 3)                                              # ConvTranspose3d layout (Cin, Cout, ...)
     p = ops.pack_tc_deconv_weight(w)
-    assert p.shape == (2, 3, 2, 3, 3 * 16, 16)
-    assert torch.equal(p, ops.pack_tc_weight(w.permute(1, 0, 2, 3, 4).contiguous(), 16, kw_order=(1, 2, 0)))
+    assert p.data.shape == (3, 2, 3, 3 * 16, 2 * 16)
+    q = ops.pack_tc_weight(w.permute(1, 0, 2, 3, 4).contiguous(), 16, kw_order=(1, 2, 0))
+    assert torch.equal(p.data, q.data) and torch.equal(p.inv, q.inv)
     head = rnd(3, 1, 32, 3, 3, 3)
     taps = ops.pack_c1_weight(head)
     assert taps.shape == (27, 32) and torch.equal(taps[(1 * 3 + 2) * 3 + 0], head[0, :, 1, 2, 0])

@@ -89,8 +89,7 @@ def layer_report():
         elif kind == "dc":
             got = ops.deconv3d(x, ops.pack_deconv_weight(wt))
             print("%-22s %-16s %+12.3e %12.3e %+12.3e" % ((name, "cuda-core") + stats(got, want) + (gain(got, want),)))
-        for mode, kappa in ((0, 0.0), (1, 0.0), (1, KAPPA)):
-            ops.set_tf32_split(mode)
+        for mode, kappa in ((1, 0.0), (1, KAPPA)):
             ops.set_rz_kappa(kappa)
             if kind == "s1":
                 got = ops.conv3d_k3_tc(ops.to_ndhwc(x), ops.pack_tc_weight(wt, ops.conv3d_tc_kc(cin, cout, w)), out_ndhwc=False)
@@ -106,7 +105,6 @@ def layer_report():
                                        dilation=dil, out_nhwc=False)
             print("%-22s %-16s %+12.3e %12.3e %+12.3e" % ((name, "tc s%d k=%.1e" % (mode, kappa)) + stats(got, want) + (gain(got, want),)))
     ops.set_rz_kappa(KAPPA)
-    ops.set_tf32_split(1)
 
 
 def build_mine(sd, cfg):
@@ -175,7 +173,6 @@ def model_report(batch):
         line("oracle CPU fp32 (MKLDNN)", cpu_disp, cpu_logits)
         line("oracle GPU cuDNN fp32 (TF32 off)", disp32, logits32, lf32["gwc_feature"])
         for mode, kappa in SWEEP:
-            ops.set_tf32_split(mode)
             ops.set_rz_kappa(kappa)
             for tc_agg, tc_bb in ((True, True), (True, False), (False, True), (False, False)):
                 if not (tc_agg or tc_bb) and (mode, kappa) != SWEEP[0]:
@@ -207,7 +204,6 @@ def model_report(batch):
             logits = eng.logits(vol)
             line("mine s%d k=%.1e hot path on oracle-cuDNN features" % (mode, kappa), ops.upsample_softargmin(logits, 192, 256, 512), logits)
             print("   volume vs oracle cuDNN volume: max abs %.3e" % (vol - vol32).abs().max().item())
-        ops.set_tf32_split(1)
         ops.set_rz_kappa(KAPPA)
         # the oracle's aggregation (cuDNN fp32) on MY features: is the backbone alone enough to move the EPE?
         m = build_mine(sd, cfg)
@@ -224,7 +220,7 @@ if __name__ == "__main__":
     ap.add_argument("--b", type=int, default=1)
     ap.add_argument("--kappas", default="", help="comma-separated kappa values to sweep at model level (split 1)")
     a = ap.parse_args()
-    SWEEP = [(1, float(k)) for k in a.kappas.split(",") if k] or [(1, KAPPA), (1, 0.0), (0, 0.0)]
+    SWEEP = [(1, float(k)) for k in a.kappas.split(",") if k] or [(1, KAPPA), (1, 0.0)]
     with torch.no_grad():
         if a.layers:
             layer_report()
