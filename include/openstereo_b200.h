@@ -37,6 +37,7 @@ extern "C" {
 #define OSB_ACT_NONE 0
 #define OSB_ACT_RELU 1
 #define OSB_ACT_LEAKY 2 /* LeakyReLU(0.01), nn.LeakyReLU default used by StereoBase */
+#define OSB_ACT_RELU6 3 /* nn.ReLU6 of LightStereo's MobileV2Residual; accepted by the CUDA-core 1x1, depthwise and 2D kernels */
 
 typedef void* osb_stream_t;
 
@@ -188,6 +189,33 @@ int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation);
 int osb_conv2d_k3_tc_fwd(const float* x_nhwc, const void* w_split, const float* scale, const float* shift, const float* residual,
                          float* y, int B, int Cin, int Cout, int H, int W, int dilation, int act, int out_nhwc, int res_nhwc,
                          osb_stream_t stream);
+/* ---- remaining volume / regression flavours of the model zoo -------------------------------------
+ * osb_gwc_volume_sum_fwd: osb_gwc_volume_fwd with a plain SUM over the K channels of a group instead of the mean:
+ *   - CoExCostVolume(maxdisp, group)(x, y) (cost_volume/cost_volume.py:9-29) = sum flavour with D = maxdisp + 1, G = group;
+ *   - FoundationStereo's L2-normalised volume (foundationstereo/core/submodule.py:422-461) = sum flavour on features that
+ *     osb_group_l2_normalize_fwd normalised per group first (y = x / max(||x_group||_2, eps), aten F.normalize, eps 1e-12).
+ * osb_sub_volume_fwd: build_sub_volume (cost_volume.py:108-117): out[b,d,h,w] = sum_c |L[..,w] - R[..,w-d]| (R = 0 for w < d).
+ * osb_regression_values_fwd: sum_d prob[b,d,h,w] * values[b,d,h,w] -> (B,H,W) (casnet/submodule.py:22-24). */
+int osb_gwc_volume_sum_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W, int D, int G,
+                           osb_stream_t stream);
+int osb_group_l2_normalize_fwd(const float* x, float* y, int B, int C, int H, int W, int G, float eps, osb_stream_t stream);
+int osb_sub_volume_fwd(const float* left, const float* right, float* out, int B, int C, int H, int W, int D, osb_stream_t stream);
+int osb_regression_values_fwd(const float* prob, const float* values, float* out, int B, int D, int H, int W, osb_stream_t stream);
+
+/* ---- LightStereo 2D cost aggregation (lightstereo/aggregation.py:7-134) ------------------------------
+ * Depthwise Conv2d (groups = C), kernel KH x KW (odd, <= 21), padding (KH/2, KW/2), stride 1 or 2, NCHW fp32:
+ *   y[b,c,oh,ow] = act(scale[c] * sum_{i,j} w[c,i,j] * x[b,c,oh*s+i-KH/2,ow*s+j-KW/2] + shift[c] + residual[b,c,oh,ow])
+ * the 3x3 dwconv of MobileV2Residual (:80-84, folded BN + ReLU6) and the strip convolutions of AttentionModule
+ * (:109-117: 1x7/7x1, 1x11/11x1, 1x21/21x1 with bias = shift; the branch sum `attn + attn_0 + ...` rides on `residual`).
+ * w: (C, KH, KW) contiguous; scale/shift/residual optional; y may alias residual. */
+int osb_dwconv2d_fwd(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* y, int B,
+                     int C, int H, int W, int KH, int KW, int stride, int act, osb_stream_t stream);
+/* ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1, bias=False) + folded BN + residual + activation
+ * (lightstereo/aggregation.py:28-34,58-59: conv5 / conv6 with `F.relu(conv5(conv4) + redir2(conv2))`): x (B,Cin,H,W) ->
+ * y (B,Cout,2H,2W); w_packed (Cin, 9, Cout) = ops.pack_deconv2d_weight of the (Cin,Cout,3,3) parameter. */
+int osb_deconv2d_k3s2_fwd(const float* x, const float* w_packed, const float* scale, const float* shift, const float* residual,
+                          float* y, int B, int Cin, int Cout, int H, int W, int act, osb_stream_t stream);
+
 /* ---- GRU-iteration lookups of IGEV / StereoBase ------------------------------------
  * Pair-average along the middle axis of a (outer, n, inner) array -> (outer, n/2, inner): the F.avg_pool2d(.., [1,2],
  * stride=[1,2]) pyramid of Combined_Geo_Encoding_Volume.__init__ (igev/geometry.py:24-30, stereobase/gru_blocks.py:187-193)

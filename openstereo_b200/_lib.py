@@ -41,6 +41,12 @@ SIGNATURES = {
     "osb_conv2d_tc_kc": [_i] * 4,
     "osb_conv2d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_ncdhw_to_ndhwc": [_f32p, _f32p, _i, _i, _i, _i, _i, _s],
+    "osb_gwc_volume_sum_fwd": [_f32p, _f32p, _f32p, _i, _i, _i, _i, _i, _i, _s],
+    "osb_group_l2_normalize_fwd": [_f32p, _f32p, _i, _i, _i, _i, _i, _f, _s],
+    "osb_sub_volume_fwd": [_f32p, _f32p, _f32p, _i, _i, _i, _i, _i, _s],
+    "osb_regression_values_fwd": [_f32p, _f32p, _f32p, _i, _i, _i, _i, _s],
+    "osb_dwconv2d_fwd": [_f32p] * 6 + [_i] * 8 + [_s],
+    "osb_deconv2d_k3s2_fwd": [_f32p] * 6 + [_i] * 6 + [_s],
 }
 
 

@@ -11,11 +11,12 @@ Graphs restated (file:line of the reference forward each engine replaces):
   GwcAggregation        gwcnet/gwcnet_disp_processor.py:83-91,128-140 + gwcnet/hourglass.py:46-56
   PSMAggregation        psmnet/psmnet_cost_processor.py:181-221,108-132 + psmnet_disp_processor.py:107-118
   StereoBaseAggregation stereobase/hourglass.py:79-104 + stereobase_gru.py:161-164
+  LightStereoAggregation lightstereo/aggregation.py:42-60 (Aggregation.forward), :94-101 (MobileV2Residual), :119-134 (AttentionModule)
 """
 import torch
 
 from . import ops
-from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU6
 
 
 class _Packed:
@@ -65,7 +66,7 @@ def _tc_weight(layer, width):
     if not kc:
         return None
     if kc not in layer._tc:
-        layer._tc[kc] = ops.pack_tc_weight(layer._w5, kc)
+        layer._tc[kc] = ops.pack_tc_weight(layer._w5, kc, pad_cout_to=16 if layer.cout < 16 else None)
     return layer._tc[kc]
 
 
@@ -205,6 +206,8 @@ class GwcAggregation(_Engine):
             for hg in self.hg:
                 out = _gwc_hourglass_channels_last(hg, out)
             cls = self.classif3[1]
+            if _tc_ok(cls, width):                                         # 32 -> 1 head on the narrow (Cout <= 16) tensor-core variant
+                return _conv_tc(cls, _conv_tc(self.classif3[0], out, ACT_RELU), ACT_NONE, out_ndhwc=False, res_ndhwc=False)
             if cls.cin == 32 and cls.cout == 1 and cls._w5 is not None and cls.stride == 1:
                 if "c1" not in cls._tc:
                     cls._tc["c1"] = ops.pack_c1_weight(cls._w5)
@@ -272,14 +275,17 @@ class PSMAggregation(_Engine):
         out2, pre2, post2 = self.hg[1](out1, pre1, post1, cost0)
         out3, pre3, post3 = self.hg[2](out2, pre2, post2, cost0)
 
-        def head(i, x):
-            if _tc_ok(self.heads[i][0], width):
-                return _conv_tc(self.heads[i][0], ops.to_ndhwc(x), ACT_RELU, out_ndhwc=False)
-            return _conv(self.heads[i][0], x, ACT_RELU)
+        def head(i, x, prev):
+            a, b = self.heads[i]
+            if _tc_ok(a, width) and _tc_ok(b, width):                   # both convs on tensor cores, channels-last in between
+                return _conv_tc(b, _conv_tc(a, ops.to_ndhwc(x), ACT_RELU), ACT_NONE, residual=prev, out_ndhwc=False, res_ndhwc=False)
+            if _tc_ok(a, width):
+                return _conv(b, _conv_tc(a, ops.to_ndhwc(x), ACT_RELU, out_ndhwc=False), residual=prev)
+            return _conv(b, _conv(a, x, ACT_RELU), residual=prev)
 
-        cost1 = _conv(self.heads[0][1], head(0, out1))
-        cost2 = _conv(self.heads[1][1], head(1, out2), residual=cost1)
-        cost3 = _conv(self.heads[2][1], head(2, out3), residual=cost2)
+        cost1 = head(0, out1, None)
+        cost2 = head(1, out2, cost1)
+        cost3 = head(2, out3, cost2)
         return [cost1, cost2, cost3]
 
     def __call__(self, raw_cost):
@@ -355,3 +361,103 @@ class StereoBaseCostHead(_Engine):
         self._ensure(geo.device)
         logits = _conv(self.layer, geo)                         # (B,1,D',H',W')
         return ops.softargmin(logits.squeeze(1), maxdisp_lowres, keepdim=True)
+
+
+# -------------------------------------------------------------------------------------------------- LightStereo
+class _PW:
+    """1x1 Conv2d (+BN or bias) packed for osb_conv3d_1x1_bn_act_fwd: weight (Cin, Cout)."""
+    __slots__ = ("w", "scale", "shift")
+
+    def __init__(self, conv, bn=None):
+        self.w = conv.weight.detach().float().reshape(conv.out_channels, conv.in_channels).t().contiguous()
+        self.scale, self.shift = ops.fold_bn(bn) if bn is not None else (None, None)
+        if conv.bias is not None:
+            bias = conv.bias.detach().float()
+            self.shift = bias.contiguous() if self.shift is None else (self.shift + bias * self.scale).contiguous()
+
+
+class _DW:
+    """Depthwise Conv2d (+BN or bias)."""
+    __slots__ = ("w", "scale", "shift", "stride")
+
+    def __init__(self, conv, bn=None):
+        assert conv.groups == conv.in_channels == conv.out_channels and conv.dilation == (1, 1)
+        assert conv.padding == (conv.kernel_size[0] // 2, conv.kernel_size[1] // 2) and conv.stride[0] == conv.stride[1]
+        self.w = conv.weight.detach().float().reshape(conv.out_channels, *conv.kernel_size).contiguous()
+        self.stride = int(conv.stride[0])
+        self.scale, self.shift = ops.fold_bn(bn) if bn is not None else (None, None)
+        if conv.bias is not None:
+            bias = conv.bias.detach().float()
+            self.shift = bias.contiguous() if self.shift is None else (self.shift + bias * self.scale).contiguous()
+
+
+class _InvertedResidual:
+    """MobileV2Residual (lightstereo/aggregation.py:63-101): pw+BN+ReLU6 -> dw3x3+BN+ReLU6 -> pw+BN (+ identity)."""
+
+    def __init__(self, m):
+        self.pw = _PW(m.pwconv[0], m.pwconv[1])
+        self.dw = _DW(m.dwconv[0], m.dwconv[1])
+        self.pl = _PW(m.pwliner[0], m.pwliner[1])
+        self.res = bool(m.use_res_connect)
+
+    def __call__(self, x):
+        h = ops.conv3d_1x1(x, self.pw.w, self.pw.scale, self.pw.shift, act=ACT_RELU6)
+        h = ops.dwconv2d(h, self.dw.w, self.dw.scale, self.dw.shift, stride=self.dw.stride, act=ACT_RELU6)
+        return ops.conv3d_1x1(h, self.pl.w, self.pl.scale, self.pl.shift, residual=x if self.res else None)
+
+
+class _StripAttention:
+    """AttentionModule (lightstereo/aggregation.py:104-134): cost * conv3(a + sum_k conv_k_2(conv_k_1(a))), a = conv0(feat)."""
+
+    def __init__(self, m):
+        self.conv0, self.conv3 = _PW(m.conv0), _PW(m.conv3)
+        self.pairs = [(_DW(getattr(m, "conv%d_1" % i)), _DW(getattr(m, "conv%d_2" % i))) for i in range(3)]
+
+    def __call__(self, cost, feat):
+        a = ops.conv3d_1x1(feat, self.conv0.w, None, self.conv0.shift)
+        acc = a
+        for first, second in self.pairs:                        # acc = a + b0 + b1 + b2, accumulated by the second strip conv
+            t = ops.dwconv2d(a, first.w, None, first.shift)
+            acc = ops.dwconv2d(t, second.w, None, second.shift, residual=acc)
+        return ops.conv3d_1x1(acc, self.conv3.w, None, self.conv3.shift, gate=cost)
+
+
+class LightStereoAggregation(_Engine):
+    """Aggregation.forward (lightstereo/aggregation.py:42-60): correlation volume (B, D/4, H/4, W/4) + left features at 1/4, 1/8,
+    1/16 -> [(B, D/4, H/4, W/4)].  53 launches for LightStereo-S; no elementwise pass of its own (BN, ReLU6, shortcuts, the
+    attention product and the final ReLUs all ride on the producing kernels)."""
+
+    def _pack(self):
+        m = self.module
+        seq = lambda s: [_InvertedResidual(b) for b in s]
+        self.conv0, self.conv2, self.conv4 = seq(m.conv0), seq(m.conv2), seq(m.conv4)
+        self.conv1, self.conv3 = _InvertedResidual(m.conv1), _InvertedResidual(m.conv3)
+        self.redir1, self.redir2 = _InvertedResidual(m.redir1), _InvertedResidual(m.redir2)
+        self.up = []
+        for blk in (m.conv5, m.conv6):
+            sc, sh = ops.fold_bn(blk[1])
+            self.up.append((ops.pack_deconv2d_weight(blk[0].weight), sc, sh))
+        self.att = [_StripAttention(a) for a in (m.att0, m.att2, m.att4)] if m.left_att else None
+
+    def __call__(self, x, features_left):
+        x = self._check(x)
+        self._ensure(x.device)
+        feats = [self._check(f) for f in features_left]
+        for blk in self.conv0:
+            x = blk(x)
+        if self.att:
+            x = self.att[0](x, feats[0])
+        half = self.conv1(x)
+        for blk in self.conv2:
+            half = blk(half)
+        if self.att:
+            half = self.att[1](half, feats[1])
+        quarter = self.conv3(half)
+        for blk in self.conv4:
+            quarter = blk(quarter)
+        if self.att:
+            quarter = self.att[2](quarter, feats[2])
+        w5, s5, b5 = self.up[0]
+        up = ops.deconv2d_k3s2(quarter, w5, s5, b5, residual=self.redir2(half), act=ACT_RELU)
+        w6, s6, b6 = self.up[1]
+        return [ops.deconv2d_k3s2(up, w6, s6, b6, residual=self.redir1(x), act=ACT_RELU)]

@@ -40,6 +40,7 @@ struct ConvParams {
 __device__ __forceinline__ float activate(float v, int act) {
   if (act == OSB_ACT_RELU) return fmaxf(v, 0.f);
   if (act == OSB_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+  if (act == OSB_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
   return v;
 }
 
@@ -623,7 +624,7 @@ int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const 
   OSB_REQUIRE(x0 && w_packed && y, "conv3d_1x1: null pointer");
   OSB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "conv3d_1x1: empty shape");
   OSB_REQUIRE(Cin0 > 0 && Cin0 <= Cin && (Cin0 == Cin || x1 != nullptr), "conv3d_1x1: bad channel split %d of %d", Cin0, Cin);
-  OSB_REQUIRE(act >= 0 && act <= 2, "conv3d_1x1: unknown activation %d", act);
+  OSB_REQUIRE(act >= 0 && act <= 3, "conv3d_1x1: unknown activation %d", act);
   ConvParams p{};
   p.x = x0, p.x1 = x1, p.w = w_packed, p.scale = scale, p.shift = shift, p.residual = residual, p.gate = gate, p.y = y;
   p.B = B, p.Cin = Cin, p.Cin0 = Cin0, p.Cout = Cout, p.D = D, p.H = H, p.W = W;

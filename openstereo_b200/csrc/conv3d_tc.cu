@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const int h = h0 + t;
         const size_t vox = (((size_t)b * p.D + d) * p.H + h) * TC_W + m;           // NDHWC voxel index
         const size_t plane = (size_t)p.D * p.H * TC_W;                             // NCDHW channel stride
-        const size_t ncdhw0 = (size_t)b * COUT * plane + ((size_t)d * p.H + h) * TC_W + m;
+        const size_t ncdhw0 = (size_t)b * p.Cout * plane + ((size_t)d * p.H + h) * TC_W + m;   // p.Cout <= COUT real channels
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * N3;
         // all 3*COUT accumulator columns of this voxel in one go: loads back to back, a single wait
         uint32_t raw[3][COUT];
@@ -313,11 +313,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           right = (lane == 31) ? xr[i] : right;       // m+1 lives in the next quadrant
           out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
         }
-        if (p.out_ndhwc && (!p.residual || p.res_ndhwc)) {       // coalesced channels-last path (BN/residual/act inside)
-          static_assert(COUT == 32, "one 32-channel chunk per voxel");
-          store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT,
-                              p.residual ? p.residual + (vox - lane) * COUT : nullptr, COUT, s_scale, s_shift, p.act);
-          continue;
+        if constexpr (COUT == 32) {
+          if (p.out_ndhwc && (!p.residual || p.res_ndhwc)) {     // coalesced channels-last path (BN/residual/act inside)
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT,
+                                p.residual ? p.residual + (vox - lane) * COUT : nullptr, COUT, s_scale, s_shift, p.act);
+            continue;
+          }
         }
 #pragma unroll
         for (int i = 0; i < COUT; ++i) out[i] = fmaf(out[i], s_scale[i], s_shift[i]);
@@ -331,7 +332,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < COUT; ++i) out[i] += __ldg(p.residual + ncdhw0 + (size_t)i * plane);
+            for (int i = 0; i < COUT; ++i)
+              if (i < p.Cout) out[i] += __ldg(p.residual + ncdhw0 + (size_t)i * plane);
           }
         }
         if (p.act == OSB_ACT_RELU) {
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           for (int i = 0; i < COUT / 4; ++i) yp[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < COUT; ++i) p.y[ncdhw0 + (size_t)i * plane] = out[i];   // 128-byte rows per warp
+          for (int i = 0; i < COUT; ++i)
+            if (i < p.Cout) p.y[ncdhw0 + (size_t)i * plane] = out[i];                 // 128-byte rows per warp
         }
       }
       // tiles this (short) block never used still take part in the hand-shake so barrier phases stay in step
@@ -449,7 +452,8 @@ extern "C" {
 // K-chunk (input channels per operand tile) of the kernel variant that serves a shape; 0 = no tensor-core variant.
 int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (stride != 1) return 0;
-  if (W == osb::TC_W && Cout == 32 && Cin % 32 == 0 && Cin >= 32) return 32;                 // conv3d_tc.cu
+  if (W == osb::TC_W && (Cout == 32 || (Cout >= 1 && Cout <= 16)) && Cin % 32 == 0 && Cin >= 32) return 32;   // conv3d_tc.cu (narrow
+                                                                                               // heads: weights zero-padded to 16 rows)
   if (Cin % 16 == 0 && Cin >= 16 &&
       ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 128)) || (W == osb::TC_W && (Cout == 64 || Cout == 128))))
     return 16;                                                                                  // conv3d_tcg.cu
@@ -493,6 +497,10 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float*
   const long long items = (long long)B * D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");
   p.items = (int)items;
+  if (Cout <= 16) {                                  // classifier heads (32 -> 1): COUT = 16 instantiation, NCDHW output only
+    OSB_REQUIRE(!out_ndhwc && (!residual || !res_ndhwc), "conv3d_k3_tc: Cout <= 16 writes (and adds) NCDHW tensors only");
+    return launch_tc<16>(p, (cudaStream_t)stream);
+  }
   return launch_tc<32>(p, (cudaStream_t)stream);
 }
 

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) volume_kernel(const __grid_constant__ 
 }
 
 static int launch_volume(const float* ref_g, const float* tgt_g, const float* ref_c, const float* tgt_c, float* out,
-                         int B, int Cg, int Cc, int H, int W, int D, int G, int mask_left, cudaStream_t stream) {
+                         int B, int Cg, int Cc, int H, int W, int D, int G, int mask_left, cudaStream_t stream, int reduce_sum = 0) {
   OSB_REQUIRE(B > 0 && H > 0 && W > 0 && D > 0, "volume: empty shape B=%d H=%d W=%d D=%d", B, H, W, D);
   OSB_REQUIRE(Cg >= 0 && Cc >= 0 && (Cg > 0 || Cc > 0), "volume: no channels");
   int K = 0;
@@ -287,7 +287,7 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   p.w_tiles = (W + kTileW - 1) / kTileW;
   p.d_chunks = (D + kChunkD - 1) / kChunkD;
   p.mask_left = mask_left;
-  p.inv_k = K > 0 ? 1.0f / (float)K : 0.f;
+  p.inv_k = K > 0 ? (reduce_sum ? 1.0f : 1.0f / (float)K) : 0.f;   // reduce_sum: plain sum over the group's channels (CoEx, L2-normalised gwc)
   auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = (W % 4 == 0) && aligned16(ref_g) && aligned16(ref_c) && aligned16(out);
   const int rows = Cg > 0 ? GU * K : GU;
@@ -341,6 +341,13 @@ int osb_gwc_volume_fwd(const float* ref, const float* tgt, float* out, int B, in
   OSB_REQUIRE(ref && tgt && out, "gwc_volume: null pointer");
   OSB_REQUIRE(C > 0, "gwc_volume: C=%d", C);
   return osb::launch_volume(ref, tgt, nullptr, nullptr, out, B, C, 0, H, W, D, G, 1, (cudaStream_t)stream);
+}
+
+int osb_gwc_volume_sum_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W, int D, int G,
+                           osb_stream_t stream) {
+  OSB_REQUIRE(ref && tgt && out, "gwc_volume_sum: null pointer");
+  OSB_REQUIRE(C > 0, "gwc_volume_sum: C=%d", C);
+  return osb::launch_volume(ref, tgt, nullptr, nullptr, out, B, C, 0, H, W, D, G, 1, (cudaStream_t)stream, 1);
 }
 
 int osb_concat_volume_fwd(const float* ref, const float* tgt, float* out, int B, int C, int H, int W, int D,

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_RELU6 = 0, 1, 2, 3
 TC_WIDTH = 128      # image width (at 1/4 resolution) handled by the tensor-core conv kernel
 TC_KC = 32          # input channels per K chunk of the tensor-core conv (128-byte K-major rows)
 
@@ -134,6 +134,53 @@ def correlation_volume(left_feature, right_feature, max_disp):
     return out.to(dt)
 
 
+def build_gwc_volume_normalized(refimg_fea, targetimg_fea, maxdisp, num_groups):
+    """FoundationStereo's L2-normalised group-wise correlation volume (foundationstereo/core/submodule.py:422-461):
+    every group's channel vector is F.normalize'd (eps 1e-12) before the dot product, which is a SUM over the group."""
+    ref, dt = _prep(refimg_fea, "refimg_fea")
+    tgt, _ = _prep(targetimg_fea, "targetimg_fea")
+    assert ref.dim() == 4 and ref.shape == tgt.shape
+    _same_device(ref, tgt)
+    b, c, h, w = ref.shape
+    assert c % num_groups == 0
+    out = torch.empty((b, num_groups, maxdisp, h, w), dtype=torch.float32, device=ref.device)
+    if out.numel():
+        rn, tn = torch.empty_like(ref), torch.empty_like(tgt)
+        _call("osb_group_l2_normalize_fwd", ref.data_ptr(), rn.data_ptr(), b, c, h, w, num_groups, 1e-12, _stream(out))
+        _call("osb_group_l2_normalize_fwd", tgt.data_ptr(), tn.data_ptr(), b, c, h, w, num_groups, 1e-12, _stream(out))
+        _call("osb_gwc_volume_sum_fwd", rn.data_ptr(), tn.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp, num_groups, _stream(out))
+    return out.to(dt)
+
+
+def coex_cost_volume(x, y, maxdisp, group=1):
+    """CoExCostVolume(maxdisp, group)(x, y), cost_volume/cost_volume.py:9-29 -> (B, group, maxdisp + 1, H, W):
+    cost[b,g,d,h,w] = sum_k x[b,gK+k,h,w] * y[b,gK+k,h,w-d], zero where w < d (the module's left zero padding)."""
+    xs, dt = _prep(x, "x")
+    ys, _ = _prep(y, "y")
+    assert xs.dim() == 4 and xs.shape == ys.shape
+    _same_device(xs, ys)
+    b, c, h, w = xs.shape
+    assert c % group == 0
+    out = torch.empty((b, group, maxdisp + 1, h, w), dtype=torch.float32, device=xs.device)
+    if out.numel():
+        _call("osb_gwc_volume_sum_fwd", xs.data_ptr(), ys.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp + 1, group, _stream(out))
+    return out.to(dt)
+
+
+def build_sub_volume(feat_l, feat_r, maxdisp):
+    """cost_volume/cost_volume.py:108-117 -> (B, maxdisp, H, W): L1 distance between the left features and the right features
+    shifted by d; columns w < d see a zero right feature."""
+    l, dt = _prep(feat_l, "feat_l")
+    r, _ = _prep(feat_r, "feat_r")
+    assert l.dim() == 4 and l.shape == r.shape
+    _same_device(l, r)
+    b, c, h, w = l.shape
+    out = torch.empty((b, maxdisp, h, w), dtype=torch.float32, device=l.device)
+    if out.numel():
+        _call("osb_sub_volume_fwd", l.data_ptr(), r.data_ptr(), out.data_ptr(), b, c, h, w, maxdisp, _stream(out))
+    return out.to(dt)
+
+
 def gwc_concat_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, maxdisp, num_groups):
     """GwcVolumeCostProcessor.forward (gwcnet_cost_processor.py:55-68): both volumes and the
     torch.cat in one launch -> (B, G + 2*Cc, maxdisp, H, W)."""
@@ -179,6 +226,19 @@ def disparity_regression_interval(prob, maxdisp, interval):
     maxdisp // interval hypotheses 0, interval, 2*interval, ...; prob is already normalised.  -> (B, 1, H, W)."""
     assert len(prob.shape) == 4
     return softargmin(prob, maxdisp // interval, keepdim=True, start=0.0, step=float(interval), normalize=False)
+
+
+def disparity_regression_values(prob, disp_values):
+    """CasStereo's expectation over per-pixel hypothesis planes (casnet/submodule.py:22-24): sum_d prob * disp_values -> (B, H, W)."""
+    p, dt = _prep(prob, "prob")
+    v, _ = _prep(disp_values, "disp_values")
+    assert len(p.shape) == 4 and p.shape == v.shape
+    _same_device(p, v)
+    b, d, h, w = p.shape
+    out = torch.empty((b, h, w), dtype=torch.float32, device=p.device)
+    if out.numel():
+        _call("osb_regression_values_fwd", p.data_ptr(), v.data_ptr(), out.data_ptr(), b, d, h, w, _stream(out))
+    return out.to(dt)
 
 
 def faster_soft_argmin(cost_volume, max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True):
@@ -341,26 +401,33 @@ def f16_split(w):
 
 class TcWeight:
     """A conv weight packed for the tcgen05 kernels: `data` fp16 [3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc hi | kc lo] of
-    w * 2^e_c, and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply."""
-    __slots__ = ("data", "inv", "kc", "cout", "_eff")
+    w * 2^e_c, and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply.
+    `cout` is the packed row count per kw slice (narrow heads are zero-padded to 16), `cout_real` the layer's channels."""
+    __slots__ = ("data", "inv", "kc", "cout", "cout_real", "_eff")
 
-    def __init__(self, data, inv, kc, cout):
+    def __init__(self, data, inv, kc, cout, cout_real=None):
         self.data, self.inv, self.kc, self.cout, self._eff = data, inv, kc, cout, None
+        self.cout_real = cout if cout_real is None else cout_real
 
     def eff_scale(self, scale):
         """Epilogue scale vector: folded-BN scale (or 1) times the exact power-of-two un-scaling of this weight."""
         key = None if scale is None else (scale.data_ptr(), scale._version)
         if self._eff is None or self._eff[0] != key:
+            if scale is not None and scale.numel() < self.inv.numel():            # zero-padded head: pad the BN scale too
+                scale = torch.cat((scale.float(), scale.new_ones(self.inv.numel() - scale.numel()).float()))
             eff = self.inv if scale is None else scale.float() * self.inv
             self._eff = (key, eff.contiguous())
         return self._eff[1]
 
 
-def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2)):
+def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2), pad_cout_to=None):
     """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> TcWeight (see there).  Per output channel the weights are scaled by the
     power of two that puts max |w| into [2^14, 2^15) (exact; undone by TcWeight.inv), then split with f16_split."""
     w = weight.detach().float()
-    cout, cin = w.shape[:2]
+    cout_real, cin = w.shape[:2]
+    if pad_cout_to is not None and cout_real < pad_cout_to:             # narrow classifier heads ride the COUT = 16 kernel variant
+        w = torch.cat((w, w.new_zeros((pad_cout_to - cout_real,) + tuple(w.shape[1:]))), 0)
+    cout = w.shape[0]
     kc = TC_KC if kc is None else kc
     assert kc in (16, 32) and cin % kc == 0 and tuple(w.shape[2:]) == (3, 3, 3)
     amax = w.abs().amax(dim=(1, 2, 3, 4))
@@ -374,7 +441,7 @@ def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2)):
     both = both.permute(4, 2, 5, 6, 1, 0, 3)                           # (kd, chunk, kh, kw, co, half, ci)
     data = both.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
     inv = torch.ldexp(torch.ones_like(amax), -(e + TC_ACT_SCALE_LOG2))
-    return TcWeight(data, inv.contiguous(), kc, cout)
+    return TcWeight(data, inv.contiguous(), kc, cout, cout_real)
 
 
 def _tc_args(w_split, cin, kc, scale):
@@ -397,10 +464,12 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
     """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
     b, d, h, w, cin = x_ndhwc.shape
-    cout = w_split.cout
+    cout = w_split.cout_real
     kc = conv3d_tc_kc(cin, cout, w)
     assert kc
     wptr, scale = _tc_args(w_split, cin, kc, scale)
+    if shift is not None and shift.numel() < w_split.cout:               # zero-padded head
+        shift = torch.cat((shift.float(), shift.new_zeros(w_split.cout - shift.numel()).float()))
     shape = (b, d, h, w, cout) if out_ndhwc else (b, cout, d, h, w)
     y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
     if residual is not None:
@@ -484,6 +553,44 @@ def conv3d_k3_c1_ndhwc(x_ndhwc, w_taps, scale=None, shift=None):
     y = torch.empty((b, 1, d, h, w), dtype=torch.float32, device=x_ndhwc.device)
     _call("osb_conv3d_k3_c1_ndhwc_fwd", x_ndhwc.data_ptr(), w_taps.data_ptr(), _ptr(scale), _ptr(shift), y.data_ptr(), b, cin, d, h, w,
           _stream(y))
+    return y
+
+
+# ------------------------------------------------------------------ LightStereo 2D aggregation
+def dwconv2d(x, weight, scale=None, shift=None, residual=None, stride=1, act=ACT_NONE, out=None):
+    """Depthwise Conv2d (groups = C, padding = k // 2) + per-channel scale/shift + residual + activation
+    (lightstereo/aggregation.py:80-84 dwconv, :109-117 strip convs).  x (B,C,H,W); weight (C,1,KH,KW) or (C,KH,KW)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    b, c, h, w = x.shape
+    kh, kw = weight.shape[-2:]
+    wt = weight.detach().float().reshape(c, kh, kw).contiguous()
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((b, c, ho, wo), dtype=torch.float32, device=x.device) if out is None else out
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+    _call("osb_dwconv2d_fwd", x.data_ptr(), wt.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, c, h, w,
+          int(kh), int(kw), int(stride), act, _stream(y))
+    return y
+
+
+def pack_deconv2d_weight(weight):
+    """(Cin, Cout, 3, 3) ConvTranspose2d parameter -> (Cin, 9, Cout) contiguous fp32."""
+    ci, co = weight.shape[:2]
+    assert tuple(weight.shape[2:]) == (3, 3)
+    return weight.detach().float().permute(0, 2, 3, 1).reshape(ci, 9, co).contiguous()
+
+
+def deconv2d_k3s2(x, w_packed, scale=None, shift=None, residual=None, act=ACT_NONE):
+    """ConvTranspose2d(k3, s2, p1, op1) + folded BN + residual + activation (lightstereo/aggregation.py:28-34,58-59)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    b, cin, h, w = x.shape
+    assert w_packed.shape[0] == cin and w_packed.shape[1] == 9
+    cout = w_packed.shape[2]
+    y = torch.empty((b, cout, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+    _call("osb_deconv2d_k3s2_fwd", x.data_ptr(), w_packed.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual), y.data_ptr(), b, cin,
+          cout, h, w, act, _stream(y))
     return y
 
 

@@ -140,3 +140,17 @@ def build_corr_volume(img_left, img_right, max_disp):
         else:
             vol[:, i, :, :] = (img_left * img_right).mean(dim=1)
     return vol.contiguous()
+
+
+def build_sub_volume(feat_l, feat_r, maxdisp):
+    """cost_volume.py:108-117 (L1 distance volume of StereoBase's USE_SUB_VOLUME).  Restated device-agnostic: the reference
+    allocates with device='cuda' and cannot run on a CPU-only machine, so this flavour is pinned by tests/test_ops_gpu.py on the
+    GPU box against the reference's own function there (oracle/_ref) instead of by a CPU-generated golden vector."""
+    cost = feat_l.new_zeros((feat_l.size(0), maxdisp, feat_l.size(2), feat_l.size(3)))
+    for i in range(maxdisp):
+        cost[:, i, :, :i] = feat_l[:, :, :, :i].abs().sum(1)
+        if i > 0:
+            cost[:, i, :, i:] = torch.norm(feat_l[:, :, :, i:] - feat_r[:, :, :, :-i], 1, 1)
+        else:
+            cost[:, i, :, i:] = torch.norm(feat_l - feat_r, 1, 1)
+    return cost.contiguous()

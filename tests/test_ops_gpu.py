@@ -447,3 +447,42 @@ def test_disparity_regression_interval_golden(ops):
     out = ops.disparity_regression_interval(dev(g["prob"]), g["maxdisp"], g["interval"])
     assert out.shape == g["out_interval"].shape
     assert_close(out, g["out_interval"], 1e-5 * g["maxdisp"], "interval regression")
+
+
+def test_gwc_normalized_and_coex_golden(ops):
+    """FoundationStereo's L2-normalised gwc volume and CoExCostVolume vs the outputs of the unmodified reference functions
+    (tests/golden, tools/make_golden.py: flavours).  <= 2e-6 abs on values of magnitude <= 1 (normalised) / <= 1e-5 of the scale."""
+    g = load_golden("gwc_normalized")
+    out = ops.build_gwc_volume_normalized(dev(g["left"]), dev(g["right"]), g["maxdisp"], g["groups"])
+    assert out.shape == g["out"].shape
+    assert_close(out, g["out"], 2e-6, "normalised gwc volume")
+    w = g["left"].shape[-1]
+    for d in range(1, min(g["maxdisp"], w)):
+        assert (out[:, :, d, :, :d] == 0).all()
+    g = load_golden("coex_volume")
+    out = ops.coex_cost_volume(dev(g["left"]), dev(g["right"]), g["maxdisp"], g["group"])
+    assert out.shape == g["out"].shape
+    assert_close(out, g["out"], 1e-5 * float(g["out"].abs().max()), "CoEx volume")
+
+
+def test_sub_volume_vs_oracle_and_reference(ops):
+    """build_sub_volume (cost_volume.py:108-117): CPU restatement, and -- the reference hard-codes device='cuda' -- the reference's
+    own function executed on this GPU when the staged tree (oracle/_ref) is present."""
+    from oracle import _reference_shim as shim
+    from oracle import cost_volume as ocv
+    for shape, d in (((2, 12, 5, 37), 9), ((1, 96, 4, 128), 48), ((1, 3, 2, 6), 8)):
+        l, r = rnd(70, *shape), rnd(71, *shape)
+        got = ops.build_sub_volume(dev(l), dev(r), d)
+        want = ocv.build_sub_volume(l, r, d)
+        assert got.shape == want.shape
+        assert_close(got, want, 1e-5 * float(want.abs().max()), "sub volume vs oracle")
+        if shim.available():
+            ref = shim.load("stereo.modeling.cost_volume.cost_volume").build_sub_volume(dev(l), dev(r), d)
+            assert_close(got, ref.cpu(), 1e-5 * float(want.abs().max()), "sub volume vs the reference on this GPU")
+
+
+def test_disparity_regression_values_golden(ops):
+    g = load_golden("regression_flavours")
+    out = ops.disparity_regression_values(dev(g["prob"]), dev(g["values"]))
+    assert out.shape == g["out_values"].shape
+    assert_close(out, g["out_values"], 1e-5 * float(g["out_values"].abs().max()), "explicit-hypothesis regression")
