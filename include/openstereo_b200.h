@@ -202,6 +202,18 @@ int osb_group_l2_normalize_fwd(const float* x, float* y, int B, int C, int H, in
 int osb_sub_volume_fwd(const float* left, const float* right, float* out, int B, int C, int H, int W, int D, osb_stream_t stream);
 int osb_regression_values_fwd(const float* prob, const float* values, float* out, int B, int D, int H, int W, osb_stream_t stream);
 
+/* Backward (adjoint) kernels so the volume constructors and the soft-argmin stay differentiable under tools/train.py
+ * (openstereo_b200/autograd.py wraps them in torch.autograd.Function).  grad_ref / grad_tgt may be NULL when not needed.
+ *   osb_gwc_volume_bwd     adjoint of osb_gwc_volume_fwd (reduce_sum = 0) / osb_gwc_volume_sum_fwd (1): grad_vol (B,G,D,H,W)
+ *   osb_concat_volume_bwd  adjoint of osb_concat_volume_fwd: grad_vol (B,2C,D,H,W)
+ *   osb_softargmin_bwd     adjoint of osb_softargmin_fwd w.r.t. cost: grad_out (B,H,W) -> grad_cost (B,D,H,W) */
+int osb_gwc_volume_bwd(const float* grad_vol, const float* ref, const float* tgt, float* grad_ref, float* grad_tgt, int B, int C,
+                       int H, int W, int D, int G, int reduce_sum, osb_stream_t stream);
+int osb_concat_volume_bwd(const float* grad_vol, float* grad_ref, float* grad_tgt, int B, int C, int H, int W, int D, int mask_left,
+                          osb_stream_t stream);
+int osb_softargmin_bwd(const float* cost, const float* grad_out, float* grad_cost, int B, int D, int H, int W, float alpha,
+                       float start, float step, int normalize, osb_stream_t stream);
+
 /* ---- LightStereo 2D cost aggregation (lightstereo/aggregation.py:7-134) ------------------------------
  * Depthwise Conv2d (groups = C), kernel KH x KW (odd, <= 21), padding (KH/2, KW/2), stride 1 or 2, NCHW fp32:
  *   y[b,c,oh,ow] = act(scale[c] * sum_{i,j} w[c,i,j] * x[b,c,oh*s+i-KH/2,ow*s+j-KW/2] + shift[c] + residual[b,c,oh,ow])

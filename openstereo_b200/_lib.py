@@ -45,6 +45,9 @@ SIGNATURES = {
     "osb_group_l2_normalize_fwd": [_f32p, _f32p, _i, _i, _i, _i, _i, _f, _s],
     "osb_sub_volume_fwd": [_f32p, _f32p, _f32p, _i, _i, _i, _i, _i, _s],
     "osb_regression_values_fwd": [_f32p, _f32p, _f32p, _i, _i, _i, _i, _s],
+    "osb_gwc_volume_bwd": [_f32p] * 5 + [_i] * 7 + [_s],
+    "osb_concat_volume_bwd": [_f32p] * 3 + [_i] * 6 + [_s],
+    "osb_softargmin_bwd": [_f32p] * 3 + [_i] * 4 + [_f, _f, _f, _i, _s],
     "osb_dwconv2d_fwd": [_f32p] * 6 + [_i] * 8 + [_s],
     "osb_deconv2d_k3s2_fwd": [_f32p] * 6 + [_i] * 6 + [_s],
 }

@@ -83,9 +83,27 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _recording(*tensors):
+    """True when autograd is recording on one of the operands: the call must go through openstereo_b200.autograd (the plain
+    path detaches its inputs)."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _grad_operands(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("openstereo_b200: not implemented on the CPU (openstereo_b200 has no CPU fallback)")
+    return [t.float() for t in tensors]
+
+
 # --------------------------------------------------------------------------- cost volumes
 def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
     """stereo/modeling/cost_volume/cost_volume.py:68-78 -> (B, num_groups, maxdisp, H, W)."""
+    if _recording(refimg_fea, targetimg_fea):
+        from .autograd import GwcVolumeFn
+        assert refimg_fea.dim() == 4 and refimg_fea.shape == targetimg_fea.shape and refimg_fea.shape[1] % num_groups == 0
+        r, t = _grad_operands(refimg_fea, targetimg_fea)
+        return GwcVolumeFn.apply(r, t, int(maxdisp), int(num_groups), False).to(refimg_fea.dtype)
     ref, dt = _prep(refimg_fea, "refimg_fea")
     tgt, _ = _prep(targetimg_fea, "targetimg_fea")
     assert ref.dim() == 4 and ref.shape == tgt.shape
@@ -101,6 +119,11 @@ def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
 
 def build_concat_volume(refimg_fea, targetimg_fea, maxdisp, mask_left=True):
     """cost_volume.py:81-92 -> (B, 2C, maxdisp, H, W); mask_left=False is igev/submodule.py:216-227."""
+    if _recording(refimg_fea, targetimg_fea):
+        from .autograd import ConcatVolumeFn
+        assert refimg_fea.dim() == 4 and refimg_fea.shape == targetimg_fea.shape
+        r, t = _grad_operands(refimg_fea, targetimg_fea)
+        return ConcatVolumeFn.apply(r, t, int(maxdisp), bool(mask_left)).to(refimg_fea.dtype)
     ref, dt = _prep(refimg_fea, "refimg_fea")
     tgt, _ = _prep(targetimg_fea, "targetimg_fea")
     assert ref.dim() == 4 and ref.shape == tgt.shape
@@ -123,6 +146,11 @@ def cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1):
 
 def correlation_volume(left_feature, right_feature, max_disp):
     """cost_volume.py:32-41 -> (B, max_disp, H, W)."""
+    if _recording(left_feature, right_feature):
+        from .autograd import GwcVolumeFn
+        assert left_feature.dim() == 4 and left_feature.shape == right_feature.shape
+        l, r = _grad_operands(left_feature, right_feature)
+        return GwcVolumeFn.apply(l, r, int(max_disp), 1, False).squeeze(1).to(left_feature.dtype)
     l, dt = _prep(left_feature, "left_feature")
     r, _ = _prep(right_feature, "right_feature")
     assert l.dim() == 4 and l.shape == r.shape
@@ -155,6 +183,11 @@ def build_gwc_volume_normalized(refimg_fea, targetimg_fea, maxdisp, num_groups):
 def coex_cost_volume(x, y, maxdisp, group=1):
     """CoExCostVolume(maxdisp, group)(x, y), cost_volume/cost_volume.py:9-29 -> (B, group, maxdisp + 1, H, W):
     cost[b,g,d,h,w] = sum_k x[b,gK+k,h,w] * y[b,gK+k,h,w-d], zero where w < d (the module's left zero padding)."""
+    if _recording(x, y):
+        from .autograd import GwcVolumeFn
+        assert x.dim() == 4 and x.shape == y.shape and x.shape[1] % group == 0
+        a, b_ = _grad_operands(x, y)
+        return GwcVolumeFn.apply(a, b_, int(maxdisp) + 1, int(group), True).to(x.dtype)
     xs, dt = _prep(x, "x")
     ys, _ = _prep(y, "y")
     assert xs.dim() == 4 and xs.shape == ys.shape
@@ -203,6 +236,12 @@ def gwc_concat_volume(ref_gwc, tgt_gwc, ref_cat, tgt_cat, maxdisp, num_groups):
 # --------------------------------------------------------------------------- soft-argmin tails
 def softargmin(cost, maxdisp, keepdim=True, alpha=1.0, start=0.0, step=1.0, normalize=True):
     """disparity_regression(F.softmax(cost, 1), maxdisp) in one pass (stereobase_gru.py:163-164)."""
+    if _recording(cost):
+        from .autograd import SoftArgminFn
+        assert cost.dim() == 4 and cost.shape[1] == maxdisp
+        (cg,) = _grad_operands(cost)
+        out = SoftArgminFn.apply(cg, float(alpha), float(start), float(step), bool(normalize)).to(cost.dtype)
+        return out.unsqueeze(1) if keepdim else out
     c, dt = _prep(cost, "cost")
     assert len(c.shape) == 4                          # disp_regression.py:9
     b, d, h, w = c.shape
