@@ -51,6 +51,9 @@ uint64_t osb_launch_count(void);
  * that met a larger value increments a sticky per-device counter.  osb_tc_overflow_count copies it to *count (host memory),
  * optionally resets it, and synchronises `stream`; osb_tc_overflow_flag returns its device address (for an asynchronous read). */
 int osb_tc_overflow_count(osb_stream_t stream, int reset, unsigned int* count);
+/* Asynchronous variant: enqueue a 4-byte copy of the counter into PINNED host memory on `stream` and return at once (the caller
+ * reads *host_pinned after an event recorded behind it has completed; the Python engines do that at the start of their next call). */
+int osb_tc_overflow_poll(osb_stream_t stream, unsigned int* host_pinned);
 const unsigned int* osb_tc_overflow_flag(void);
 /* Expected round-towards-zero loss per accumulating tcgen05.mma, undone by the conv epilogues (csrc/tc_common.cuh: rz_kappa;
  * DESIGN.md section 4.3).  Process-wide; returns the previous value; 0 switches the correction off.  The default is the
@@ -157,6 +160,11 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
 int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* Same, reading an NCDHW input (B,Cin,D,H,W) -- the cost volume exactly as osb_gwc_concat_volume_fwd / build_*_volume return it --
+ * so the first aggregation layer needs no layout-conversion pass.  Served by the W = 128 variant (Cout = 32 or <= 16). */
+int osb_conv3d_k3_tc_ncdhw_fwd(const float* x_ncdhw, const void* w_split, const float* scale, const float* shift,
+                               const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                               int out_ndhwc, int res_ndhwc, osb_stream_t stream);
 /* Stride-2 variant (the down-sampling convs of the hourglasses): x (B,D,H,W,Cin) channels-last with even D,H,W ->
  * y (B,Cout,D/2,H/2,W/2) or channels-last.  w_split like above but with the kw slices stored in the order (1,0,2)
  * (ops.pack_tc_weight(..., kw_order=(1,0,2))), 16-channel K chunks.  Supported: W=128/Cout=64, W=64/Cout=64|128. */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "osb_deconv3d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv3d_k3_s2_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv3d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
+    "osb_conv3d_k3_tc_ncdhw_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv1x1_ndhwc_fwd": [_f32p] * 5 + [ctypes.c_longlong, _i, _i, _i, _s],
     "osb_conv3d_k3_c1_ndhwc_fwd": [_f32p] * 5 + [_i] * 5 + [_s],
     "osb_avgpool_pairs_fwd": [_f32p, _f32p, ctypes.c_longlong, _i, ctypes.c_longlong, _s],
@@ -68,6 +69,8 @@ def _load():
     lib.osb_launch_count.restype = ctypes.c_uint64
     lib.osb_tc_overflow_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint)]
     lib.osb_tc_overflow_count.restype = ctypes.c_int
+    lib.osb_tc_overflow_poll.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.osb_tc_overflow_poll.restype = ctypes.c_int
     lib.osb_tc_overflow_flag.argtypes = []
     lib.osb_tc_overflow_flag.restype = ctypes.c_void_p
     lib.osb_set_rz_kappa.argtypes = [ctypes.c_float]

@@ -74,9 +74,16 @@ def _tc_ok(layer, width):
     return _tc_weight(layer, width) is not None
 
 
-def _conv_tc(layer, x_ndhwc, act=ACT_NONE, residual=None, out_ndhwc=True, res_ndhwc=True):
-    wt = _tc_weight(layer, x_ndhwc.shape[3])
-    return ops.conv3d_k3_tc(x_ndhwc, wt, layer.scale, layer.shift, residual, act, out_ndhwc, res_ndhwc)
+def _conv_tc(layer, x_ndhwc, act=ACT_NONE, residual=None, out_ndhwc=True, res_ndhwc=True, in_ncdhw=False):
+    wt = _tc_weight(layer, x_ndhwc.shape[4] if in_ncdhw else x_ndhwc.shape[3])
+    return ops.conv3d_k3_tc(x_ndhwc, wt, layer.scale, layer.shift, residual, act, out_ndhwc, res_ndhwc, in_ncdhw)
+
+
+def _stem_in(layer, volume, act):
+    """First aggregation layer on an NCDHW cost volume: the W = 128 kernel reads NCDHW directly, other variants convert once."""
+    if ops.conv3d_tc_kc(layer.cin, layer.cout, volume.shape[-1]) == 32:
+        return _conv_tc(layer, volume, act, in_ncdhw=True)
+    return _conv_tc(layer, ops.to_ndhwc(volume), act)
 
 
 def _conv_auto(layer, x, act=ACT_NONE, residual=None):
@@ -111,6 +118,14 @@ class _Engine:
     def __init__(self, module):
         self.module = module
         self._stamp = None
+
+    def _watch(self, device):
+        """fp16-range guard of the tensor-core convolutions: report a past overflow, schedule the next asynchronous read."""
+        if USE_TENSOR_CORES:
+            mon = ops.TcOverflowMonitor.get(device)
+            mon.check()
+            return mon
+        return None
 
     def _ensure(self, device):
         stamp = (str(device), _versions(self.module), tuple(p.data_ptr() for p in self.module.parameters()))
@@ -201,7 +216,7 @@ class GwcAggregation(_Engine):
         b, _, dd, hh, ww = volume.shape
         if stem_tc and _tc_ok(self.classif3[0], width) and all(_hg_channels_last_ok(hg, (b, dd, hh, ww, 32)) for hg in self.hg):
             # everything from the volume to the classifier runs channels-last on the tensor cores: ONE layout conversion
-            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)
+            c = _conv_tc(self.dres0[1], _stem_in(self.dres0[0], volume, ACT_RELU), ACT_RELU)
             out = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
             for hg in self.hg:
                 out = _gwc_hourglass_channels_last(hg, out)
@@ -217,7 +232,7 @@ class GwcAggregation(_Engine):
             return _conv(cls, head)
         if stem_tc:
             # full-resolution stem on the tensor cores: channels-last inside, NCDHW handed to the hourglasses
-            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(volume), ACT_RELU), ACT_RELU)
+            c = _conv_tc(self.dres0[1], _stem_in(self.dres0[0], volume, ACT_RELU), ACT_RELU)
             cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)
         else:
             c = _conv(self.dres0[1], _conv(self.dres0[0], volume, ACT_RELU), ACT_RELU)
@@ -232,7 +247,11 @@ class GwcAggregation(_Engine):
         return _conv(self.classif3[1], head)
 
     def __call__(self, volume, h, w):
-        return ops.upsample_softargmin(self.logits(volume), self.module.maxdisp, h, w, align_corners=False)
+        mon = self._watch(volume.device)
+        out = ops.upsample_softargmin(self.logits(volume), self.module.maxdisp, h, w, align_corners=False)
+        if mon is not None:
+            mon.poll()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------------ PSMNet
@@ -266,7 +285,7 @@ class PSMAggregation(_Engine):
         self._ensure(raw_cost.device)
         width = raw_cost.shape[-1]
         if all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1])):
-            c = _conv_tc(self.dres0[1], _conv_tc(self.dres0[0], ops.to_ndhwc(raw_cost), ACT_RELU), ACT_RELU)
+            c = _conv_tc(self.dres0[1], _stem_in(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
             cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)
         else:
             c = _conv(self.dres0[1], _conv(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
@@ -291,8 +310,12 @@ class PSMAggregation(_Engine):
     def __call__(self, raw_cost):
         b, c, d, h, w = raw_cost.shape
         max_disp = self.module.max_disp
-        return [ops.upsample_softargmin(cost, max_disp, 4 * h, 4 * w, align_corners=True)
-                for cost in self.logits(raw_cost)]
+        mon = self._watch(raw_cost.device)
+        out = [ops.upsample_softargmin(cost, max_disp, 4 * h, 4 * w, align_corners=True)
+               for cost in self.logits(raw_cost)]
+        if mon is not None:
+            mon.poll()
+        return out
 
 
 # -------------------------------------------------------------------------------------------------- StereoBase

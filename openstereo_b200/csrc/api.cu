@@ -138,4 +138,16 @@ int osb_tc_overflow_count(osb_stream_t stream, int reset, unsigned int* count) {
   return OSB_OK;
 }
 const unsigned int* osb_tc_overflow_flag(void) { return osb::tc_overflow_flag(); }
+int osb_tc_overflow_poll(osb_stream_t stream, unsigned int* host_pinned) {
+  using namespace osb;
+  OSB_REQUIRE(host_pinned, "tc_overflow_poll: null pointer");
+  unsigned int* flag = tc_overflow_flag();
+  if (!flag) return OSB_ECUDA;
+  cudaError_t e = cudaMemcpyAsync(host_pinned, flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("tc_overflow_poll: %s", cudaGetErrorString(e));
+    return OSB_ECUDA;
+  }
+  return OSB_OK;
+}
 }

@@ -56,6 +56,7 @@ struct TcParams {
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
+  int in_ncdhw;      // the INPUT is (B, Cin, D, H, W): the first aggregation layer reads the cost volume as the volume kernel wrote it
   int items, hblocks;
 };
 
@@ -220,7 +221,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const int d = (s.it / p.hblocks) % p.D;
       const int b = s.it / (p.hblocks * p.D);
       const int hin = hb * TC_TILES - 1 + s.r, din = d + s.kd - 1;
-      if (hin >= 0 && hin < p.H) {                    // rows outside the image are the conv's zero padding
+      if (hin >= 0 && hin < p.H && p.in_ncdhw) {
+        // NCDHW input: this thread stages voxel (column) lt for all eight channel quads; every LDG.32 of a warp is one
+        // contiguous 128-byte row segment of a channel plane.  v[j] holds channels 4*qj .. 4*qj+3, qj = j ^ ((lt >> 3) & 1)
+        // (the swap keeps the STS.64 of lanes 8 apart -- same swizzled chunk -- on different 8-byte halves).
+        const size_t plane = (size_t)p.D * p.H * TC_W;
+        const float* src = p.x + (((size_t)b * p.Cin + s.ch * TC_KC) * p.D + din) * p.H * TC_W + (size_t)hin * TC_W + lt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float* q = src + (size_t)(4 * (j ^ ((lt >> 3) & 1))) * plane;
+          v[j] = make_float4(__ldg(q), __ldg(q + plane), __ldg(q + 2 * plane), __ldg(q + 3 * plane));
+        }
+      } else if (hin >= 0 && hin < p.H) {             // rows outside the image are the conv's zero padding
         const float* src = p.x + (((size_t)b * p.D + din) * p.H + hin) * row_stride + s.ch * TC_KC + c16 * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(vcol + 16 * j) * p.Cin));
@@ -234,8 +246,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const uint32_t s = rowc % TC_STAGES, par = (rowc / TC_STAGES) & 1;
       mbar_wait_relaxed(&a_empty[s], par ^ 1);        // the MMAs that read this slot last time have completed
       uint8_t* tile = a_buf + s * TC_ROW_BYTES;
+      if (p.in_ncdhw) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) stage_f16_split<TC_KC>(tile, vcol + 16 * j, c16, v[j], amax);   // tile row = image column
+        for (int j = 0; j < 8; ++j) stage_f16_split<TC_KC>(tile, lt, j ^ ((lt >> 3) & 1), v[j], amax);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stage_f16_split<TC_KC>(tile, vcol + 16 * j, c16, v[j], amax);   // tile row = image column
+      }
       fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_ready[s]);
       ++rowc;
@@ -473,9 +490,9 @@ int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int
   return check_launch("ncdhw_to_ndhwc_kernel");
 }
 
-int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
-                         const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
-                         int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                             const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                             int out_ndhwc, int res_ndhwc, int in_ncdhw, osb_stream_t stream) {
   using namespace osb;
   OSB_REQUIRE(x_ndhwc && w_split && y, "conv3d_k3_tc: null pointer");
   OSB_REQUIRE(B > 0 && D > 0 && H > 0, "conv3d_k3_tc: empty shape");
@@ -484,6 +501,7 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float*
   OSB_REQUIRE((reinterpret_cast<uintptr_t>(x_ndhwc) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_split) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
               "conv3d_k3_tc: pointers must be 16-byte aligned");
+  OSB_REQUIRE(!in_ncdhw || osb_conv3d_tc_kc(Cin, Cout, W, 1) == 32, "conv3d_k3_tc: NCDHW input is served by the W = 128 kernel only");
   if (osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16)
     return launch_tcg_dispatch(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc,
                                (cudaStream_t)stream);
@@ -492,7 +510,7 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float*
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.Cout = Cout, p.act = act;
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "conv3d_k3_tc: cannot allocate the overflow flag");
-  p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc, p.in_ncdhw = in_ncdhw;
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");
@@ -502,6 +520,18 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float*
     return launch_tc<16>(p, (cudaStream_t)stream);
   }
   return launch_tc<32>(p, (cudaStream_t)stream);
+}
+
+int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                         const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                         int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  return conv3d_k3_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc, 0, stream);
+}
+
+int osb_conv3d_k3_tc_ncdhw_fwd(const float* x_ncdhw, const void* w_split, const float* scale, const float* shift,
+                               const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                               int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  return conv3d_k3_tc_impl(x_ncdhw, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc, 1, stream);
 }
 
 int osb_conv2d_tc_kc(int Cin, int Cout, int W, int dilation) {

@@ -21,6 +21,8 @@
 // concat unit: pure shifted copy; right rows are staged per warp in the same shared buffer.
 //
 // Roofline: HBM-bound.  Algorithmic bytes = 4*(2*B*C*H*W + B*Cout*D*H*W)  (BASELINE.md section 3).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace osb {
@@ -40,6 +42,7 @@ struct VolParams {
   int Ctot, oc_cat;
   int GU, n_gwc_units, n_cat_units, w_tiles, d_chunks;
   int mask_left, use_tma, vec_ok;
+  int order;           // work-item order: 0 = unit fastest, 1 = image row fastest (adjacent CTAs write adjacent 512-byte rows)
   float inv_k;
 };
 
@@ -71,10 +74,17 @@ struct Item {
 __device__ __forceinline__ Item decode_item(const VolParams& p, int it) {
   Item i;
   const int units = p.n_gwc_units + p.n_cat_units;
-  i.unit = it % units;
-  it /= units;
-  i.h = it % p.H;
-  it /= p.H;
+  if (p.order == 1) {                               // rows fastest: CTAs resident together fill neighbouring rows of one (c, d) plane
+    i.h = it % p.H;
+    it /= p.H;
+    i.unit = it % units;
+    it /= units;
+  } else {
+    i.unit = it % units;
+    it /= units;
+    i.h = it % p.H;
+    it /= p.H;
+  }
   i.d0 = (it % p.d_chunks) * kChunkD;
   it /= p.d_chunks;
   i.w0 = (it % p.w_tiles) * kTileW;
@@ -287,6 +297,13 @@ static int launch_volume(const float* ref_g, const float* tgt_g, const float* re
   p.w_tiles = (W + kTileW - 1) / kTileW;
   p.d_chunks = (D + kChunkD - 1) / kChunkD;
   p.mask_left = mask_left;
+  {
+    static const int order = [] {                   // OSB_VOLUME_ORDER=0 restores the round-1 item order (A/B in tools/kbench.py)
+      const char* e = getenv("OSB_VOLUME_ORDER");
+      return e ? atoi(e) : 1;
+    }();
+    p.order = order;
+  }
   p.inv_k = K > 0 ? (reduce_sum ? 1.0f : 1.0f / (float)K) : 0.f;   // reduce_sum: plain sum over the group's channels (CoEx, L2-normalised gwc)
   auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = (W % 4 == 0) && aligned16(ref_g) && aligned16(ref_c) && aligned16(out);

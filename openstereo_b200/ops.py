@@ -429,6 +429,45 @@ def tc_overflow_count(device=None, reset=False):
     return int(out.value)
 
 
+class TcOverflowMonitor:
+    """Asynchronous watch on the fp16-range counter (include/openstereo_b200.h: osb_tc_overflow_poll).  An engine calls poll()
+    after its last kernel (a 4-byte device->pinned-host copy on the current stream, no synchronisation) and check() before its
+    next forward: once the copy has landed, a non-zero count raises -- an activation left the +-4094 range of the tensor-core
+    convolutions and the previous result was computed from saturated operands."""
+    _instances = {}
+
+    @classmethod
+    def get(cls, device):
+        dev = torch.device(device)
+        if dev.index not in cls._instances:
+            cls._instances[dev.index] = cls(dev)
+        return cls._instances[dev.index]
+
+    def __init__(self, device):
+        self.device = device
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    def poll(self):
+        stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.osb_tc_overflow_poll(stream.cuda_stream, self.host.data_ptr())
+        if rc != 0:
+            raise RuntimeError("osb_tc_overflow_poll: %s" % (_lib.lib.osb_last_error() or b"").decode())
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+
+    def check(self):
+        if self.event is not None and self.event.query():
+            self.event = None
+            n = int(self.host.item()) & 0xFFFFFFFF
+            if n:
+                tc_overflow_count(self.device, reset=True)
+                raise RuntimeError("openstereo_b200: %d loader threads met activations outside the fp16 range of the tensor-core "
+                                   "convolutions (|x| >= 4094); the previous result is invalid.  Run those layers with "
+                                   "aggregation.USE_TENSOR_CORES = False" % n)
+
+
 def f16_split(w):
     """fp32 tensor (already scaled into the fp16 range) -> (hi, lo) fp16 with hi = rn(w), lo = rn(w - hi):
     |w - hi - lo| <= 2^-22 |w| while lo stays a normal fp16 number (|w| >= 2^-3), 2^-25 absolute below that."""
@@ -499,10 +538,15 @@ def to_ndhwc(x):
     return y
 
 
-def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=True, res_ndhwc=True):
-    """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin)."""
+def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=True, res_ndhwc=True,
+                 in_ncdhw=False):
+    """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin), or the NCDHW
+    tensor (B,Cin,D,H,W) with in_ncdhw=True (W = 128 layers only: the cost volume goes in as the volume kernel wrote it)."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
-    b, d, h, w, cin = x_ndhwc.shape
+    if in_ncdhw:
+        b, cin, d, h, w = x_ndhwc.shape
+    else:
+        b, d, h, w, cin = x_ndhwc.shape
     cout = w_split.cout_real
     kc = conv3d_tc_kc(cin, cout, w)
     assert kc
@@ -514,7 +558,8 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
     if residual is not None:
         want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
-    _call("osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
+    assert not in_ncdhw or kc == 32
+    _call("osb_conv3d_k3_tc_ncdhw_fwd" if in_ncdhw else "osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
 

@@ -294,7 +294,7 @@ def test_to_ndhwc(ops):
 
 @pytest.mark.parametrize("b,cin,d,h", [(1, 32, 1, 5), (1, 32, 3, 7), (2, 64, 4, 11), (1, 32, 2, 64), (1, 96, 2, 3)])
 def test_conv3d_tc_matches_fp32(ops, b, cin, d, h):
-    """3xTF32 tensor-core conv vs the fp32 reference conv: same 1e-5 bar as the CUDA-core kernel."""
+    """3xFP16-split tensor-core conv vs the fp32 reference conv: same 1e-5 bar as the CUDA-core kernel."""
     import torch.nn.functional as F
     w, cout = 128, 32
     assert ops.conv3d_tc_supported(cin, cout, w)
@@ -314,6 +314,45 @@ def test_conv3d_tc_matches_fp32(ops, b, cin, d, h):
     got = ops.conv3d_k3_tc(xc, wp, dev(sc), dev(sh), dev(res.permute(0, 2, 3, 4, 1).contiguous()), ops.ACT_RELU,
                            out_ndhwc=True, res_ndhwc=True)
     rel_close(got.permute(0, 4, 1, 2, 3), want2, 1e-5, "tc bn+res+relu ndhwc")
+    # NCDHW input (the cost volume as the volume kernel wrote it): same numbers, no layout-conversion pass
+    got = ops.conv3d_k3_tc(dev(x), wp, dev(sc), dev(sh), dev(res), ops.ACT_RELU, out_ndhwc=False, res_ndhwc=False, in_ncdhw=True)
+    rel_close(got, want2, 1e-5, "tc ncdhw-in")
+    assert ops.tc_overflow_count() == 0
+
+
+@pytest.mark.parametrize("cout", [1, 3, 16])
+def test_conv3d_tc_narrow_head(ops, cout):
+    """Classifier heads (32 -> 1, gwcnet_disp_processor.py:60-70) on the COUT = 16 instantiation: weights zero-padded to 16 rows,
+    only the real channels are written; NCDHW residual = PSMNet's cost_{i-1} (psmnet_cost_processor.py:196-198)."""
+    import torch.nn.functional as F
+    x, wt = rnd(65, 2, 32, 3, 7, 128), rnd(66, cout, 32, 3, 3, 3, scale=0.2)
+    want = F.conv3d(x.double(), wt.double(), padding=1).float()
+    wp = ops.pack_tc_weight(dev(wt), 32, pad_cout_to=16)
+    got = ops.conv3d_k3_tc(ops.to_ndhwc(dev(x)), wp, out_ndhwc=False, res_ndhwc=False)
+    assert got.shape == want.shape
+    rel_close(got, want, 1e-5, "narrow head")
+    res, sh = rnd(67, *want.shape), rnd(68, cout, scale=0.1)
+    got = ops.conv3d_k3_tc(ops.to_ndhwc(dev(x)), wp, None, dev(sh), dev(res), out_ndhwc=False, res_ndhwc=False)
+    rel_close(got, want + sh.view(1, -1, 1, 1, 1) + res, 1e-5, "narrow head + bias + residual")
+
+
+def test_tc_fp16_range_guard(ops):
+    """Activations beyond +-4094 do not fit the fp16 operand split: conversions saturate (finite output) and the sticky counter
+    reports it; in-range inputs with a huge dynamic range (1e-6 .. 1e3) keep fp32-level accuracy."""
+    import torch.nn.functional as F
+    ops.tc_overflow_count(reset=True)
+    wt = rnd(81, 32, 32, 3, 3, 3, scale=0.1)
+    wp = ops.pack_tc_weight(dev(wt))
+    x = rnd(80, 1, 32, 2, 5, 128) * torch.logspace(-6, 3, 128).view(1, 1, 1, 1, 128)
+    got = ops.conv3d_k3_tc(ops.to_ndhwc(dev(x)), wp, out_ndhwc=False)
+    want = F.conv3d(x.double(), wt.double(), padding=1).float()
+    assert ops.tc_overflow_count() == 0
+    err = (got.cpu() - want).abs()
+    col_scale = want.abs().amax(dim=(0, 1, 2, 3)).clamp(min=1e-7)                # per-column magnitude spans 9 decades
+    assert (err.amax(dim=(0, 1, 2, 3)) <= 2e-5 * col_scale + 1e-8).all()
+    x[0, 0, 0, 0, 5] = 1e4
+    got = ops.conv3d_k3_tc(ops.to_ndhwc(dev(x)), wp, out_ndhwc=False)
+    assert torch.isfinite(got).all() and ops.tc_overflow_count(reset=True) >= 1 and ops.tc_overflow_count() == 0
 
 
 @pytest.mark.parametrize("b,cin,cout,d,h,w", [
