@@ -1,4 +1,4 @@
-"""patch(model): make an UNMODIFIED OpenStereo model instance (GwcNet / PSMNet / StereoBase, built by the
+"""patch(model): make an UNMODIFIED OpenStereo model instance (GwcNet / PSMNet / StereoBase / LightStereo / IGEVStereo, built by the
 reference's own classes from an unchanged cfg YAML) run its cost-volume hot path on the sm_100a kernels.
 
 The reference has no operator registry; names are bound three different ways, and each
@@ -8,6 +8,7 @@ needs its own rebinding:
               forward (gwcnet_disp_processor.py:83-140)                    -> per-instance ``forward`` override
 * PSMNet      ``cat_fms`` captured by functools.partial at construction (psmnet_cost_processor.py:227-232),
               aggregator + FasterSoftArgmin modules                          -> ``CostProcessor.forward`` / ``FasterSoftArgmin.forward``
+* LightStereo / IGEVStereo  like StereoBase: names imported into lightstereo.py:4-6 / igev_stereo.py:1-3 (``from .submodule import *``)
 * StereoBase  functions imported INTO the module namespace (stereobase_gru.py:5-6,10-11) and the ``cost_agg``
               Hourglass                                                      -> per-INSTANCE copies of the methods that use those names,
                                                                                 with a private globals dict (the module itself, and
@@ -256,7 +257,80 @@ def _patch_stereobase(model, strict, backbone=True):
     return model
 
 
-_PATCHERS = {"GwcNet": _patch_gwcnet, "PSMNet": _patch_psmnet, "StereoBase": _patch_stereobase}
+def _volume_tail_overrides(model, strict, orig, with_corr):
+    """Guarded replacements of the module-global hot-path functions LightStereo / IGEV import into their model module."""
+    out = {}
+    if with_corr:
+        def corr(left, right, max_disp):
+            if _accelerable(model, left, right):
+                return ops.correlation_volume(left, right, max_disp)
+            return orig["correlation_volume"](left, right, max_disp) if not strict else _refuse("correlation_volume")
+        out["correlation_volume"] = corr
+    else:
+        def gwc(ref, tgt, maxdisp, groups):
+            if _accelerable(model, ref, tgt):
+                return ops.build_gwc_volume(ref, tgt, maxdisp, groups)
+            return orig["build_gwc_volume"](ref, tgt, maxdisp, groups) if not strict else _refuse("build_gwc_volume")
+        out["build_gwc_volume"] = gwc
+
+    def regression(x, maxdisp):
+        if _accelerable(model, x):
+            return ops.disparity_regression(x, maxdisp)
+        return orig["disparity_regression"](x, maxdisp) if not strict else _refuse("disparity_regression")
+
+    def upsample(disp_low, up_weights, scale_factor=4):
+        if scale_factor == 4 and _accelerable(model, disp_low, up_weights):
+            return ops.context_upsample(disp_low, up_weights, 4).to(disp_low.dtype)
+        if strict:
+            _refuse("context_upsample")
+        return orig["context_upsample"](disp_low, up_weights) if scale_factor == 4 else orig["context_upsample"](disp_low, up_weights, scale_factor)
+
+    out["disparity_regression"], out["context_upsample"] = regression, upsample
+    return out
+
+
+def _patch_lightstereo(model, strict, backbone=True):
+    """LightStereo (BASELINE config 4; lightstereo/lightstereo.py:44-70): correlation_volume, the 2D `Aggregation` hourglass
+    (cost_agg), disparity_regression and context_upsample; backbone / refine heads stay the reference's cuDNN code."""
+    from .aggregation import LightStereoAggregation
+    g = type(model).forward.__globals__
+    orig = {n: g[n] for n in ("correlation_volume", "disparity_regression", "context_upsample")}
+    _rebind_methods(model, _volume_tail_overrides(model, strict, orig, with_corr=True))
+    agg_mod = model.cost_agg
+    agg_orig = agg_mod.forward
+    engine = LightStereoAggregation(agg_mod)
+
+    def agg_forward(self, x, features_left):
+        if not _accelerable(self, x, features_left[:3]):
+            return agg_orig(x, features_left) if not strict else _refuse("LightStereo Aggregation")
+        return [t.to(x.dtype) for t in engine(x, features_left[:3])]
+
+    agg_mod.forward = types.MethodType(agg_forward, agg_mod)
+    return model
+
+
+def _patch_igev(model, strict, backbone=True):
+    """IGEV-Stereo (BASELINE config 5; igev/igev_stereo.py:136-213): the gwc volume, the soft-argmin regression of the initial
+    disparity, the per-GRU-iteration lookup of the combined geometry-encoding volume and the convex up-sampling.  The hourglass(8),
+    feature nets and ConvGRU update blocks stay the reference's cuDNN code."""
+    g = type(model).forward.__globals__
+    orig = {n: g[n] for n in ("build_gwc_volume", "disparity_regression", "context_upsample", "Combined_Geo_Encoding_Volume")}
+    over = _volume_tail_overrides(model, strict, orig, with_corr=False)
+
+    def geo_factory(fmap1, fmap2, volume, num_levels=2, radius=4):
+        fast = _accelerable(model, fmap1, fmap2, volume)
+        if not fast and strict:
+            _refuse("Combined_Geo_Encoding_Volume")
+        cls = CombinedGeoEncodingVolume if fast else orig["Combined_Geo_Encoding_Volume"]
+        return cls(fmap1, fmap2, volume, num_levels=num_levels, radius=radius)
+
+    over["Combined_Geo_Encoding_Volume"] = geo_factory
+    _rebind_methods(model, over)
+    return model
+
+
+_PATCHERS = {"GwcNet": _patch_gwcnet, "PSMNet": _patch_psmnet, "StereoBase": _patch_stereobase, "LightStereo": _patch_lightstereo,
+             "IGEVStereo": _patch_igev}
 
 
 def patch(model, strict=True, backbone=True):

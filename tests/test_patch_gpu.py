@@ -101,6 +101,71 @@ def test_patch_stereobase_reference_class(osb):
     assert e_final_gpu <= max(10 * floor, 1e-2)
 
 
+def _lightstereo():
+    shim.install_timm_stub()
+    cfg = shim.load_cfg("cfgs/lightstereo/lightstereo_s_sceneflow.yaml").MODEL
+    m = shim.load("stereo.modeling.models.lightstereo.lightstereo").LightStereo(cfg).eval()
+    m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=11))
+    return m
+
+
+def _igev():
+    shim.install_timm_stub()
+    cfg = shim.load_cfg("cfgs/igev/igev_sceneflow_amp.yaml").MODEL
+    m = shim.load("stereo.modeling.models.igev.igev_stereo").IGEVStereo(cfg).eval()
+    m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=12, scale={"classifier.weight": 8.0}))
+    return m
+
+
+def test_patch_lightstereo_reference_class(osb):
+    """BASELINE config 4's model (cfgs/lightstereo/lightstereo_s_sceneflow.yaml unchanged; timm encoder stand-in) at 320x736:
+    correlation volume, the 2D aggregation hourglass with strip attention, regression and convex up-sampling in this library
+    (>= 50 launches), compared with the unpatched reference on the same GPU and on the CPU."""
+    lib, patch = osb
+    m = _lightstereo()
+    x = _inputs(1, 320, 736, 30)
+    with torch.no_grad():
+        want_cpu = m(dict(x))["disp_pred"]
+        m.cuda()
+        xg = {k: v.cuda() for k, v in x.items()}
+        want_gpu = m(dict(xg))["disp_pred"]
+        patch(m)
+        before = lib.launch_count()
+        got = m(dict(xg))["disp_pred"]
+        launches = lib.launch_count() - before
+    e_gpu = (got - want_gpu).abs().mean().item()
+    e_cpu = (got.cpu() - want_cpu).abs().mean().item()
+    floor = (want_gpu.cpu() - want_cpu).abs().mean().item()
+    print("patch(LightStereo) 320x736: EPE %.3e vs GPU ref, %.3e vs CPU ref (reference GPU-vs-CPU floor %.3e); %d launches"
+          % (e_gpu, e_cpu, floor, launches))
+    assert launches >= 50 and want_cpu.std() > 1e-2
+    assert e_gpu <= max(EPE_BAR, 3 * floor) and e_cpu <= max(EPE_BAR, 3 * floor)
+
+
+def test_patch_igev_reference_class(osb):
+    """BASELINE config 5's model (cfgs/igev/igev_sceneflow_amp.yaml unchanged: 32 GRU iterations at eval) at 256x512: gwc volume,
+    soft-argmin regression, 32 geometry-volume lookups and the final convex up-sampling in this library; like StereoBase the
+    recurrent refinement amplifies any fp32 reordering, so the bound follows the reference's own GPU-vs-CPU floor."""
+    lib, patch = osb
+    m = _igev()
+    g = torch.Generator().manual_seed(31)
+    x = {"left": torch.rand(1, 3, 256, 512, generator=g) * 255, "right": torch.rand(1, 3, 256, 512, generator=g) * 255}
+    with torch.no_grad():
+        want_cpu = m(dict(x))["disp_pred"]
+        m.cuda()
+        xg = {k: v.cuda() for k, v in x.items()}
+        want_gpu = m(dict(xg))["disp_pred"]
+        patch(m)
+        before = lib.launch_count()
+        got = m(dict(xg))["disp_pred"]
+        launches = lib.launch_count() - before
+    e_gpu = (got - want_gpu).abs().mean().item()
+    floor = (want_gpu.cpu() - want_cpu).abs().mean().item()
+    print("patch(IGEVStereo) 256x512: disp_pred EPE %.3e vs GPU ref (reference GPU-vs-CPU floor %.3e); %d launches" % (e_gpu, floor, launches))
+    assert launches >= 1 + 1 + 32 + 1 and torch.isfinite(got).all()
+    assert e_gpu <= max(10 * floor, 1e-2)
+
+
 def test_patch_never_cuts_autograd_on_cuda(osb):
     """a CUDA call that autograd is recording must not reach the kernels (no backward, inputs detached).
     strict=False -> the reference's own code runs and gradients reach the Backbone; strict=True -> loud RuntimeError."""

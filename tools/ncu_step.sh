@@ -15,7 +15,7 @@ BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-comparators"
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > /dev/null 2>&1
 ncu --set full --clock-control none --profile-from-start off --kernel-name-base demangled -k regex:osb:: -f -o /tmp/${TAG} $BENCH > gpurun_out/${TAG}_ncu.log 2>&1
 ncu -i /tmp/${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
-python tools/ncu_summary.py /tmp/${TAG}.ncu-rep > gpurun_out/${TAG}_summary.md 2>/dev/null
+python tools/ncu_summary.py --aggregate /tmp/${TAG}.ncu-rep > gpurun_out/${TAG}_summary.md 2>/dev/null
 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled -k regex:conv3d_tc_kernel -c 1 -f \
     -o gpurun_out/${TAG}_conv3d_tc $BENCH > /dev/null 2>&1
 ls -la gpurun_out/${TAG}_* /tmp/${TAG}.ncu-rep

@@ -37,7 +37,45 @@ def rows_of(path):
             yield hdr, units, r
 
 
+def aggregate(path):
+    """One row per distinct kernel name: launches, total / mean duration, launch-averaged metrics."""
+    groups, order = {}, []
+    hdr = units = None
+    for hdr, units, r in rows_of(path):
+        name = r[hdr.index("Kernel Name")]
+        if name not in groups:
+            groups[name] = []
+            order.append(name)
+        groups[name].append(r)
+    print("## %s (aggregated per kernel)\n" % path.split("/")[-1])
+    cols = [(k, l) for k, l in METRICS if hdr and k in hdr]
+    print("| kernel | launches | total time | " + " | ".join(l for _, l in cols[1:]) + " |")
+    print("|---|---|---|" + "---|" * (len(cols) - 1))
+
+    def num(x):
+        try:
+            return float(x.replace(",", ""))
+        except ValueError:
+            return None
+
+    ti = hdr.index("gpu__time_duration.sum")
+    for name in order:
+        rs = groups[name]
+        total = sum(num(r[ti]) or 0.0 for r in rs)
+        cells = []
+        for k, _ in cols[1:]:
+            vals = [num(r[hdr.index(k)]) for r in rs]
+            vals = [v for v in vals if v is not None]
+            cells.append("%.4g %s" % (sum(vals) / len(vals), units[hdr.index(k)]) if vals else "")
+        print("| `%s` | %d | %.4g %s | %s |" % (name[:110], len(rs), total, units[ti], " | ".join(cells)))
+    print()
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--aggregate":
+        for path in sys.argv[2:]:
+            aggregate(path)
+        return
     for path in sys.argv[1:]:
         print("## %s\n" % path.split("/")[-1])
         for hdr, units, r in rows_of(path):
