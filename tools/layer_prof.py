@@ -12,7 +12,8 @@ from openstereo_b200 import ops  # noqa: E402
 from tools.kbench import timeit  # noqa: E402
 
 LAYERS = {  # name: (kind, cin, cout, D, H, W of the INPUT)
-    "stem": ("s1", 32, 32, 48, 64, 128), "stem64": ("s1", 64, 32, 48, 64, 128),
+    "stem": ("s1", 32, 32, 48, 64, 128), "stem64": ("s1", 64, 32, 48, 64, 128), "stem64n": ("s1n", 64, 32, 48, 64, 128),
+    "head": ("s1h", 32, 1, 48, 64, 128),
     "conv2": ("s1", 64, 64, 24, 32, 64), "conv4": ("s1", 128, 128, 12, 16, 32),
     "conv1s2": ("s2", 32, 64, 48, 64, 128), "conv3s2": ("s2", 64, 128, 24, 32, 64),
     "conv5": ("dc", 128, 64, 12, 16, 32), "conv6": ("dc", 64, 32, 24, 32, 64),
@@ -40,6 +41,17 @@ def main():
         wp = ops.pack_tc_weight(wgt, 16, kw_order=(1, 0, 2))
         fn = lambda: ops.conv3d_k3_s2_tc(x, wp, sc, sh, None, ops.ACT_RELU, out_ndhwc=True)  # noqa: E731
         macs = B * (d // 2) * (h // 2) * (w // 2) * 27 * cin * cout
+    elif kind == "s1n":                                        # NCDHW input (the cost volume as the volume kernel wrote it)
+        wgt = torch.randn(cout, cin, 3, 3, 3, device=dev, generator=g) * 0.05
+        wp = ops.pack_tc_weight(wgt, ops.conv3d_tc_kc(cin, cout, w))
+        xn = x.permute(0, 4, 1, 2, 3).contiguous()
+        fn = lambda: ops.conv3d_k3_tc(xn, wp, sc, sh, None, ops.ACT_RELU, out_ndhwc=True, in_ncdhw=True)  # noqa: E731
+        macs = B * d * h * w * 27 * cin * cout
+    elif kind == "s1h":                                        # 32 -> 1 classifier head on the narrow variant
+        wgt = torch.randn(cout, cin, 3, 3, 3, device=dev, generator=g) * 0.05
+        wp = ops.pack_tc_weight(wgt, 32, pad_cout_to=16)
+        fn = lambda: ops.conv3d_k3_tc(x, wp, None, None, None, ops.ACT_NONE, out_ndhwc=False, res_ndhwc=False)  # noqa: E731
+        macs = B * d * h * w * 27 * cin * cout
     else:
         wgt = torch.randn(cout, cin, 3, 3, 3, device=dev, generator=g) * 0.05
         wp = ops.pack_tc_weight(wgt, ops.conv3d_tc_kc(cin, cout, w))
