@@ -322,13 +322,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const float* xl = (q > 0) ? xb + ((q - 1) * 2) * COUT : zeros;
         const float* xr = (q < 3) ? xb + ((q + 1) * 2 + 1) * COUT : zeros;
         float out[COUT];
+        // The neighbour-quadrant values are loaded UNCONDITIONALLY (warp-uniform addresses: broadcast LDS.128) and merged with
+        // selects: the `lane == 0 ? xl[i] : left` form compiled to a branch around a load per element -- 32 % of the kernel's
+        // stall samples sat on it (branch_resolving; profiles/r2_step_summary.md) and the MMA warp waited for acc_empty.
 #pragma unroll
-        for (int i = 0; i < COUT; ++i) {
-          float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), 1);
-          float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);
-          left = (lane == 0) ? xl[i] : left;          // m-1 lives in the previous quadrant (zero at the image edge)
-          right = (lane == 31) ? xr[i] : right;       // m+1 lives in the next quadrant
-          out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
+        for (int i0 = 0; i0 < COUT; i0 += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(xl + i0);
+          const float4 r4 = *reinterpret_cast<const float4*>(xr + i0);
+          const float le[4] = {l4.x, l4.y, l4.z, l4.w}, re[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), 1);
+            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);
+            left = (lane == 0) ? le[k] : left;        // m-1 lives in the previous quadrant (zero at the image edge)
+            right = (lane == 31) ? re[k] : right;     // m+1 lives in the next quadrant
+            out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
+          }
         }
         if constexpr (COUT == 32) {
           if (p.out_ndhwc && (!p.residual || p.res_ndhwc)) {     // coalesced channels-last path (BN/residual/act inside)

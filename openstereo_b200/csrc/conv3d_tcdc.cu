@@ -302,11 +302,17 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           const float* xr = has_right_q ? xb + ((q + 1) * 2) * 32 : zeros;
           float ev[32], od_[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
-            right = (lane == 31) ? xr[i] : right;                                        // zero beyond the last input column
-            ev[i] = __uint_as_float(raw[0][i]) * corr;
-            od_[i] = (__uint_as_float(raw[1][i]) + right) * corr;
+          for (int i0 = 0; i0 < 32; i0 += 4) {        // neighbour values loaded unconditionally, merged with selects (no branches)
+            const float4 r4 = *reinterpret_cast<const float4*>(xr + i0);
+            const float re[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k;
+              float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
+              right = (lane == 31) ? re[k] : right;                                        // zero beyond the last input column
+              ev[i] = __uint_as_float(raw[0][i]) * corr;
+              od_[i] = (__uint_as_float(raw[1][i]) + right) * corr;
+            }
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride

@@ -295,12 +295,19 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
           const float* xr = has_right_q ? xb + (((q + 1) * 2 + 1) * DIL + (lane >= 32 - DIL ? lane - (32 - DIL) : 0)) * 32 : zeros;
           float out[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), DIL);
-            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), DIL);
-            left = (lane < DIL) ? xl[i] : left;       // column w-DIL (zero at the image edge)
-            right = (lane >= 32 - DIL) ? xr[i] : right;   // column w+DIL
-            out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
+          for (int i0 = 0; i0 < 32; i0 += 4) {        // neighbour values loaded unconditionally, merged with selects (no branches)
+            const float4 l4 = *reinterpret_cast<const float4*>(xl + i0);
+            const float4 r4 = *reinterpret_cast<const float4*>(xr + i0);
+            const float le[4] = {l4.x, l4.y, l4.z, l4.w}, re[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k;
+              float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[0][i]), DIL);
+              float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), DIL);
+              left = (lane < DIL) ? le[k] : left;       // column w-DIL (zero at the image edge)
+              right = (lane >= 32 - DIL) ? re[k] : right;   // column w+DIL
+              out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
+            }
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,

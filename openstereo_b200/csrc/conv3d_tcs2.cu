@@ -282,10 +282,16 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           const float* xl = has_left_q ? xb + ((q - 1) * 2) * 32 : zeros;
           float out[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[1][i]), 1);   // P0 of output column ow-1
-            left = (lane == 0) ? xl[i] : left;                                        // zero at ow = 0 (left padding)
-            out[i] = ((left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i])) * corr;
+          for (int i0 = 0; i0 < 32; i0 += 4) {        // neighbour values loaded unconditionally, merged with selects (no branches)
+            const float4 l4 = *reinterpret_cast<const float4*>(xl + i0);
+            const float le[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k;
+              float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[1][i]), 1);   // P0 of output column ow-1
+              left = (lane == 0) ? le[k] : left;                                        // zero at ow = 0 (left padding)
+              out[i] = ((left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i])) * corr;
+            }
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
