@@ -31,7 +31,8 @@
 // tensor core through fence.proxy.async + mbarrier; arbitrary gathers (stride 2, multi-row tiles) come for free.
 //
 // Warp roles (352 threads, 1 CTA/SM, persistent): warp 0 = MMA issuer (+ TMEM allocator), warps 1-4 = A-row loaders,
-// warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warps 9-10 = weight-slice loaders.
+// warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warp 9 = weight-slice producer (one elected lane issuing
+// 1-D TMA bulk copies of the pre-swizzled slices into two buffer sets), warp 10 idle.
 #include "tc_common.cuh"
 
 namespace osb {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   static_assert(TC_TILES * N3 <= 512, "accumulators exceed TMEM");
   constexpr int A_OFF = 0;
   constexpr int B_OFF = A_OFF + TC_STAGES * TC_ROW_BYTES;      // [3 kh]
-  constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
+  constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + A_OFF;
@@ -76,9 +77,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
   uint64_t* a_empty = a_ready + TC_STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
-  uint64_t* b_full = a_empty + TC_STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
-  uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
-  uint64_t* acc_full = b_empty + 3;                 // [TILES]  MMA -> epilogue, one per accumulator tile
+  uint64_t* b_full = a_empty + TC_STAGES;           // [2][3]   weight producer -> MMA (expect_tx + TMA bytes)
+  uint64_t* b_empty = b_full + TC_BSLOTS * 3;       // [2][3]   MMA -> weight producer (tcgen05.commit)
+  uint64_t* acc_full = b_empty + TC_BSLOTS * 3;     // [TILES]  MMA -> epilogue, one per accumulator tile
   uint64_t* acc_empty = acc_full + TC_TILES;        // [TILES]  epilogue -> MMA       (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_TILES);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       mbar_init(&a_ready[s], 128);
       mbar_init(&a_empty[s], 1);
     }
-    for (int k = 0; k < 3; ++k) {
-      mbar_init(&b_full[k], 64);
+    for (int k = 0; k < TC_BSLOTS * 3; ++k) {
+      mbar_init(&b_full[k], 1);
       mbar_init(&b_empty[k], 1);
     }
     for (int t = 0; t < TC_TILES; ++t) {
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
             for (int r = 0; r < TC_ROWS; ++r) {
               const uint32_t s = rowc % TC_STAGES, par = (rowc / TC_STAGES) & 1;
               mbar_wait(&a_ready[s], par);
-              if (r < 3) mbar_wait(&b_full[r], phc & 1);       // slice kh = r is first needed by row r (tile 0)
+              const uint32_t bslot = (phc & 1) * 3;           // weight buffers alternate between phases
+              if (r < 3) mbar_wait(&b_full[bslot + r], (phc >> 1) & 1);   // slice kh = r is first needed by row r (tile 0)
               tc_fence_after();
               const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
                 }
                 if (t < ntiles) {
                   const uint32_t acc = tmem + t * N3;
-                  const uint64_t db0 = dbase | (uint64_t)(b16 + kh * (B_SLICE / 16));
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + kh) * (B_SLICE / 16));
                   if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
                   }
                   __syncwarp();
                 }
-                if (t == TC_TILES - 1 && elect_one()) mma_commit(&b_empty[kh]);   // row 4+kh: last user of slice kh
+                if (t == TC_TILES - 1 && elect_one()) mma_commit(&b_empty[bslot + kh]);   // row 4+kh: last user of slice kh
               }
               if (elect_one()) {
                 mma_commit(&a_empty[s]);              // ring slot reusable once these MMAs have read it
@@ -387,37 +389,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       }
     }
   }
-  // ---------------------------------------------------------------------------------------------- weight-slice loaders
-  else {
-    const int wt = threadIdx.x - 9 * 32;             // 0..63
-    constexpr int CHUNKS = B_SLICE / 16;             // 768 16-byte chunks per kh slice
-    const uint4* wsrc = reinterpret_cast<const uint4*>(p.w);
-    uint32_t phc = 0;
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const int d = (it / p.hblocks) % p.D;
-      for (int kd = 0; kd < 3; ++kd) {
-        const int din = d + kd - 1;
-        if (din < 0 || din >= p.D) continue;
-        for (int ch = 0; ch < nchunk; ++ch, ++phc) {
-          for (int kh = 0; kh < 3; ++kh) {
-            // global slice (kd, ch, kh): N3 rows x 128 bytes, row-major
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)CHUNKS;
-            uint4 v[CHUNKS / 64];
-#pragma unroll
-            for (int j = 0; j < CHUNKS / 64; ++j) v[j] = __ldg(wsrc + slice + wt + 64 * j);
-            mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);   // last reader (row 4+kh of the previous phase) is done
-#pragma unroll
-            for (int j = 0; j < CHUNKS / 64; ++j) {
-              const int f = wt + 64 * j;              // chunk index inside the slice: row n = f / 8, chunk = f % 8
-              const int n = f >> 3, c = f & 7;
-              *reinterpret_cast<uint4*>(b_buf + kh * B_SLICE + n * 128 + ((c ^ (n & 7)) << 4)) = v[j];
+  // ---------------------------------------------------------------------------------------------- weight-slice producer
+  // One elected lane streams the pre-swizzled (kd, chunk, kh) slices with 1-D TMA bulk copies into the two buffer sets; it runs up
+  // to a whole phase ahead of the MMAs (the other 63 threads of warps 9-10 idle: the slot they used to fill by LDG/STS is gone).
+  else if (warp == 9) {
+    if (elect_one()) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+      uint32_t phc = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const int d = (it / p.hblocks) % p.D;
+        for (int kd = 0; kd < 3; ++kd) {
+          const int din = d + kd - 1;
+          if (din < 0 || din >= p.D) continue;
+          for (int ch = 0; ch < nchunk; ++ch, ++phc) {
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t slot = (phc & 1) * 3 + kh;
+              const size_t slice = ((size_t)kd * nchunk + ch) * 3 + kh;
+              mbar_wait_relaxed(&b_empty[slot], ((phc >> 1) & 1) ^ 1);   // the MMAs that read this buffer two phases ago are done
+              mbar_arrive_expect_tx(&b_full[slot], B_SLICE);
+              bulk_g2s(b_buf + slot * B_SLICE, wsrc + slice * B_SLICE, B_SLICE, &b_full[slot]);
             }
-            fence_proxy_async();
-            mbar_arrive(&b_full[kh]);
           }
         }
       }
     }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -448,7 +444,7 @@ __global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __rest
 template <int COUT>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   constexpr int N3 = 3 * COUT;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_ROW_BYTES + 3 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_ROW_BYTES + TC_BSLOTS * 3 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
                       3 * COUT * 4 + TP_BYTES;
   auto kernel = conv3d_tc_kernel<COUT>;
   static PerDeviceFlag configured;

@@ -41,7 +41,7 @@ struct TcdcCfg {
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
-  static constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
+  static constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
   uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
-  uint64_t* b_full = a_empty + C::STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
-  uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
-  uint64_t* acc_full = b_empty + 3;                 // [TILES]
+  uint64_t* b_full = a_empty + C::STAGES;           // [2][3]   weight producer -> MMA (expect_tx + TMA bytes)
+  uint64_t* b_empty = b_full + TC_BSLOTS * 3;       // [2][3]   MMA -> weight producer (tcgen05.commit)
+  uint64_t* acc_full = b_empty + TC_BSLOTS * 3;                 // [TILES]
   uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
   float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       mbar_init(&a_ready[s], 32);                     // one loader warp fills a unit
       mbar_init(&a_empty[s], 1);
     }
-    for (int k = 0; k < 3; ++k) {
-      mbar_init(&b_full[k], 64);
+    for (int k = 0; k < TC_BSLOTS * 3; ++k) {
+      mbar_init(&b_full[k], 1);
       mbar_init(&b_empty[k], 1);
     }
     for (int t = 0; t < TILES; ++t) {
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               if (!kh_valid(w.ph, kh)) continue;        // warp-uniform
               const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
               mbar_wait(&a_ready[slot], ph);
-              if (t == 0) mbar_wait(&b_full[kh], bph[kh] & 1);   // first use of slice kh in this phase
+              const uint32_t bslot = (bph[kh] & 1) * 3 + kh;   // the buffers of tap kh alternate between its uses
+              if (t == 0) mbar_wait(&b_full[bslot], (bph[kh] >> 1) & 1);   // first use of slice kh in this phase
               tc_fence_after();
               const uint32_t accum = (started >> t) & 1;
               if (!accum) {                             // hand-shake taken for unused tiles too (parity must not alias)
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
                 if (elect_one()) {
                   const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
                   const uint32_t acc = tmem + t * C::N3;
-                  const uint64_t db0 = dbase | (uint64_t)(b16 + (kh * C::B_SLICE) / 16);
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot * C::B_SLICE) / 16);
 #pragma unroll
                   for (int ks = 0; ks < C::KSTEPS; ++ks) {
                     mma_f16(acc, da0 + C::LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               }
               if (elect_one()) {
                 mma_commit(&a_empty[slot]);
-                if (t == TILES - 1) mma_commit(&b_empty[kh]);                    // last user of slice kh in this phase
+                if (t == TILES - 1) mma_commit(&b_empty[bslot]);                 // last user of slice kh in this phase
                 if (last_phase && kh == w.last_kh) mma_commit(&acc_full[t]);     // tile t has received its last tap
               }
               __syncwarp();
@@ -377,38 +378,32 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       }
     }
   }
-  // ---------------------------------------------------------------------------------------------- weight-slice loaders
-  else {
-    const int wt = threadIdx.x - 9 * 32;             // 0..63
-    constexpr int F4 = C::B_SLICE / 16;              // float4 per (kh, hi|lo)
-    constexpr int PER = F4 / 64;                     // per thread
-    constexpr int CPR = C::ROWB / 16;
-    static_assert(F4 % 64 == 0, "weight slice must split evenly over 64 loader threads");
-    uint32_t bph[3] = {0, 0, 0};
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const ItemDc w = decode_dc<C>(p, it);
-      for (int kd = 0; kd < 3; ++kd) {
-        if (!kd_valid(w.od, kd, p.D)) continue;         // same phase enumeration as the MMA warp and the A loaders
-        for (int ch = 0; ch < nchunk; ++ch) {
-          for (int kh = 0; kh < 3; ++kh) {
-            if (!kh_valid(w.ph, kh)) continue;
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)F4;
-            uint4 v[PER];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(p.w) + slice + wt + 64 * j);
-            mbar_wait_relaxed(&b_empty[kh], (bph[kh] & 1) ^ 1);
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-              const int f = wt + 64 * j;
-              *reinterpret_cast<uint4*>(b_buf + kh * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
+  // ---------------------------------------------------------------------------------------------- weight-slice producer
+  // One elected lane streams the pre-swizzled (kd, chunk, kh) slices with 1-D TMA bulk copies into the two buffers of tap kh, up
+  // to a whole use ahead of the MMAs (tc_common.cuh: bulk_g2s).
+  else if (warp == 9) {
+    if (elect_one()) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+      uint32_t bph[3] = {0, 0, 0};
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const ItemDc w = decode_dc<C>(p, it);
+        for (int kd = 0; kd < 3; ++kd) {
+          if (!kd_valid(w.od, kd, p.D)) continue;         // same phase enumeration as the MMA warp and the A loaders
+          for (int ch = 0; ch < nchunk; ++ch) {
+            for (int kh = 0; kh < 3; ++kh) {
+              if (!kh_valid(w.ph, kh)) continue;
+              const uint32_t slot = (bph[kh] & 1) * 3 + kh;
+              const size_t slice = ((size_t)kd * nchunk + ch) * 3 + kh;
+              mbar_wait_relaxed(&b_empty[slot], ((bph[kh] >> 1) & 1) ^ 1);
+              mbar_arrive_expect_tx(&b_full[slot], C::B_SLICE);
+              bulk_g2s(b_buf + slot * C::B_SLICE, wsrc + slice * C::B_SLICE, C::B_SLICE, &b_full[slot]);
+              ++bph[kh];
             }
-            fence_proxy_async();
-            mbar_arrive(&b_full[kh]);
-            ++bph[kh];
           }
         }
       }
     }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -41,7 +41,7 @@ struct Tcs2Cfg {
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
-  static constexpr int BAR_OFF = B_OFF + 3 * B_SLICE;
+  static constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
   uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
-  uint64_t* b_full = a_empty + C::STAGES;           // [3]      weight loaders -> MMA (64 arrivals)
-  uint64_t* b_empty = b_full + 3;                   // [3]      MMA -> weight loaders (tcgen05.commit)
-  uint64_t* acc_full = b_empty + 3;                 // [TILES]
+  uint64_t* b_full = a_empty + C::STAGES;           // [2][3]   weight producer -> MMA (expect_tx + TMA bytes)
+  uint64_t* b_empty = b_full + TC_BSLOTS * 3;       // [2][3]   MMA -> weight producer (tcgen05.commit)
+  uint64_t* acc_full = b_empty + TC_BSLOTS * 3;                 // [TILES]
   uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
   float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       mbar_init(&a_ready[s], 32);                     // one loader warp fills a unit
       mbar_init(&a_empty[s], 1);
     }
-    for (int k = 0; k < 3; ++k) {
-      mbar_init(&b_full[k], 64);
+    for (int k = 0; k < TC_BSLOTS * 3; ++k) {
+      mbar_init(&b_full[k], 1);
       mbar_init(&b_empty[k], 1);
     }
     for (int t = 0; t < TILES; ++t) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               for (int par = 0; par < 2; ++par) {       // par 0: even input columns (kw = 1); par 1: odd columns (kw = 0, 2)
                 const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
                 mbar_wait(&a_ready[slot], ph);
-                if (t == 0 && par == 0) mbar_wait(&b_full[kh], phc & 1);   // first use of slice kh in this phase
+                if (t == 0 && par == 0) mbar_wait(&b_full[(phc & 1) * 3 + kh], (phc >> 1) & 1);   // first use of slice kh in this phase
                 tc_fence_after();
                 const uint32_t accum = (started >> (2 * t + par)) & 1;
                 if (((started >> (2 * t)) & 3u) == 0u) {     // first touch of this tile in this item (unused tiles too)
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
                     const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + slot * C::UNIT_BYTES) & 0x3FFFF) >> 4);
                     // slice rows: [W1 (Cout) | W0 (Cout) | W2 (Cout)]; accumulator columns: [P1 | P0 | P2]
                     const uint32_t acc = tmem + t * C::N3 + (par ? COUT : 0);
-                    const uint64_t db0 = dbase | (uint64_t)(b16 + (kh * C::B_SLICE + (par ? COUT * C::ROWB : 0)) / 16);
+                    const uint64_t db0 = dbase | (uint64_t)(b16 + (((phc & 1) * 3 + kh) * C::B_SLICE + (par ? COUT * C::ROWB : 0)) / 16);
                     const uint32_t idesc = par ? idesc_o : idesc_e;
 #pragma unroll
                     for (int ks = 0; ks < C::KSTEPS; ++ks) {
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
                 }
                 if (elect_one()) {
                   mma_commit(&a_empty[slot]);
-                  if (t == TILES - 1 && par == 1) mma_commit(&b_empty[kh]);        // last user of slice kh in this phase
+                  if (t == TILES - 1 && par == 1) mma_commit(&b_empty[(phc & 1) * 3 + kh]);   // last user of slice kh in this phase
                   if (last_phase && kh == 2 && par == 1) mma_commit(&acc_full[t]); // tile t has received its last tap
                 }
                 __syncwarp();
@@ -336,37 +336,31 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       }
     }
   }
-  // ---------------------------------------------------------------------------------------------- weight-slice loaders
-  else {
-    const int wt = threadIdx.x - 9 * 32;             // 0..63
-    constexpr int F4 = C::B_SLICE / 16;              // float4 per (kh, hi|lo)
-    constexpr int PER = F4 / 64;                     // per thread
-    constexpr int CPR = C::ROWB / 16;
-    static_assert(F4 % 64 == 0, "weight slice must split evenly over 64 loader threads");
-    uint32_t phc = 0;
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const int od = (it / p.hblocks) % (p.D / 2);
-      for (int kd = 0; kd < 3; ++kd) {
-        const int din = 2 * od + kd - 1;              // must enumerate the same phases as the MMA warp and the loaders
-        if (din < 0 || din >= p.D) continue;
-        for (int ch = 0; ch < nchunk; ++ch, ++phc) {
-          for (int kh = 0; kh < 3; ++kh) {
-            const size_t slice = (((size_t)kd * nchunk + ch) * 3 + kh) * (size_t)F4;
-            uint4 v[PER];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(p.w) + slice + wt + 64 * j);
-            mbar_wait_relaxed(&b_empty[kh], (phc & 1) ^ 1);
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-              const int f = wt + 64 * j;
-              *reinterpret_cast<uint4*>(b_buf + kh * C::B_SLICE + swz_offset<KC>(f / CPR, f % CPR)) = v[j];
+  // ---------------------------------------------------------------------------------------------- weight-slice producer
+  // One elected lane streams the pre-swizzled (kd, chunk, kh) slices with 1-D TMA bulk copies into the two buffer sets, up to a
+  // whole phase ahead of the MMAs (tc_common.cuh: bulk_g2s).
+  else if (warp == 9) {
+    if (elect_one()) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
+      uint32_t phc = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const int od = (it / p.hblocks) % (p.D / 2);
+        for (int kd = 0; kd < 3; ++kd) {
+          const int din = 2 * od + kd - 1;              // must enumerate the same phases as the MMA warp and the loaders
+          if (din < 0 || din >= p.D) continue;
+          for (int ch = 0; ch < nchunk; ++ch, ++phc) {
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t slot = (phc & 1) * 3 + kh;
+              const size_t slice = ((size_t)kd * nchunk + ch) * 3 + kh;
+              mbar_wait_relaxed(&b_empty[slot], ((phc >> 1) & 1) ^ 1);
+              mbar_arrive_expect_tx(&b_full[slot], C::B_SLICE);
+              bulk_g2s(b_buf + slot * C::B_SLICE, wsrc + slice * C::B_SLICE, C::B_SLICE, &b_full[slot]);
             }
-            fence_proxy_async();
-            mbar_arrive(&b_full[kh]);
           }
         }
       }
     }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -479,7 +479,7 @@ def f16_split(w):
 
 class TcWeight:
     """A conv weight packed for the tcgen05 kernels: `data` fp16 [3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc hi | kc lo] of
-    w * 2^e_c, and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply.
+    w * 2^e_c with the 16-byte chunks of every row stored in UMMA swizzle order (pack_tc_weight), and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply.
     `cout` is the packed row count per kw slice (narrow heads are zero-padded to 16), `cout_real` the layer's channels."""
     __slots__ = ("data", "inv", "kc", "cout", "cout_real", "_eff")
 
@@ -518,6 +518,16 @@ def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2), pad_cout_to=None):
     both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (half, co, chunk, ci, kd, kh, kw)
     both = both.permute(4, 2, 5, 6, 1, 0, 3)                           # (kd, chunk, kh, kw, co, half, ci)
     data = both.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
+    # Pre-swizzle: the kernels copy a (kd, chunk, kh) slice into shared memory with ONE 1-D TMA bulk copy, so global memory already
+    # holds the UMMA K-major swizzled layout: 16-byte chunk c of row n sits at chunk c ^ (n & 7) (128-byte rows, SWIZZLE_128B) or
+    # c ^ ((n >> 1) & 3) (64-byte rows, SWIZZLE_64B) -- an XOR within the row, i.e. a gather with an involutive index.
+    cpr = (2 * kc) // 8                                                 # 16-byte chunks per row (8 halfs each)
+    rows = torch.arange(3 * cout, device=data.device)
+    key = (rows & 7) if kc == 32 else ((rows >> 1) & 3)
+    src = torch.arange(cpr, device=data.device).view(1, cpr) ^ key.view(-1, 1)              # (rows, cpr): chunk stored at position c
+    data = data.view(3, cin // kc, 3, 3 * cout, cpr, 8)
+    data = torch.gather(data, 4, src.view(1, 1, 1, 3 * cout, cpr, 1).expand(3, cin // kc, 3, 3 * cout, cpr, 8).contiguous())
+    data = data.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
     inv = torch.ldexp(torch.ones_like(amax), -(e + TC_ACT_SCALE_LOG2))
     return TcWeight(data, inv.contiguous(), kc, cout, cout_real)
 

@@ -25,8 +25,15 @@ def test_pack_tc_weight_split(kc, order):
     assert isinstance(p, ops.TcWeight) and p.kc == kc and p.cout == cout
     assert p.data.shape == (3, cin // kc, 3, 3 * cout, 2 * kc) and p.data.is_contiguous() and p.data.dtype == torch.float16
     assert torch.isfinite(p.data.float()).all()
+    # undo the UMMA pre-swizzle (16-byte chunk c of row n is stored at c ^ key(n): an involution), then
     # un-permute: [kd][chunk][kh][kw*cout + co][half*kc + ci] -> (half, co, ci, kd, kh, kw) in the requested kw order
-    t = p.data.double().view(3, cin // kc, 3, 3, cout, 2, kc).permute(5, 4, 1, 6, 0, 2, 3).reshape(2, cout, cin, 3, 3, 3)
+    cpr = 2 * kc // 8
+    rows = torch.arange(3 * cout)
+    key = (rows & 7) if kc == 32 else ((rows >> 1) & 3)
+    src = (torch.arange(cpr).view(1, cpr) ^ key.view(-1, 1)).view(1, 1, 1, 3 * cout, cpr, 1).expand(3, cin // kc, 3, 3 * cout, cpr, 8)
+    lin = torch.gather(p.data.view(3, cin // kc, 3, 3 * cout, cpr, 8), 4, src).reshape(3, cin // kc, 3, 3 * cout, 2 * kc)
+    assert not torch.equal(lin, p.data)                                                       # the swizzle really moved chunks
+    t = lin.double().view(3, cin // kc, 3, 3, cout, 2, kc).permute(5, 4, 1, 6, 0, 2, 3).reshape(2, cout, cin, 3, 3, 3)
     hi, lo = t[0], t[1]
     scale = 2.0 ** -ops.TC_ACT_SCALE_LOG2 / p.inv.double()                                  # 2^e_c
     assert torch.equal(torch.log2(scale), torch.log2(scale).round())                          # exact powers of two

@@ -14,6 +14,8 @@ from tools.kbench import timeit  # noqa: E402
 LAYERS = {  # name: (kind, cin, cout, D, H, W of the INPUT)
     "stem": ("s1", 32, 32, 48, 64, 128), "stem64": ("s1", 64, 32, 48, 64, 128), "stem64n": ("s1n", 64, 32, 48, 64, 128),
     "head": ("s1h", 32, 1, 48, 64, 128),
+    # 2D backbone residual-block convs as one-plane volumes (B = 16 images = 8 pairs): layer2 64->64, layer3 128->128, front 32->32
+    "bb64": ("2d", 64, 64, 1, 64, 128), "bb128": ("2d", 128, 128, 1, 64, 128), "bb32": ("2d", 32, 32, 1, 256, 128),
     "conv2": ("s1", 64, 64, 24, 32, 64), "conv4": ("s1", 128, 128, 12, 16, 32),
     "conv1s2": ("s2", 32, 64, 48, 64, 128), "conv3s2": ("s2", 64, 128, 24, 32, 64),
     "conv5": ("dc", 128, 64, 12, 16, 32), "conv6": ("dc", 64, 32, 24, 32, 64),
@@ -30,7 +32,16 @@ def main():
     x = torch.randn(B, d, h, w, cin, device=dev, generator=g)
     sc, sh = torch.rand(cout, device=dev, generator=g) + 0.5, torch.randn(cout, device=dev, generator=g) * 0.1
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-    if kind == "dc":
+    if kind == "2d":
+        B = 2 * B
+        x = torch.randn(B, h, w, cin, device=dev, generator=g)
+        w5 = torch.zeros(cout, cin, 3, 3, 3, device=dev)
+        w5[:, :, 1] = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * 0.05
+        wp = ops.pack_tc_weight(w5, ops.conv2d_tc_kc(cin, cout, w, 1))
+        res = torch.randn(B, h, w, cout, device=dev, generator=g)
+        fn = lambda: ops.conv2d_k3_tc(x, wp, None, sh, res, ops.ACT_RELU)  # noqa: E731
+        macs = B * h * w * 9 * cin * cout
+    elif kind == "dc":
         wgt = torch.randn(cin, cout, 3, 3, 3, device=dev, generator=g) * 0.05
         wp = ops.pack_tc_deconv_weight(wgt)
         res = torch.randn(B, 2 * d, 2 * h, 2 * w, cout, device=dev, generator=g)
