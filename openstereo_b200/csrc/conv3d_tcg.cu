@@ -50,13 +50,8 @@ struct TcgCfg {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
   static constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
-  static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight producer (11 warps)
-  // A-unit loads in flight per loader warp, staged as raw fp32 by cp.async (0 = through registers, one unit at a time: the
-  // Cout = 128 variants have no shared memory left for the staging ring)
-  static constexpr int RAW = (COUT >= 128) ? 0 : 3;
-  static constexpr int RAW_UNIT = 128 * KC * 4;             // bytes one warp stages per unit = 128 rows x KC fp32
-  static constexpr int RAW_BYTES = 4 * RAW * RAW_UNIT;
-  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * DIL * 32 * 4 + 3 * COUT * 4 + TP_BYTES + RAW_BYTES;
+  static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
+  static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * DIL * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
   static_assert(TILES * N3 <= 512, "accumulators exceed TMEM");
   static_assert(B_SLICE % 1024 == 0 && UNIT_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
@@ -89,7 +84,6 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
   float* s_shift = s_scale + COUT;
   float* zeros = s_shift + COUT;
   float* tpose = zeros + COUT;                      // [4 warps][32][TP_STRIDE] transpose tiles of the epilogue
-  uint8_t* raw_ring = reinterpret_cast<uint8_t*>(tpose) + TP_BYTES;   // [4 loader warps][RAW][RAW_UNIT] cp.async staging of raw fp32 rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
@@ -207,8 +201,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
     float amax = 0.f;
     const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
-    // Register path (RAW == 0): load -> wait -> convert -> store, one unit at a time per warp.
-    auto fill_regs = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
+    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
       // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column)
       float4 v[NLD];
@@ -225,52 +218,6 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
       for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
       mbar_arrive(&a_ready[lw]);
-    };
-    // cp.async path (RAW > 0): up to RAW units of raw fp32 rows in flight per warp.  ncu (profiles/r2_step_ncu_summary.md): with one
-    // unit per warp the loaders delivered 4 units per L2 round trip -- ~520 clk per unit where its 3 MMAs need ~165 -- and the tensor
-    // pipe of the K = 16 kernels sat at 12-30 %.  Each lane later reads back exactly the 16-byte pieces it copied.
-    constexpr int RAWN = C::RAW > 0 ? C::RAW : 1;
-    uint8_t* raw = raw_ring + (size_t)lw * RAWN * C::RAW_UNIT;
-    uint32_t issued = 0, done = 0;
-    uint32_t pend_u[RAWN];
-    auto finish = [&]() {                               // convert the oldest staged unit into its ring slot
-      const uint32_t u = pend_u[done % RAWN];
-      const uint8_t* src = raw + (size_t)(done % RAWN) * C::RAW_UNIT + lane * 16;
-      ++done;
-      const uint32_t ph = (u / C::STAGES) & 1;
-      mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
-#pragma unroll
-      for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, *reinterpret_cast<const float4*>(src + j * 512), amax);
-      fence_proxy_async();
-      mbar_arrive(&a_ready[lw]);
-    };
-    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
-      if constexpr (C::RAW == 0) {
-        fill_regs(base, rstride, cstride, h_first, h_step, u);
-      } else {
-        if (issued - done == (uint32_t)RAWN) {          // staging ring full: retire the oldest unit first
-          cp_async_wait<RAWN - 1>();
-          finish();
-        }
-        uint8_t* dst = raw + (size_t)(issued % RAWN) * C::RAW_UNIT + lane * 16;
-#pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-          const int hin = h_first + h_step * ((VPL * j) / W);
-          const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
-          const bool ok = hin >= 0 && hin < p.H;
-          cp_async16(dst + j * 512, ok ? base + off : p.x, ok);
-        }
-        cp_async_commit();
-        pend_u[issued % RAWN] = u;
-        ++issued;
-      }
-    };
-    auto drain = [&]() {                                // end of the unit stream: retire what is still staged
-      if constexpr (C::RAW > 0) {
-        cp_async_wait<0>();
-        while (done < issued) finish();
-      }
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int hb = it % p.hblocks;
@@ -295,7 +242,6 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
         }
       }
     }
-    drain();
     tc_report_overflow(p.overflow, amax);
   }
   // ---------------------------------------------------------------------------------------------- epilogue
