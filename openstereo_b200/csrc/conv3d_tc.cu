@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   if (warp == 0) {
     {
       const uint32_t idesc = idesc_f16(128, N3);
+      const uint32_t idesc2 = idesc_f16(128, 2 * N3);   // two kh taps of one input row in ONE MMA (see the row loop)
       constexpr uint32_t LO = TcK<TC_KC>::LO_OFF;     // descriptor offset of the lo half of an operand row
       const uint64_t dbase = desc_sw128_base();
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 bytes).
@@ -149,28 +150,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
               if (r < 3) mbar_wait(&b_full[bslot + r], (phc >> 1) & 1);   // slice kh = r is first needed by row r (tile 0)
               tc_fence_after();
               const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
+              // kh-stacked issue.  Input row r feeds tile r-kh through tap kh.  Accumulator tile t lives at TMEM column
+              // (TILES-1-t)*N3, so tiles (t, t-1) are adjacent in that order -- exactly the order of the weight slices (kh, kh+1)
+              // in shared memory: ONE MMA of N = 2*N3 against [slice kh | slice kh+1] adds both taps.  Possible whenever both
+              // tiles have already been started in this item (one accumulate flag per MMA), i.e. in every phase but the first:
+              // 10 instead of 15 MMA groups per phase.  The issuing thread sustains one MMA per ~150 clk (ncu: 40 % of the MMA
+              // warp's samples are issue stalls), the tensor pipe needs 50-100: fewer, wider instructions.
+              bool stacked[3] = {false, false, false};
+              if (r >= 1 && r <= TC_TILES) {
+                const int khp = (r == TC_TILES) ? 1 : 0;            // pair (khp, khp+1) -> tiles (tp, tp-1)
+                const int tp = r - khp;
+                if (((started >> tp) & 1u) && ((started >> (tp - 1)) & 1u) && tp < ntiles) {
+                  const uint32_t acc = tmem + (TC_TILES - 1 - tp) * N3;
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + khp) * (B_SLICE / 16));
+                  if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
+                      mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc2, 1);
+                      mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc2, 1);
+                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc2, 1);
+                    }
+                  }
+                  __syncwarp();
+                  stacked[khp] = stacked[khp + 1] = true;
+                }
+              }
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
                 const int t = r - kh;                 // output row tile fed by input row r through tap kh (compile time)
                 if (t < 0 || t >= TC_TILES) continue;
-                const uint32_t accum = (started >> t) & 1;
-                if (!accum) {                         // first touch of this tile in this item: the previous item's epilogue
-                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);     // must have drained it.  Taken for UNUSED tiles too: otherwise
-                  tc_fence_after();                            // acc_full[t] could complete twice before the epilogue looks
-                  started |= 1u << t;                          // and the mbarrier parity would alias (deadlock).
-                }
-                if (t < ntiles) {
-                  const uint32_t acc = tmem + t * N3;
-                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + kh) * (B_SLICE / 16));
-                  if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
-                      mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
-                      mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc, 1);
-                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
-                    }
+                if (!stacked[kh]) {
+                  const uint32_t accum = (started >> t) & 1;
+                  if (!accum) {                       // first touch of this tile in this item: the previous item's epilogue
+                    mbar_wait(&acc_empty[t], (itc & 1) ^ 1);   // must have drained it.  Taken for UNUSED tiles too: otherwise
+                    tc_fence_after();                          // acc_full[t] could complete twice before the epilogue looks
+                    started |= 1u << t;                        // and the mbarrier parity would alias (deadlock).
                   }
-                  __syncwarp();
+                  if (t < ntiles) {
+                    const uint32_t acc = tmem + (TC_TILES - 1 - t) * N3;
+                    const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + kh) * (B_SLICE / 16));
+                    if (elect_one()) {
+#pragma unroll
+                      for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
+                        mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                        mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc, 1);
+                        mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
+                      }
+                    }
+                    __syncwarp();
+                  }
                 }
                 if (t == TC_TILES - 1 && elect_one()) mma_commit(&b_empty[bslot + kh]);   // row 4+kh: last user of slice kh
               }
@@ -194,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const int vcol = ((vsel & 1) << 2) | ((vsel >> 1) & 3) | (vsel & 8);
     float amax = 0.f;
     const size_t row_stride = (size_t)TC_W * p.Cin;  // floats per image row
-    // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run TWO rows ahead of
+    // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run THREE rows ahead of
     // the stores (software pipeline in registers) so that a full L2/HBM round trip is always in flight.
     struct RowIter {
       int it, kd, ch, r;
@@ -261,19 +289,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     };
     RowIter ld{(int)blockIdx.x, 0, 0, -1};
     if (ld.it < p.items) ld.kd = (((ld.it / p.hblocks) % p.D) == 0) ? 1 : 0;
-    float4 va[8], vb[8];
+    // three rows of loads in flight per thread (ncu, profiles/r2_step_ncu_summary.md: with two, 16 % of the kernel's stall samples
+    // were loader threads waiting for their LDG data -- a row of MMAs lasts ~0.5 us, an L2 / HBM round trip under load more than 1 us)
+    float4 va[8], vb[8], vc[8];
     bool has_a = advance(ld);
     if (has_a) load_row(ld, va);
     bool has_b = has_a && advance(ld);
     if (has_b) load_row(ld, vb);
+    bool has_c = has_b && advance(ld);
+    if (has_c) load_row(ld, vc);
     while (has_a) {
       store_row(va);
-      has_a = has_b && advance(ld);
+      has_a = has_c && advance(ld);
       if (has_a) load_row(ld, va);
       if (!has_b) break;
       store_row(vb);
       has_b = has_a && advance(ld);
       if (has_b) load_row(ld, vb);
+      if (!has_c) break;
+      store_row(vc);
+      has_c = has_b && advance(ld);
+      if (has_c) load_row(ld, vc);
     }
     tc_report_overflow(p.overflow, amax);
   }
@@ -298,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const size_t vox = (((size_t)b * p.D + d) * p.H + h) * TC_W + m;           // NDHWC voxel index
         const size_t plane = (size_t)p.D * p.H * TC_W;                             // NCDHW channel stride
         const size_t ncdhw0 = (size_t)b * p.Cout * plane + ((size_t)d * p.H + h) * TC_W + m;   // p.Cout <= COUT real channels
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * N3;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (TC_TILES - 1 - t) * N3;   // tiles sit in reverse column order
         // all 3*COUT accumulator columns of this voxel in one go: loads back to back, a single wait
         uint32_t raw[3][COUT];
 #pragma unroll

@@ -58,7 +58,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // cross-lane synchronisation beyond cp.async.wait_group is needed).
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t n = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -205,12 +205,12 @@ constexpr int TP_BYTES = 4 * TP_WARP_FLOATS * 4;    // four epilogue warps
 // owned by lane 0; lane k's voxel lies vstride floats further per lane.  sc / sh point at channel c of the folded BN.
 __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const float (&sum)[32], float* y0, const float* res0,
                                                     size_t vstride, const float* sc, const float* sh, int act) {
+  const int c4 = 4 * (lane & 7), sub = lane >> 3;
   __syncwarp();                                     // the previous chunk's readers are done with the tile
   float4* row = reinterpret_cast<float4*>(tbuf + lane * TP_STRIDE);
 #pragma unroll
   for (int i = 0; i < 8; ++i) row[i] = make_float4(sum[4 * i], sum[4 * i + 1], sum[4 * i + 2], sum[4 * i + 3]);
   __syncwarp();
-  const int c4 = 4 * (lane & 7), sub = lane >> 3;
   const float4 a = *reinterpret_cast<const float4*>(sc + c4);
   const float4 b = *reinterpret_cast<const float4*>(sh + c4);
   float4 o[8];
