@@ -30,6 +30,7 @@ class _Packed:
         self.transposed = isinstance(conv, (torch.nn.ConvTranspose3d, torch.nn.ConvTranspose2d))
         self.kernel = int(conv.kernel_size[0])
         self.stride = int(conv.stride[0])
+        self._validate(conv)
         wt = conv.weight
         if wt.dim() == 4:                                       # Conv2d 1x1 (FeatureAtt)
             wt = wt.unsqueeze(2)
@@ -47,6 +48,27 @@ class _Packed:
         if getattr(conv, "bias", None) is not None:
             bias = conv.bias.detach().float()
             self.shift = bias.contiguous() if self.shift is None else (self.shift + bias * self.scale).contiguous()
+
+
+def _packed_validate(self, conv):
+    """The kernels implement exactly the hyper-parameters of the three reference architectures (isotropic k in {1, 3} or the k4
+    transposed conv, stride 1/2, padding k // 2, dilation 1, groups 1).  A module tree that deviates would silently compute a
+    different convolution: refuse it instead."""
+    ks, st = tuple(conv.kernel_size), tuple(conv.stride)
+    ok = len(set(ks)) == 1 and len(set(st)) == 1 and tuple(conv.dilation) == (1,) * len(ks) and conv.groups == 1
+    if self.transposed:
+        op = tuple(conv.output_padding)
+        ok = ok and ((ks[0] == 3 and st[0] == 2 and tuple(conv.padding) == (1,) * len(ks) and op == (1,) * len(ks))
+                     or (ks[0] == 4 and st[0] == 2 and tuple(conv.padding) == (1,) * len(ks) and op == (0,) * len(ks)))
+    else:
+        ok = ok and ks[0] in (1, 3) and st[0] in (1, 2) and tuple(conv.padding) == (ks[0] // 2,) * len(ks)
+        ok = ok and getattr(conv, "padding_mode", "zeros") == "zeros"
+    if not ok:
+        raise NotImplementedError("openstereo_b200: no kernel for %r (supported: Conv k1/k3, stride 1/2, padding k//2, dilation 1, "
+                                  "groups 1; ConvTranspose k3 s2 p1 op1 or k4 s2 p1)" % (conv,))
+
+
+_Packed._validate = _packed_validate
 
 
 def _conv(layer, x, act=ACT_NONE, residual=None, gate=None):

@@ -33,6 +33,8 @@
 // Warp roles (352 threads, 1 CTA/SM, persistent): warp 0 = MMA issuer (+ TMEM allocator), warps 1-4 = A-row loaders,
 // warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warp 9 = weight-slice producer (one elected lane issuing
 // 1-D TMA bulk copies of the pre-swizzled slices into two buffer sets), warp 10 idle.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace osb {
@@ -57,6 +59,7 @@ struct TcParams {
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
+  int stack_kh;      // issue two kh taps per MMA where possible (OSB_TC_STACK, A/B switch)
   int in_ncdhw;      // the INPUT is (B, Cin, D, H, W): the first aggregation layer reads the cost volume as the volume kernel wrote it
   int items, hblocks;
 };
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
               // 10 instead of 15 MMA groups per phase.  The issuing thread sustains one MMA per ~150 clk (ncu: 40 % of the MMA
               // warp's samples are issue stalls), the tensor pipe needs 50-100: fewer, wider instructions.
               bool stacked[3] = {false, false, false};
-              if (r >= 1 && r <= TC_TILES) {
+              if (p.stack_kh && r >= 1 && r <= TC_TILES) {
                 const int khp = (r == TC_TILES) ? 1 : 0;            // pair (khp, khp+1) -> tiles (tp, tp-1)
                 const int tp = r - khp;
                 if (((started >> tp) & 1u) && ((started >> (tp - 1)) & 1u) && tp < ntiles) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const int vcol = ((vsel & 1) << 2) | ((vsel >> 1) & 3) | (vsel & 8);
     float amax = 0.f;
     const size_t row_stride = (size_t)TC_W * p.Cin;  // floats per image row
-    // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run THREE rows ahead of
+    // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run TWO rows ahead of
     // the stores (software pipeline in registers) so that a full L2/HBM round trip is always in flight.
     struct RowIter {
       int it, kd, ch, r;
@@ -289,27 +292,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     };
     RowIter ld{(int)blockIdx.x, 0, 0, -1};
     if (ld.it < p.items) ld.kd = (((ld.it / p.hblocks) % p.D) == 0) ? 1 : 0;
-    // three rows of loads in flight per thread (ncu, profiles/r2_step_ncu_summary.md: with two, 16 % of the kernel's stall samples
-    // were loader threads waiting for their LDG data -- a row of MMAs lasts ~0.5 us, an L2 / HBM round trip under load more than 1 us)
-    float4 va[8], vb[8], vc[8];
+    // two rows of loads in flight per thread.  A third one was measured and rejected (profiles/r2_stem_ab.log: 0.78 -> 0.92 ms for
+    // the 32->32 layer): the extra 32 registers of the loader role cost more than the deeper prefetch gained.
+    float4 va[8], vb[8];
     bool has_a = advance(ld);
     if (has_a) load_row(ld, va);
     bool has_b = has_a && advance(ld);
     if (has_b) load_row(ld, vb);
-    bool has_c = has_b && advance(ld);
-    if (has_c) load_row(ld, vc);
     while (has_a) {
       store_row(va);
-      has_a = has_c && advance(ld);
+      has_a = has_b && advance(ld);
       if (has_a) load_row(ld, va);
       if (!has_b) break;
       store_row(vb);
       has_b = has_a && advance(ld);
       if (has_b) load_row(ld, vb);
-      if (!has_c) break;
-      store_row(vc);
-      has_c = has_b && advance(ld);
-      if (has_c) load_row(ld, vc);
     }
     tc_report_overflow(p.overflow, amax);
   }
@@ -553,6 +550,10 @@ static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const fl
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "conv3d_k3_tc: cannot allocate the overflow flag");
   p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc, p.in_ncdhw = in_ncdhw;
+  {
+    static const int stack = [] { const char* e = getenv("OSB_TC_STACK"); return e ? atoi(e) : 1; }();   // 0: one tap per MMA (A/B)
+    p.stack_kh = stack;
+  }
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");

@@ -117,3 +117,17 @@ def test_host_mirror_state_dict_keys_match_the_oracle_models():
     assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     mine, ref = hm.PSMNet({"MAX_DISP": 192}), omodels.PSMNet(192)
     assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+
+
+def test_packed_layer_refuses_unsupported_hyperparameters():
+    """an engine built from a module tree that deviates from the reference architectures must not silently compute a
+    different convolution (the kernels hard-wire padding k//2, dilation 1, groups 1, the two transposed-conv flavours)."""
+    import torch.nn as nn
+    from openstereo_b200 import aggregation as agg
+    for good in (nn.Conv3d(8, 8, 3, 1, 1, bias=False), nn.Conv3d(8, 8, 3, 2, 1), nn.Conv3d(8, 4, 1), nn.Conv2d(8, 8, 1),
+                 nn.ConvTranspose3d(8, 8, 3, 2, 1, 1, bias=False), nn.ConvTranspose3d(8, 8, 4, 2, 1, bias=False)):
+        agg._Packed(good)
+    for bad in (nn.Conv3d(8, 8, 3, 1, 2, dilation=2), nn.Conv3d(8, 8, 3, 1, 1, groups=2), nn.Conv3d(8, 8, (3, 1, 1), 1, (1, 0, 0)),
+                nn.Conv3d(8, 8, 3, 1, 0), nn.Conv3d(8, 8, 5, 1, 2), nn.ConvTranspose3d(8, 8, 3, 2, 1, 0), nn.ConvTranspose3d(8, 8, 4, 2, 0)):
+        with pytest.raises(NotImplementedError):
+            agg._Packed(bad)
