@@ -474,6 +474,71 @@ __global__ void __launch_bounds__(64) conv1x1_ndhwc_kernel(const float* __restri
   }
 }
 
+// 32 -> 32 specialisation (redir1 at full resolution: 806 MB per launch, the bigger of the two redirs).  ncu on the generic
+// kernel above: l1tex throughput 85 % -- every FMA quadruple needed one broadcast LDS.128 of weights.  Here a lane keeps the weights
+// of FOUR output channels for all 32 inputs in registers (32 float4) and walks the 8 voxels of its sub-row: one LDS.128 of inputs
+// feeds 16 FMAs, and the results leave as coalesced STG.128 without a second transpose.
+__global__ void __launch_bounds__(64) conv1x1_ndhwc_32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ scale, const float* __restrict__ shift,
+                                                               float* __restrict__ y, size_t V, int act) {
+  constexpr int C = 32, TS = C + 4, F4 = C / 4;
+  __shared__ __align__(16) float tile[2][32 * TS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c4 = 4 * (lane & 7), sub = lane >> 3;
+  float4 wr[C];                                     // w[ci][c4 .. c4+3]
+#pragma unroll
+  for (int ci = 0; ci < C; ++ci) wr[ci] = __ldg(reinterpret_cast<const float4*>(w + ci * C + c4));
+  const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + c4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float* tl = tile[warp];
+  const size_t ngroups = (V + 31) / 32;
+  float4 nxt[F4];
+  auto fetch = [&](size_t g) {
+    const size_t v0 = g * 32;
+    const int nv = (int)min((size_t)32, V - v0);
+    const float4* src = reinterpret_cast<const float4*>(x + v0 * C);
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      const int f = lane + 32 * j;
+      nxt[j] = (f / F4 < nv) ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  const size_t g0 = (size_t)blockIdx.x * 2 + warp, gstep = (size_t)gridDim.x * 2;
+  if (g0 < ngroups) fetch(g0);
+  for (size_t g = g0; g < ngroups; g += gstep) {
+    const size_t v0 = g * 32;
+    const int nv = (int)min((size_t)32, V - v0);
+    __syncwarp();                                   // the previous group's readers are done with the tile
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      const int f = lane + 32 * j;
+      *reinterpret_cast<float4*>(tl + (f / F4) * TS + 4 * (f % F4)) = nxt[j];
+    }
+    __syncwarp();
+    if (g + gstep < ngroups) fetch(g + gstep);      // next group's loads fly while this one is multiplied
+    float4* dst = reinterpret_cast<float4*>(y + v0 * C);
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+      const int vox = 4 * j + sub;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < F4; ++i) {
+        const float4 xv = *reinterpret_cast<const float4*>(tl + vox * TS + 4 * i);     // 8-lane broadcast, 4 rows per instruction
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 wv = wr[4 * i + k];
+          acc.x = fmaf(xs[k], wv.x, acc.x), acc.y = fmaf(xs[k], wv.y, acc.y);
+          acc.z = fmaf(xs[k], wv.z, acc.z), acc.w = fmaf(xs[k], wv.w, acc.w);
+        }
+      }
+      acc.x = activate(fmaf(acc.x, sc.x, sh.x), act), acc.y = activate(fmaf(acc.y, sc.y, sh.y), act);
+      acc.z = activate(fmaf(acc.z, sc.z, sh.z), act), acc.w = activate(fmaf(acc.w, sc.w, sh.w), act);
+      if (vox < nv) dst[vox * F4 + (lane & 7)] = acc;                                   // 4 voxels x 128 B per instruction
+    }
+  }
+}
+
 // --------------------------------------------------------------------- channels-last 3x3x3 conv to ONE output channel
 // The classifier head `classif*[2]` = Conv3d(32, 1, 3, 1, 1, bias=False) (gwcnet_disp_processor.py:60-70,
 // psmnet_cost_processor.py:106-124) on a channels-last input: with one output channel there is no GEMM N dimension to
@@ -663,7 +728,7 @@ int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* sc
   const long long groups = (voxels + 31) / 32;
   const unsigned blocks = (unsigned)std::min<long long>((groups + 1) / 2, 148ll * 16);   // 2 warps per CTA, grid-stride over 32-voxel groups
   cudaStream_t s = (cudaStream_t)stream;
-  if (Cin == 32 && Cout == 32) conv1x1_ndhwc_kernel<32, 32><<<blocks, 64, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
+  if (Cin == 32 && Cout == 32) conv1x1_ndhwc_32_kernel<<<blocks, 64, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
   else if (Cin == 64 && Cout == 64) conv1x1_ndhwc_kernel<64, 64><<<blocks, 64, 0, s>>>(x, w_packed, scale, shift, y, (size_t)voxels, act);
   else {
     set_error("conv1x1_ndhwc: unsupported channels %d -> %d (32->32 and 64->64 are instantiated)", Cin, Cout);

@@ -33,8 +33,6 @@
 // Warp roles (352 threads, 1 CTA/SM, persistent): warp 0 = MMA issuer (+ TMEM allocator), warps 1-4 = A-row loaders,
 // warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warp 9 = weight-slice producer (one elected lane issuing
 // 1-D TMA bulk copies of the pre-swizzled slices into two buffer sets), warp 10 idle.
-#include <cstdlib>
-
 #include "tc_common.cuh"
 
 namespace osb {
@@ -59,7 +57,6 @@ struct TcParams {
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
-  int stack_kh;      // issue two kh taps per MMA where possible (OSB_TC_STACK, A/B switch)
   int in_ncdhw;      // the INPUT is (B, Cin, D, H, W): the first aggregation layer reads the cost volume as the volume kernel wrote it
   int items, hblocks;
 };
@@ -128,7 +125,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   if (warp == 0) {
     {
       const uint32_t idesc = idesc_f16(128, N3);
-      const uint32_t idesc2 = idesc_f16(128, 2 * N3);   // two kh taps of one input row in ONE MMA (see the row loop)
       constexpr uint32_t LO = TcK<TC_KC>::LO_OFF;     // descriptor offset of the lo half of an operand row
       const uint64_t dbase = desc_sw128_base();
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 bytes).
@@ -153,55 +149,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
               if (r < 3) mbar_wait(&b_full[bslot + r], (phc >> 1) & 1);   // slice kh = r is first needed by row r (tile 0)
               tc_fence_after();
               const uint64_t da0 = dbase | (uint64_t)((smem_u32(a_buf + s * TC_ROW_BYTES) & 0x3FFFF) >> 4);
-              // kh-stacked issue.  Input row r feeds tile r-kh through tap kh.  Accumulator tile t lives at TMEM column
-              // (TILES-1-t)*N3, so tiles (t, t-1) are adjacent in that order -- exactly the order of the weight slices (kh, kh+1)
-              // in shared memory: ONE MMA of N = 2*N3 against [slice kh | slice kh+1] adds both taps.  Possible whenever both
-              // tiles have already been started in this item (one accumulate flag per MMA), i.e. in every phase but the first:
-              // 10 instead of 15 MMA groups per phase.  The issuing thread sustains one MMA per ~150 clk (ncu: 40 % of the MMA
-              // warp's samples are issue stalls), the tensor pipe needs 50-100: fewer, wider instructions.
-              bool stacked[3] = {false, false, false};
-              if (p.stack_kh && r >= 1 && r <= TC_TILES) {
-                const int khp = (r == TC_TILES) ? 1 : 0;            // pair (khp, khp+1) -> tiles (tp, tp-1)
-                const int tp = r - khp;
-                if (((started >> tp) & 1u) && ((started >> (tp - 1)) & 1u) && tp < ntiles) {
-                  const uint32_t acc = tmem + (TC_TILES - 1 - tp) * N3;
-                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + khp) * (B_SLICE / 16));
-                  if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
-                      mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc2, 1);
-                      mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc2, 1);
-                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc2, 1);
-                    }
-                  }
-                  __syncwarp();
-                  stacked[khp] = stacked[khp + 1] = true;
-                }
-              }
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
                 const int t = r - kh;                 // output row tile fed by input row r through tap kh (compile time)
                 if (t < 0 || t >= TC_TILES) continue;
-                if (!stacked[kh]) {
-                  const uint32_t accum = (started >> t) & 1;
-                  if (!accum) {                       // first touch of this tile in this item: the previous item's epilogue
-                    mbar_wait(&acc_empty[t], (itc & 1) ^ 1);   // must have drained it.  Taken for UNUSED tiles too: otherwise
-                    tc_fence_after();                          // acc_full[t] could complete twice before the epilogue looks
-                    started |= 1u << t;                        // and the mbarrier parity would alias (deadlock).
-                  }
-                  if (t < ntiles) {
-                    const uint32_t acc = tmem + (TC_TILES - 1 - t) * N3;
-                    const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + kh) * (B_SLICE / 16));
-                    if (elect_one()) {
+                const uint32_t accum = (started >> t) & 1;
+                if (!accum) {                         // first touch of this tile in this item: the previous item's epilogue
+                  mbar_wait(&acc_empty[t], (itc & 1) ^ 1);     // must have drained it.  Taken for UNUSED tiles too: otherwise
+                  tc_fence_after();                            // acc_full[t] could complete twice before the epilogue looks
+                  started |= 1u << t;                          // and the mbarrier parity would alias (deadlock).
+                }
+                if (t < ntiles) {
+                  const uint32_t acc = tmem + t * N3;
+                  const uint64_t db0 = dbase | (uint64_t)(b16 + (bslot + kh) * (B_SLICE / 16));
+                  if (elect_one()) {
 #pragma unroll
-                      for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
-                        mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
-                        mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc, 1);
-                        mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
-                      }
+                    for (int ks = 0; ks < TcK<TC_KC>::KSTEPS; ++ks) {
+                      mma_f16(acc, da0 + LO + 2 * ks, db0 + 2 * ks, idesc, ks > 0 ? 1u : accum);   // small terms first
+                      mma_f16(acc, da0 + 2 * ks, db0 + LO + 2 * ks, idesc, 1);
+                      mma_f16(acc, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
                     }
-                    __syncwarp();
                   }
+                  __syncwarp();
                 }
                 if (t == TC_TILES - 1 && elect_one()) mma_commit(&b_empty[bslot + kh]);   // row 4+kh: last user of slice kh
               }
@@ -292,8 +261,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     };
     RowIter ld{(int)blockIdx.x, 0, 0, -1};
     if (ld.it < p.items) ld.kd = (((ld.it / p.hblocks) % p.D) == 0) ? 1 : 0;
-    // two rows of loads in flight per thread.  A third one was measured and rejected (profiles/r2_stem_ab.log: 0.78 -> 0.92 ms for
-    // the 32->32 layer): the extra 32 registers of the loader role cost more than the deeper prefetch gained.
     float4 va[8], vb[8];
     bool has_a = advance(ld);
     if (has_a) load_row(ld, va);
@@ -331,7 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const size_t vox = (((size_t)b * p.D + d) * p.H + h) * TC_W + m;           // NDHWC voxel index
         const size_t plane = (size_t)p.D * p.H * TC_W;                             // NCDHW channel stride
         const size_t ncdhw0 = (size_t)b * p.Cout * plane + ((size_t)d * p.H + h) * TC_W + m;   // p.Cout <= COUT real channels
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (TC_TILES - 1 - t) * N3;   // tiles sit in reverse column order
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * N3;
         // all 3*COUT accumulator columns of this voxel in one go: loads back to back, a single wait
         uint32_t raw[3][COUT];
 #pragma unroll
@@ -550,10 +517,6 @@ static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const fl
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "conv3d_k3_tc: cannot allocate the overflow flag");
   p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc, p.in_ncdhw = in_ncdhw;
-  {
-    static const int stack = [] { const char* e = getenv("OSB_TC_STACK"); return e ? atoi(e) : 1; }();   // 0: one tap per MMA (A/B)
-    p.stack_kh = stack;
-  }
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");
