@@ -33,6 +33,8 @@
 // Warp roles (352 threads, 1 CTA/SM, persistent): warp 0 = MMA issuer (+ TMEM allocator), warps 1-4 = A-row loaders,
 // warps 5-8 = epilogue (TMEM -> registers -> BN/residual/ReLU -> global), warp 9 = weight-slice producer (one elected lane issuing
 // 1-D TMA bulk copies of the pre-swizzled slices into two buffer sets), warp 10 idle.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace osb {
@@ -41,7 +43,8 @@ constexpr int TC_W = 128;          // image width handled (UMMA M)
 constexpr int TC_KC = 32;          // input channels per phase: 128-byte K-major rows [32 hi | 32 lo] fp16, SWIZZLE_128B
 constexpr int TC_TILES = 5;        // output rows (accumulator tiles) per work item
 constexpr int TC_ROWS = TC_TILES + 2;
-constexpr int TC_STAGES = 6;       // A-row ring depth
+constexpr int TC_STAGES = 4;       // A-row ring depth (converted fp16 hi|lo tiles)
+constexpr int TC_RAW = 4;          // raw fp32 rows staged by 1-D TMA bulk copies ahead of the converters (Cin = 32 channels-last layers)
 constexpr int TC_ROW_BYTES = TC_W * TC_KC * 4;     // 16384: one staged input row (hi and lo halves of every voxel)
 constexpr int TC_THREADS = 352;
 
@@ -57,6 +60,8 @@ struct TcParams {
   float kappa;       // expected round-towards-zero loss per accumulating MMA (tc_common.cuh)
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
+  int bulk_rows;     // input rows staged by TMA bulk copies, TC_RAW deep: Cin == 32 channels-last (one 16 KB copy per row) or NCDHW
+                     // (32 copies of 512 bytes, one per channel plane)
   int in_ncdhw;      // the INPUT is (B, Cin, D, H, W): the first aggregation layer reads the cost volume as the volume kernel wrote it
   int items, hblocks;
 };
@@ -69,11 +74,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   static_assert(TC_TILES * N3 <= 512, "accumulators exceed TMEM");
   constexpr int A_OFF = 0;
   constexpr int B_OFF = A_OFF + TC_STAGES * TC_ROW_BYTES;      // [3 kh]
-  constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
+  constexpr int RAW_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;    // [TC_RAW] raw fp32 input rows
+  constexpr int BAR_OFF = RAW_OFF + TC_RAW * TC_ROW_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + A_OFF;
   uint8_t* b_buf = smem + B_OFF;
+  uint8_t* raw_buf = smem + RAW_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (128 arrivals)
   uint64_t* a_empty = a_ready + TC_STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
@@ -81,7 +88,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   uint64_t* b_empty = b_full + TC_BSLOTS * 3;       // [2][3]   MMA -> weight producer (tcgen05.commit)
   uint64_t* acc_full = b_empty + TC_BSLOTS * 3;     // [TILES]  MMA -> epilogue, one per accumulator tile
   uint64_t* acc_empty = acc_full + TC_TILES;        // [TILES]  epilogue -> MMA       (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_TILES);
+  uint64_t* raw_full = acc_empty + TC_TILES;        // [RAW]    row producer -> converters (expect_tx + TMA bytes, or a plain arrive)
+  uint64_t* raw_empty = raw_full + TC_RAW;          // [RAW]    converters -> row producer (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + TC_RAW);
   float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned
   //   // [2 tile parities][4 warps][2][COUT] boundary exchange
   float* s_scale = xchg + 2 * 4 * 2 * COUT;                // [COUT]
@@ -105,6 +114,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       mbar_init(&acc_full[t], 1);
       mbar_init(&acc_empty[t], 128);
     }
+    for (int k = 0; k < TC_RAW; ++k) {
+      mbar_init(&raw_full[k], 1);
+      mbar_init(&raw_empty[k], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -119,6 +132,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run TWO rows ahead of
+  // the stores (software pipeline in registers) so that a full L2/HBM round trip is always in flight.
+  struct RowIter {
+    int it, kd, ch, r;
+  };
+  auto advance = [&](RowIter& s) {                  // -> false when the sequence is exhausted
+    for (;;) {
+      if (s.it >= p.items) return false;
+      if (++s.r < TC_ROWS) return true;
+      s.r = -1;
+      if (++s.ch < nchunk) continue;
+      s.ch = 0;
+      const int d = (s.it / p.hblocks) % p.D;
+      for (++s.kd; s.kd < 3; ++s.kd) {
+        const int din = d + s.kd - 1;
+        if (din >= 0 && din < p.D) break;
+      }
+      if (s.kd < 3) continue;
+      s.it += gridDim.x;
+      if (s.it >= p.items) return false;
+      const int d2 = (s.it / p.hblocks) % p.D;
+      s.kd = (d2 == 0) ? 1 : 0;                     // first input plane that exists
+    }
+  };
   const uint32_t tmem = *tmem_slot;
 
   // ---------------------------------------------------------------------------------------------- MMA issuer
@@ -194,30 +231,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const int vcol = ((vsel & 1) << 2) | ((vsel >> 1) & 3) | (vsel & 8);
     float amax = 0.f;
     const size_t row_stride = (size_t)TC_W * p.Cin;  // floats per image row
-    // The rows a CTA stages form one flat sequence (item, kd, chunk, r).  `RowIter` walks it; loads run TWO rows ahead of
-    // the stores (software pipeline in registers) so that a full L2/HBM round trip is always in flight.
-    struct RowIter {
-      int it, kd, ch, r;
-    };
-    auto advance = [&](RowIter& s) {                  // -> false when the sequence is exhausted
-      for (;;) {
-        if (s.it >= p.items) return false;
-        if (++s.r < TC_ROWS) return true;
-        s.r = -1;
-        if (++s.ch < nchunk) continue;
-        s.ch = 0;
-        const int d = (s.it / p.hblocks) % p.D;
-        for (++s.kd; s.kd < 3; ++s.kd) {
-          const int din = d + s.kd - 1;
-          if (din >= 0 && din < p.D) break;
-        }
-        if (s.kd < 3) continue;
-        s.it += gridDim.x;
-        if (s.it >= p.items) return false;
-        const int d2 = (s.it / p.hblocks) % p.D;
-        s.kd = (d2 == 0) ? 1 : 0;                     // first input plane that exists
-      }
-    };
     auto load_row = [&](const RowIter& s, float4 (&v)[8]) {
       const int hb = s.it % p.hblocks;
       const int d = (s.it / p.hblocks) % p.D;
@@ -261,8 +274,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     };
     RowIter ld{(int)blockIdx.x, 0, 0, -1};
     if (ld.it < p.items) ld.kd = (((ld.it / p.hblocks) % p.D) == 0) ? 1 : 0;
+    if (p.bulk_rows) {
+      // The row producer (warp 10) keeps TC_RAW rows of raw fp32 in flight with 16 KB TMA bulk copies; these four warps only
+      // convert: LDS.128 (a warp reads 512 contiguous bytes) -> fp16 hi|lo -> swizzled STS.64.  No load latency on this path.
+      uint32_t rawc = 0;
+      while (advance(ld)) {
+        const int hb = ld.it % p.hblocks;
+        const int hin = hb * TC_TILES - 1 + ld.r;
+        const uint32_t slot = rawc % TC_RAW, par = (rawc / TC_RAW) & 1;
+        mbar_wait_relaxed(&raw_full[slot], par);
+        float4 v[8];
+        if (hin >= 0 && hin < p.H && p.in_ncdhw) {    // raw slot = [32 channels][128 columns]: this thread's column, 8 channel quads
+          const float* src = reinterpret_cast<const float*>(raw_buf + slot * TC_ROW_BYTES) + lt;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* q = src + 4 * (j ^ ((lt >> 3) & 1)) * TC_W;
+            v[j] = make_float4(q[0], q[TC_W], q[2 * TC_W], q[3 * TC_W]);
+          }
+        } else if (hin >= 0 && hin < p.H) {
+          const float* src = reinterpret_cast<const float*>(raw_buf + slot * TC_ROW_BYTES) + c16 * 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + (vcol + 16 * j) * TC_KC);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        store_row(v);                                 // consumes v: the reads of the raw slot are complete behind it
+        mbar_arrive(&raw_empty[slot]);
+        ++rawc;
+      }
+      tc_report_overflow(p.overflow, amax);
+      amax = 0.f;
+    }
     float4 va[8], vb[8];
-    bool has_a = advance(ld);
+    bool has_a = !p.bulk_rows && advance(ld);
     if (has_a) load_row(ld, va);
     bool has_b = has_a && advance(ld);
     if (has_b) load_row(ld, vb);
@@ -415,6 +460,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     }
     __syncwarp();
   }
+  // ---------------------------------------------------------------------------------------------- raw-row producer
+  else if (warp == 10 && p.bulk_rows) {
+    if (elect_one()) {
+      RowIter ld{(int)blockIdx.x, 0, 0, -1};
+      if (ld.it < p.items) ld.kd = (((ld.it / p.hblocks) % p.D) == 0) ? 1 : 0;
+      uint32_t rawc = 0;
+      while (advance(ld)) {
+        const int hb = ld.it % p.hblocks;
+        const int d = (ld.it / p.hblocks) % p.D;
+        const int b = ld.it / (p.hblocks * p.D);
+        const int hin = hb * TC_TILES - 1 + ld.r, din = d + ld.kd - 1;
+        const uint32_t slot = rawc % TC_RAW, par = (rawc / TC_RAW) & 1;
+        mbar_wait_relaxed(&raw_empty[slot], par ^ 1);
+        if (hin >= 0 && hin < p.H && p.in_ncdhw) {      // NCDHW: 32 channel planes, each contributes one 512-byte image row
+          const size_t plane = (size_t)p.D * p.H * TC_W;
+          const float* src = p.x + (((size_t)b * p.Cin + ld.ch * TC_KC) * p.D + din) * p.H * TC_W + (size_t)hin * TC_W;
+          mbar_arrive_expect_tx(&raw_full[slot], TC_ROW_BYTES);
+          for (int c = 0; c < TC_KC; ++c)
+            bulk_g2s(raw_buf + slot * TC_ROW_BYTES + c * (TC_W * 4), src + c * plane, TC_W * 4, &raw_full[slot]);
+        } else if (hin >= 0 && hin < p.H) {             // one image row = 128 voxels x 32 channels x 4 B, contiguous
+          const float* src = p.x + (((size_t)b * p.D + din) * p.H + hin) * (size_t)(TC_W * TC_KC);
+          mbar_arrive_expect_tx(&raw_full[slot], TC_ROW_BYTES);
+          bulk_g2s(raw_buf + slot * TC_ROW_BYTES, src, TC_ROW_BYTES, &raw_full[slot]);
+        } else {
+          mbar_arrive(&raw_full[slot]);                 // zero-padding row: nothing to copy, the converters write zeros
+        }
+        ++rawc;
+      }
+    }
+    __syncwarp();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -444,7 +520,7 @@ __global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __rest
 template <int COUT>
 static int launch_tc(const TcParams& p, cudaStream_t stream) {
   constexpr int N3 = 3 * COUT;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_ROW_BYTES + TC_BSLOTS * 3 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
+  const size_t smem = 1024 + (size_t)(TC_STAGES + TC_RAW) * TC_ROW_BYTES + TC_BSLOTS * 3 * (size_t)(N3 * TC_KC * 4) + 512 + 2 * 4 * 2 * COUT * 4 +
                       3 * COUT * 4 + TP_BYTES;
   auto kernel = conv3d_tc_kernel<COUT>;
   static PerDeviceFlag configured;
@@ -517,6 +593,10 @@ static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const fl
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "conv3d_k3_tc: cannot allocate the overflow flag");
   p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc, p.in_ncdhw = in_ncdhw;
+  {
+    static const int bulk = [] { const char* e = getenv("OSB_TC_BULK"); return e ? atoi(e) : 1; }();   // 0: register-staged rows (A/B)
+    p.bulk_rows = (bulk && (in_ncdhw || Cin == TC_KC)) ? 1 : 0;   // channels-last Cin = 64 rows are strided: register path
+  }
   p.hblocks = (H + TC_TILES - 1) / TC_TILES;
   const long long items = (long long)B * D * p.hblocks;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_k3_tc: too many work items");
