@@ -35,7 +35,8 @@ struct Tcs2Cfg {
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = 3 * COUT;
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
-  static constexpr int STAGES = 4;                          // one loader warp per ring slot
+  static constexpr int STAGES = 5;                          // one loader warp per ring slot: warps 1-4 and 10 (the former second
+                                                            // weight-loader warp, idle since the slices come by TMA)
   static constexpr int HBLK = TILES * R;                    // output rows per work item
   static constexpr int KSTEPS = KC / 16;                    // K = 16 fp16 channels per MMA
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   // (profiles/r1_ncu_summary.md, r1_tcdc_conv6): with all four warps on one unit at a time the loaders sat on the load
   // latency and the tensor pipe was 17 % busy.  The (tile, tap) loops are runtime loops: one copy of the body (unrolled
   // bodies took the kernel to 254 KB of code).
-  else if (warp < 5) {
-    const int lw = warp - 1;
+  else if (warp < 5 || warp == 10) {
+    const int lw = warp < 5 ? warp - 1 : 4;
     static_assert(KC == 16, "lane_voxel / unit-row mapping below is written for 64-byte operand rows");
     constexpr int CPR = KC / 4;                      // fp32 16-byte chunks per voxel of the K chunk
     constexpr int VPL = 32 / CPR;                    // voxels covered by one warp-wide LDG.128
