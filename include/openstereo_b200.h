@@ -154,8 +154,13 @@ int osb_conv3d_1x1_bn_act_fwd(const float* x0, const float* x1, int Cin0, const 
  * `scale` (REQUIRED here, Cout floats) must already contain the exact inverse 2^-(e_c + 4) times the folded-BN scale
  * (TcWeight.eff_scale).  y and residual are fp32, NCDHW or NDHWC according to out_ndhwc / res_ndhwc. */
 int osb_conv3d_tc_supported(int Cin, int Cout, int W, int stride);
+/* General widths: every W >= OSB_TC_MIN_WIDTH that has no whole-row variant is served by 128-column tiles of one image row with a
+ * one-column halo (conv3d_tcg.cu / conv3d_tcs2.cu / conv3d_tcdc.cu, GW instantiations): 240 (the reference's 544x960 timing shape,
+ * tools/measure.py:32), 312 (KITTI), 160 (IGEV) ... -- stride 1: Cout 32|64|128; stride 2: Cout 64|128; transposed: Cout 32|64. */
+#define OSB_TC_MIN_WIDTH 24
+int osb_tc_general_width(int W);
 /* K chunk (16 or 32 input channels per operand tile) the weight tensor must be packed with; 0 = unsupported shape.
- * Variants: W=128/Cout=32 (kc 32); W=64/Cout=64, W=32/Cout=64|128 (kc 16, M tile = 128/W image rows). */
+ * Variants: W=128/Cout=32 (kc 32); W=64/Cout=64, W=32/Cout=64|128 (kc 16, M tile = 128/W image rows); general widths (kc 16). */
 int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
 int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "osb_conv3d_1x1_bn_act_fwd": [_f32p, _f32p, _i] + [_f32p] * 6 + [_i] * 8 + [_s],
     "osb_conv3d_tc_supported": [_i, _i, _i, _i],
     "osb_conv3d_tc_kc": [_i, _i, _i, _i],
+    "osb_tc_general_width": [_i],
     "osb_conv3d_s2_tc_supported": [_i, _i, _i, _i, _i],
     "osb_deconv3d_tc_supported": [_i, _i, _i],
     "osb_deconv3d_k3_tc_fwd": [_f32p] * 6 + [_i] * 9 + [_s],

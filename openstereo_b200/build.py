@@ -46,7 +46,7 @@ def _fingerprint():
     for path in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
             os.path.join(ROOT, "include", "openstereo_b200.h"), os.path.abspath(__file__)]:
         with open(path, "rb") as f:
-            h.update(path.encode() + b"\0" + f.read())
+            h.update(os.path.relpath(path, ROOT).encode() + b"\0" + f.read())   # relative: the stamp survives a move of the tree
     return h.hexdigest()
 
 

@@ -548,6 +548,10 @@ int launch_tcg_dilated2(const float* x, const void* w, const float* scale, const
 
 extern "C" {
 
+// Widths served by the general-width (column-tile) instantiations of conv3d_tcg.cu / conv3d_tcs2.cu / conv3d_tcdc.cu: any row of
+// at least OSB_TC_MIN_WIDTH voxels (below that a 128-column tile is mostly padding and the fp32 CUDA-core kernels win).
+int osb_tc_general_width(int W) { return W >= OSB_TC_MIN_WIDTH ? 1 : 0; }
+
 // K-chunk (input channels per operand tile) of the kernel variant that serves a shape; 0 = no tensor-core variant.
 int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (stride != 1) return 0;
@@ -556,6 +560,8 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (Cin % 16 == 0 && Cin >= 16 &&
       ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 128)) || (W == osb::TC_W && (Cout == 64 || Cout == 128))))
     return 16;                                                                                  // conv3d_tcg.cu
+  if (Cin % 16 == 0 && Cin >= 16 && osb_tc_general_width(W) && (Cout == 32 || Cout == 64 || Cout == 128))
+    return 16;                                                                                  // conv3d_tcg.cu, column tiles
   return 0;
 }
 

@@ -9,6 +9,9 @@
 //   E[m] = A[m].W1 -> output column 2m,      P2[m] = A[m].W2 and P0[m] = A[m].W0 -> output column 2m+1 = P2[m] + P0[m+1];
 // the epilogue does that single right shift (zero at m = Win-1: the column beyond the input) and writes both columns.
 // Tap pairs per tile: 1, 2, 2 or 4 depending on (od&1, ph); work items interleave the classes so every CTA gets a mix.
+// GENERAL WIDTHS (GW = true, W = 128 instantiations; see conv3d_tcg.cu): an M tile is a 128-column segment of one INPUT row of
+// runtime width Wr starting at input column ct * 127; tile column 127 is the halo that provides P0[m+1] (zero beyond the image) and
+// its two output columns are not stored.
 #include "tc_common.cuh"
 
 namespace osb {
@@ -26,10 +29,14 @@ struct TcdcParams {
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
+  int Wr, ctiles;          // general-width instantiations: INPUT width and column tiles per row (whole-row kernels: W, 1)
 };
 
-template <int COUT, int KC, int W, int TILES>     // W = INPUT width
+template <int COUT, int KC, int W, int TILES, bool GW = false>     // W = INPUT width
 struct TcdcCfg {
+  static_assert(!GW || W == 128, "general-width tiles are 128-column segments of one input row");
+  static constexpr int HALO = GW ? 1 : 0;                   // halo columns on the RIGHT of a column tile
+  static constexpr int CSTEP = 128 - HALO;                  // input columns a column tile produces outputs for
   static constexpr int R = 128 / W;                         // input rows (= output rows of one parity) per M tile
   static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row: [KC fp16 hi | KC fp16 lo]
   static constexpr int UNIT_BYTES = 128 * ROWB;
@@ -54,11 +61,16 @@ struct TcdcCfg {
 // work item = (image b, output plane od, row parity ph, block of TILES*R input rows); parity bits vary fastest so that the
 // 1/2/2/4-tap classes are interleaved over the persistent CTAs
 struct ItemDc {
-  int b, od, ph, j0, last_kd, last_kh;
+  int b, od, ph, j0, last_kd, last_kh, ct;
 };
 template <class C>
 __device__ __forceinline__ ItemDc decode_dc(const TcdcParams& p, int it) {
   ItemDc w;
+  w.ct = 0;
+  if (C::HALO) {                                    // general widths: the column tile varies fastest
+    w.ct = it % p.ctiles;
+    it /= p.ctiles;
+  }
   w.ph = it & 1;
   it >>= 1;
   const int Do = 2 * p.D;
@@ -77,9 +89,9 @@ __device__ __forceinline__ bool kd_valid(int od, int kd, int D) {
 }
 __device__ __forceinline__ bool kh_valid(int ph, int kh) { return ((ph + 1 - kh) & 1) == 0; }
 
-template <int COUT, int KC, int W, int TILES>
-__global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3d_tcdc_kernel(const TcdcParams p) {
-  using C = TcdcCfg<COUT, KC, W, TILES>;
+template <int COUT, int KC, int W, int TILES, bool GW = false>
+__global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) conv3d_tcdc_kernel(const TcdcParams p) {
+  using C = TcdcCfg<COUT, KC, W, TILES, GW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + C::A_OFF;
@@ -100,6 +112,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
+  const int Wp = GW ? p.Wr : W;                     // INPUT width (the output is 2 * Wp wide)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -206,15 +219,18 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     float amax = 0.f;
     const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
-    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
+    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
-      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column)
+      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
+      // General widths: col0 = INPUT column of load 0 (columns >= Wp are zero: beyond the image).
       float4 v[NLD];
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int hin = h_first + h_step * ((VPL * j) / W);
         const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
-        v[j] = (hin >= 0 && hin < p.H) ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok = hin >= 0 && hin < p.H;
+        if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
+        v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
@@ -229,7 +245,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       for (int kd = 0; kd < 3; ++kd) {
         if (!kd_valid(w.od, kd, p.D)) continue;
         const int id = (w.od + 1 - kd) >> 1;         // input plane feeding output plane od through tap kd
-        const float* plane = p.x + ((size_t)w.b * p.D + id) * p.H * (size_t)W * p.Cin;
+        const float* plane = p.x + ((size_t)w.b * p.D + id) * p.H * (size_t)Wp * p.Cin;
+        const int col0 = w.ct * C::CSTEP + v0;       // INPUT column of this lane's first load (whole-row kernels: v0)
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
           for (int t = 0; t < TILES; ++t) {
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
               if (mine && unitc % C::STAGES == (uint32_t)lw) {
                 // operand row v = input voxel (row j0 + t*R + v / W (+1 for tap kh = 0), column v % W)
                 const int h_first = w.j0 + t * C::R + (kh == 0 ? 1 : 0);
-                const float* base = plane + ((size_t)h_first * W + v0) * p.Cin + ch * KC + c * 4;
-                fill(base, (size_t)W * p.Cin, (size_t)p.Cin, h_first, 1, unitc);
+                const float* base = plane + ((size_t)h_first * Wp + col0) * p.Cin + ch * KC + c * 4;
+                fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h_first, 1, unitc, col0);
               }
               ++unitc;
             }
@@ -257,19 +274,23 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     const int rr = m / W, wcol = m % W;              // input row inside the tile, input column
     const bool has_right_q = (((q + 1) * 32) % W) != 0;   // the next quadrant continues the same image row
     const int Do = 2 * p.D, Ho = 2 * p.H;
-    constexpr int Wo = 2 * W;
+    const int Wo = 2 * Wp;
     uint32_t itc = 0, exc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
       const ItemDc w = decode_dc<C>(p, it);
       const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
       // tap pairs of this parity class: (1 or 2 kd) x (1 or 2 kh); each adds chunks x k-steps x 3 MMAs (tc_common.cuh: rz_kappa)
       const float corr = 1.f + p.kappa * (float)(((w.od & 1) + 1) * (w.ph + 1) * nchunk * C::KSTEPS * 3);
+      // general widths: input column of this thread's tile column; the halo column and columns beyond the image are not stored
+      const int col = GW ? w.ct * C::CSTEP + m : wcol;
+      const bool cvalid = !GW || (m < C::CSTEP && col < Wp);
+      const uint32_t vmask = GW ? __ballot_sync(0xffffffffu, cvalid) : 0xffffffffu;
       for (int t = 0; t < ntiles; ++t) {
         const int j = w.j0 + t * C::R + rr;
         const bool live = j < p.H;
         const int oh = 2 * j + w.ph;
-        const size_t vox = (((size_t)w.b * Do + w.od) * Ho + oh) * Wo + 2 * wcol;      // NDHWC index of the EVEN output voxel
-        if (live && p.residual && p.res_ndhwc) {
+        const size_t vox = (((size_t)w.b * Do + w.od) * Ho + oh) * Wo + 2 * col;       // NDHWC index of the EVEN output voxel
+        if (live && cvalid && p.residual && p.res_ndhwc) {
           // the residual streams from HBM: start pulling this thread's two voxels (2*COUT floats, contiguous) into L2 while
           // the tile is still being accumulated, so the loads after the transpose do not expose the DRAM latency per tile
           const float* rp = p.residual + vox * COUT;
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
         mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
         const size_t plane = (size_t)Do * Ho * Wo;                                   // NCDHW channel stride
-        const size_t ncdhw0 = (size_t)w.b * COUT * plane + ((size_t)w.od * Ho + oh) * Wo + 2 * wcol;
+        const size_t ncdhw0 = (size_t)w.b * COUT * plane + ((size_t)w.od * Ho + oh) * Wo + 2 * col;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
 #pragma unroll 1
         for (int cg = 0; cg < COUT; cg += 32) {
@@ -320,10 +341,10 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
             // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride
             float* y0 = p.y + (vox - 2 * lane) * COUT + cg;
             const float* r0 = p.residual ? p.residual + (vox - 2 * lane) * COUT + cg : nullptr;
-            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, ev, y0, r0, 2 * COUT, s_scale + cg, s_shift + cg, p.act);
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, ev, y0, r0, 2 * COUT, s_scale + cg, s_shift + cg, p.act, vmask);
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, od_, y0 + COUT, r0 ? r0 + COUT : nullptr, 2 * COUT, s_scale + cg,
-                                s_shift + cg, p.act);
-          } else if (live) {
+                                s_shift + cg, p.act, vmask);
+          } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               ev[i] = fmaf(ev[i], s_scale[cg + i], s_shift[cg + i]);
@@ -411,10 +432,10 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES>
+template <int COUT, int KC, int W, int TILES, bool GW = false>
 static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
-  using C = TcdcCfg<COUT, KC, W, TILES>;
-  auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES>;
+  using C = TcdcCfg<COUT, KC, W, TILES, GW>;
+  auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES, GW>;
   static PerDeviceFlag configured;
   if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -425,7 +446,9 @@ static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
     configured.here() = true;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
-  const long long items = (long long)p.B * (2 * p.D) * 2 * p.hblocks;
+  if (GW) p.ctiles = (p.Wr + C::CSTEP - 1) / C::CSTEP;
+  else p.Wr = W, p.ctiles = 1;
+  const long long items = (long long)p.B * (2 * p.D) * 2 * p.hblocks * p.ctiles;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcdc: too many work items");
   p.items = (int)items;
   const int sms = sm_count();
@@ -450,7 +473,8 @@ extern "C" {
 
 int osb_deconv3d_tc_supported(int Cin, int Cout, int W) {
   if (Cin % 16 != 0 || Cin < 16) return 0;
-  return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) ? 1 : 0;
+  if ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) return 1;                          // whole-row variants
+  return (osb_tc_general_width(W) && (Cout == 32 || Cout == 64)) ? 1 : 0;                   // 128-column tiles of the INPUT row
 }
 
 int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
@@ -467,7 +491,10 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const floa
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
   cudaStream_t s = (cudaStream_t)stream;
-  if (W == 32) return launch_tcdc<64, 16, 32, 2>(p, s);
-  return launch_tcdc<32, 16, 64, 5>(p, s);
+  if (W == 32 && Cout == 64) return launch_tcdc<64, 16, 32, 2>(p, s);
+  if (W == 64 && Cout == 32) return launch_tcdc<32, 16, 64, 5>(p, s);
+  p.Wr = W;
+  if (Cout == 64) return launch_tcdc<64, 16, 128, 2, true>(p, s);
+  return launch_tcdc<32, 16, 128, 5, true>(p, s);
 }
 }

@@ -10,6 +10,11 @@
 //     kh weight slices of a phase fit in shared memory next to the ring for Cout = 64 / 128;
 //   * for Cout = 128 the kw-stacked N = 384 exceeds the UMMA maximum and is issued as three N = 128 MMAs;
 //   * the epilogue's +-1 column shift never crosses an image-row boundary (tile rows are whole image rows).
+// GENERAL WIDTHS (GW = true, W = 128 instantiations): an M tile is a 128-column SEGMENT of one image row of runtime width Wr,
+// starting at column ct * (128 - 2 DIL) - DIL: the first / last DIL tile columns are a halo (loaded like any other column, zero
+// outside the image -- the conv's padding), the kw-stacked partial sums are un-shifted across the whole tile exactly as before and
+// only the 128 - 2 DIL interior columns that exist in the image are stored.  Work items gain a column-tile index (fastest), so
+// widths such as 240 (the reference's 544x960 timing shape), 312 (KITTI) or 160 take the tensor-core path with 1.6 % halo overhead.
 #include "tc_common.cuh"
 
 namespace osb {
@@ -27,10 +32,14 @@ struct TcgParams {
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
+  int Wr, ctiles;          // general-width instantiations: image width and column tiles per row (whole-row kernels: W, 1)
 };
 
-template <int COUT, int KC, int W, int TILES, int DIL = 1>
+template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
 struct TcgCfg {
+  static_assert(!GW || W == 128, "general-width tiles are 128-column segments of one image row");
+  static constexpr int HALO = GW ? DIL : 0;                 // halo columns on each side of a column tile
+  static constexpr int CSTEP = 128 - 2 * HALO;              // image columns a column tile produces
   // DIL = 2: dilated 2D convs of the backbone (layer4 of gwcnet_backbone.py:38-60, psmnet_backbone.py) as one-plane volumes:
   // tap kh of output row t reads input row t + (kh-1)*DIL, the kw-stacked partial sums are un-shifted by DIL columns.
   static_assert(DIL == 1 || (W == 128 && DIL == 2 && COUT >= 64), "dilation 2 is instantiated for full-width rows only");
@@ -65,9 +74,9 @@ struct TcgCfg {
   static constexpr bool used(int s) { return tile_of(s, 0) >= 0 || tile_of(s, 1) >= 0 || tile_of(s, 2) >= 0; }
 };
 
-template <int COUT, int KC, int W, int TILES, int DIL = 1>
-__global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) conv3d_tcg_kernel(const TcgParams p) {
-  using C = TcgCfg<COUT, KC, W, TILES, DIL>;
+template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
+__global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 1) conv3d_tcg_kernel(const TcgParams p) {
+  using C = TcgCfg<COUT, KC, W, TILES, DIL, GW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + C::A_OFF;
@@ -88,6 +97,8 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
+  const int Wp = GW ? p.Wr : W;                     // image width = row pitch in voxels
+  const int ctiles = GW ? p.ctiles : 1;             // work item = (b, d, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -125,8 +136,8 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
     const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
     uint32_t unitc = 0, phc = 0, itc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
-      const int hb = it % p.hblocks;
-      const int d = (it / p.hblocks) % p.D;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int d = (it / (ctiles * p.hblocks)) % p.D;
       const int ntiles = min(TILES, (p.H - hb * C::HBLK + C::R - 1) / C::R);
       const int last_kd = (d + 1 < p.D) ? 2 : 1;
       uint32_t started = 0;
@@ -202,15 +213,18 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
     float amax = 0.f;
     const bool mine = lw < C::STAGES;
     uint32_t unitc = 0;
-    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
+    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
-      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column)
+      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
+      // General widths: col0 = image column of load 0 (may be -HALO .. or beyond Wr: those columns are zero padding).
       float4 v[NLD];
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int hin = h_first + h_step * ((VPL * j) / W);
         const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
-        v[j] = (hin >= 0 && hin < p.H) ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok = hin >= 0 && hin < p.H;
+        if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
+        v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
@@ -221,22 +235,24 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
       mbar_arrive(&a_ready[lw]);
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const int hb = it % p.hblocks;
-      const int d = (it / p.hblocks) % p.D;
-      const int b = it / (p.hblocks * p.D);
+      const int ct = it % ctiles;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int d = (it / (ctiles * p.hblocks)) % p.D;
+      const int b = it / (ctiles * p.hblocks * p.D);
       const int h0 = hb * C::HBLK;
+      const int col0 = ct * C::CSTEP - C::HALO + v0;   // image column of this lane's first load (whole-row kernels: v0)
       for (int kd = 0; kd < 3; ++kd) {
         const int din = d + kd - 1;
         if (din < 0 || din >= p.D) continue;
-        const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)W * p.Cin;
+        const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)Wp * p.Cin;
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
           for (int s = C::S_FIRST; s <= C::S_LAST; ++s) {
             if (!C::used(s)) continue;
             if (mine && unitc % C::STAGES == (uint32_t)lw) {
               // unit = R consecutive image rows starting at h0 + s: operand row v is voxel (h0 + s) * W + v of the plane
-              const float* base = plane + ((ptrdiff_t)(h0 + s) * W + v0) * p.Cin + ch * KC + c * 4;
-              fill(base, (size_t)W * p.Cin, (size_t)p.Cin, h0 + s, 1, unitc);
+              const float* base = plane + ((ptrdiff_t)(h0 + s) * Wp + col0) * p.Cin + ch * KC + c * 4;
+              fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h0 + s, 1, unitc, col0);
             }
             ++unitc;
           }
@@ -254,20 +270,25 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
     const bool has_right_q = (((q + 1) * 32) % W) != 0;
     uint32_t itc = 0, exc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
-      const int hb = it % p.hblocks;
-      const int d = (it / p.hblocks) % p.D;
-      const int b = it / (p.hblocks * p.D);
+      const int ct = it % ctiles;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int d = (it / (ctiles * p.hblocks)) % p.D;
+      const int b = it / (ctiles * p.hblocks * p.D);
       const int h0 = hb * C::HBLK;
       const int ntiles = min(TILES, (p.H - h0 + C::R - 1) / C::R);
+      // general widths: image column of this thread's tile column; halo columns and columns beyond the image are not stored
+      const int col = GW ? ct * C::CSTEP - C::HALO + m : wcol;
+      const bool cvalid = !GW || (m >= C::HALO && m < 128 - C::HALO && col < Wp);
+      const uint32_t vmask = GW ? __ballot_sync(0xffffffffu, cvalid) : 0xffffffffu;
       const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (d + 1 < p.D)) * nchunk * 3 * C::KSTEPS * 3);   // tc_common.cuh: rz_kappa
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
         const int h = h0 + t * C::R + rr;
         const bool live = h < p.H;
-        const size_t vox = (((size_t)b * p.D + d) * p.H + h) * W + wcol;           // NDHWC voxel index
-        const size_t plane = (size_t)p.D * p.H * W;                                // NCDHW channel stride
-        const size_t ncdhw0 = (size_t)b * COUT * plane + ((size_t)d * p.H + h) * W + wcol;
+        const ptrdiff_t vox = (((ptrdiff_t)b * p.D + d) * p.H + h) * Wp + col;     // NDHWC voxel index
+        const size_t plane = (size_t)p.D * p.H * Wp;                               // NCDHW channel stride
+        const ptrdiff_t ncdhw0 = (ptrdiff_t)b * COUT * plane + ((ptrdiff_t)d * p.H + h) * Wp + col;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
 #pragma unroll 1
         for (int cg = 0; cg < COUT; cg += 32) {
@@ -312,8 +333,9 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
-                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act);
-          } else if (live) {
+                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act,
+                                vmask);
+          } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
             if (p.residual) {
@@ -361,7 +383,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
       uint32_t phc = 0;
       for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-        const int d = (it / p.hblocks) % p.D;
+        const int d = (it / (ctiles * p.hblocks)) % p.D;
         for (int kd = 0; kd < 3; ++kd) {
           const int din = d + kd - 1;
           if (din < 0 || din >= p.D) continue;
@@ -384,10 +406,10 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL>::THREADS, 1) c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES, int DIL = 1>
+template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
 static int launch_tcg(TcgParams& p, cudaStream_t stream) {
-  using C = TcgCfg<COUT, KC, W, TILES, DIL>;
-  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL>;
+  using C = TcgCfg<COUT, KC, W, TILES, DIL, GW>;
+  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL, GW>;
   static PerDeviceFlag configured;
   if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -398,7 +420,9 @@ static int launch_tcg(TcgParams& p, cudaStream_t stream) {
     configured.here() = true;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
-  const long long items = (long long)p.B * p.D * p.hblocks;
+  if (GW) p.ctiles = (p.Wr + C::CSTEP - 1) / C::CSTEP;
+  else p.Wr = W, p.ctiles = 1;
+  const long long items = (long long)p.B * p.D * p.hblocks * p.ctiles;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcg: too many work items");
   p.items = (int)items;
   const int sms = sm_count();
@@ -431,6 +455,11 @@ int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
   if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
+  // every other width: 128-column tiles with a one-column halo (tc_general_width() is the single source of the W bound)
+  p.Wr = W;
+  if (Cout == 32) return launch_tcg<32, 16, 128, 5, 1, true>(p, stream);
+  if (Cout == 64) return launch_tcg<64, 16, 128, 2, 1, true>(p, stream);
+  if (Cout == 128) return launch_tcg<128, 16, 128, 1, 1, true>(p, stream);
   return -1;
 }
 

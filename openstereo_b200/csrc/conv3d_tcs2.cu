@@ -9,6 +9,9 @@
 //   E x W1 (N = Cout) into accumulator columns [0,Cout) and O x [W0 | W2] (N = 2 Cout) into [Cout, 3 Cout); the epilogue
 //   adds P1[ow] + P2[ow] + P0[ow-1] (a single left shift, zero at ow = 0 = the conv's left padding).
 // Weight slices are packed with the kw order (1, 0, 2) so both MMAs read contiguous rows.
+// GENERAL WIDTHS (GW = true, W = 128 instantiations; see conv3d_tcg.cu): an M tile is a 128-column segment of one OUTPUT row of
+// runtime width Wr starting at output column ct * 127 - 1; tile column 0 is the halo that provides O[ow-1] (zero at ow = -1) and is
+// not stored.
 #include "tc_common.cuh"
 
 namespace osb {
@@ -26,10 +29,14 @@ struct Tcs2Params {
   unsigned int* overflow;  // sticky fp16-range flag (tc_common.cuh)
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
+  int Wr, ctiles;          // general-width instantiations: OUTPUT width and column tiles per row (whole-row kernels: W, 1)
 };
 
-template <int COUT, int KC, int W, int TILES>     // W = OUTPUT width
+template <int COUT, int KC, int W, int TILES, bool GW = false>     // W = OUTPUT width
 struct Tcs2Cfg {
+  static_assert(!GW || W == 128, "general-width tiles are 128-column segments of one output row");
+  static constexpr int HALO = GW ? 1 : 0;                   // halo columns on the LEFT of a column tile
+  static constexpr int CSTEP = 128 - HALO;                  // output columns a column tile produces
   static constexpr int R = 128 / W;                         // OUTPUT image rows per M tile
   static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row: [KC fp16 hi | KC fp16 lo]
   static constexpr int UNIT_BYTES = 128 * ROWB;
@@ -51,9 +58,9 @@ struct Tcs2Cfg {
   static_assert(COUT % 16 == 0 && 2 * COUT <= 256, "invalid UMMA N");
 };
 
-template <int COUT, int KC, int W, int TILES>
-__global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3d_tcs2_kernel(const Tcs2Params p) {
-  using C = Tcs2Cfg<COUT, KC, W, TILES>;
+template <int COUT, int KC, int W, int TILES, bool GW = false>
+__global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) conv3d_tcs2_kernel(const Tcs2Params p) {
+  using C = Tcs2Cfg<COUT, KC, W, TILES, GW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + C::A_OFF;
@@ -74,6 +81,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
+  const int Wp = GW ? p.Wr : W;                     // OUTPUT width (the input is 2 * Wp wide)
+  const int ctiles = GW ? p.ctiles : 1;             // work item = (b, od, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -112,8 +121,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     const int Do = p.D / 2, Ho = p.H / 2;
     uint32_t unitc = 0, phc = 0, itc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
-      const int hb = it % p.hblocks;
-      const int od = (it / p.hblocks) % Do;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int od = (it / (ctiles * p.hblocks)) % Do;
       const int ntiles = min(TILES, (Ho - hb * C::HBLK + C::R - 1) / C::R);
       uint32_t started = 0;
       for (int kd = 0; kd < 3; ++kd) {
@@ -183,18 +192,21 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
     float amax = 0.f;
     const bool mine = lw < C::STAGES;
-    constexpr int WI = 2 * W;                        // input width
+    const int WI = 2 * Wp;                           // input width
     const int Do = p.D / 2;
     uint32_t unitc = 0;
-    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u) {
+    auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
-      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column)
+      // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
+      // General widths: col0 = OUTPUT column of load 0 (-1 = the left halo; columns outside [0, Wp) are zero padding).
       float4 v[NLD];
 #pragma unroll
       for (int j = 0; j < NLD; ++j) {
         const int hin = h_first + h_step * ((VPL * j) / W);
         const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
-        v[j] = (hin >= 0 && hin < p.H) ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok = hin >= 0 && hin < p.H;
+        if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
+        v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
@@ -205,10 +217,12 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       mbar_arrive(&a_ready[lw]);
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const int hb = it % p.hblocks;
-      const int od = (it / p.hblocks) % Do;
-      const int b = it / (p.hblocks * Do);
+      const int ct = it % ctiles;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int od = (it / (ctiles * p.hblocks)) % Do;
+      const int b = it / (ctiles * p.hblocks * Do);
       const int h0 = hb * C::HBLK;                   // first OUTPUT row of the block
+      const int col0 = ct * C::CSTEP - C::HALO + v0; // OUTPUT column of this lane's first load (whole-row kernels: v0)
       for (int kd = 0; kd < 3; ++kd) {
         const int din = 2 * od + kd - 1;
         if (din < 0 || din >= p.D) continue;
@@ -223,8 +237,8 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
                 if (mine && unitc % C::STAGES == (uint32_t)lw) {
                   // operand row v = output voxel (row h0 + t*R + v / W, column v % W) reading input (2*row + kh - 1, 2*col + par)
                   const int h_first = 2 * (h0 + t * C::R) + kh - 1;
-                  const float* base = plane + ((ptrdiff_t)h_first * WI + 2 * v0 + par) * p.Cin + ch * KC + c * 4;
-                  fill(base, (size_t)2 * WI * p.Cin, (size_t)2 * p.Cin, h_first, 2, unitc);
+                  const float* base = plane + ((ptrdiff_t)h_first * WI + 2 * col0 + par) * p.Cin + ch * KC + c * 4;
+                  fill(base, (size_t)2 * WI * p.Cin, (size_t)2 * p.Cin, h_first, 2, unitc, col0);
                 }
                 ++unitc;
               }
@@ -244,11 +258,16 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
     const int Do = p.D / 2, Ho = p.H / 2;
     uint32_t itc = 0, exc = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
-      const int hb = it % p.hblocks;
-      const int d = (it / p.hblocks) % Do;
-      const int b = it / (p.hblocks * Do);
+      const int ct = it % ctiles;
+      const int hb = (it / ctiles) % p.hblocks;
+      const int d = (it / (ctiles * p.hblocks)) % Do;
+      const int b = it / (ctiles * p.hblocks * Do);
       const int h0 = hb * C::HBLK;
       const int ntiles = min(TILES, (Ho - h0 + C::R - 1) / C::R);
+      // general widths: output column of this thread's tile column; the halo column and columns beyond the image are not stored
+      const int col = GW ? ct * C::CSTEP - C::HALO + m : wcol;
+      const bool cvalid = !GW || (m >= C::HALO && col < Wp);
+      const uint32_t vmask = GW ? __ballot_sync(0xffffffffu, cvalid) : 0xffffffffu;
       // input planes 2d-1, 2d, 2d+1: the first is missing for d = 0 (tc_common.cuh: rz_kappa)
       const float corr = 1.f + p.kappa * (float)(((d > 0) + 1 + (2 * d + 1 < p.D)) * nchunk * 3 * C::KSTEPS * 3);
       for (int t = 0; t < ntiles; ++t) {
@@ -256,9 +275,9 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
         tc_fence_after();
         const int h = h0 + t * C::R + rr;
         const bool live = h < Ho;
-        const size_t vox = (((size_t)b * Do + d) * Ho + h) * W + wcol;             // NDHWC voxel index (output)
-        const size_t plane = (size_t)Do * Ho * W;                                  // NCDHW channel stride (output)
-        const size_t ncdhw0 = (size_t)b * COUT * plane + ((size_t)d * Ho + h) * W + wcol;
+        const ptrdiff_t vox = (((ptrdiff_t)b * Do + d) * Ho + h) * Wp + col;       // NDHWC voxel index (output)
+        const size_t plane = (size_t)Do * Ho * Wp;                                 // NCDHW channel stride (output)
+        const ptrdiff_t ncdhw0 = (ptrdiff_t)b * COUT * plane + ((ptrdiff_t)d * Ho + h) * Wp + col;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
 #pragma unroll 1
         for (int cg = 0; cg < COUT; cg += 32) {
@@ -296,8 +315,9 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
-                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act);
-          } else if (live) {
+                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act,
+                                vmask);
+          } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
             if (p.residual) {
@@ -345,7 +365,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
       uint32_t phc = 0;
       for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-        const int od = (it / p.hblocks) % (p.D / 2);
+        const int od = (it / (ctiles * p.hblocks)) % (p.D / 2);
         for (int kd = 0; kd < 3; ++kd) {
           const int din = 2 * od + kd - 1;              // must enumerate the same phases as the MMA warp and the loaders
           if (din < 0 || din >= p.D) continue;
@@ -368,10 +388,10 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES>::THREADS, 1) conv3
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES>
+template <int COUT, int KC, int W, int TILES, bool GW = false>
 static int launch_tcs2(Tcs2Params& p, cudaStream_t stream) {
-  using C = Tcs2Cfg<COUT, KC, W, TILES>;
-  auto kernel = conv3d_tcs2_kernel<COUT, KC, W, TILES>;
+  using C = Tcs2Cfg<COUT, KC, W, TILES, GW>;
+  auto kernel = conv3d_tcs2_kernel<COUT, KC, W, TILES, GW>;
   static PerDeviceFlag configured;
   if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -382,7 +402,9 @@ static int launch_tcs2(Tcs2Params& p, cudaStream_t stream) {
     configured.here() = true;
   }
   p.hblocks = (p.H / 2 + C::HBLK - 1) / C::HBLK;
-  const long long items = (long long)p.B * (p.D / 2) * p.hblocks;
+  if (GW) p.ctiles = (p.Wr + C::CSTEP - 1) / C::CSTEP;
+  else p.Wr = W, p.ctiles = 1;
+  const long long items = (long long)p.B * (p.D / 2) * p.hblocks * p.ctiles;
   OSB_REQUIRE(items < (1ll << 31), "conv3d_tcs2: too many work items");
   p.items = (int)items;
   const int sms = sm_count();
@@ -407,7 +429,8 @@ extern "C" {
 
 int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
   if (Cin % 16 != 0 || Cin < 16 || D % 2 || H % 2 || W % 2) return 0;
-  return ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 128))) ? 1 : 0;
+  if ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 128))) return 1;      // whole-row variants
+  return (osb_tc_general_width(W / 2) && (Cout == 64 || Cout == 128)) ? 1 : 0;              // 128-column tiles of the OUTPUT row
 }
 
 int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
@@ -427,6 +450,9 @@ int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const flo
   cudaStream_t s = (cudaStream_t)stream;
   if (W == 128 && Cout == 64) return launch_tcs2<64, 16, 64, 2>(p, s);
   if (W == 64 && Cout == 64) return launch_tcs2<64, 16, 32, 2>(p, s);
-  return launch_tcs2<128, 16, 32, 1>(p, s);
+  if (W == 64 && Cout == 128) return launch_tcs2<128, 16, 32, 1>(p, s);
+  p.Wr = W / 2;
+  if (Cout == 64) return launch_tcs2<64, 16, 128, 2, true>(p, s);
+  return launch_tcs2<128, 16, 128, 1, true>(p, s);
 }
 }

@@ -203,8 +203,11 @@ constexpr int TP_BYTES = 4 * TP_WARP_FLOATS * 4;    // four epilogue warps
 
 // sum[32]: raw accumulator sums of this lane's voxel for channels [c, c+32).  y0 / res0 point at channel c of the voxel
 // owned by lane 0; lane k's voxel lies vstride floats further per lane.  sc / sh point at channel c of the folded BN.
+// vmask: bit k set = the voxel of lane k exists in the output (general-width column tiles mask their halo columns and the part of
+// the last tile beyond the image; whole-row tiles pass all ones and the tests fold away).
 __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const float (&sum)[32], float* y0, const float* res0,
-                                                    size_t vstride, const float* sc, const float* sh, int act) {
+                                                    size_t vstride, const float* sc, const float* sh, int act,
+                                                    uint32_t vmask = 0xffffffffu) {
   const int c4 = 4 * (lane & 7), sub = lane >> 3;
   __syncwarp();                                     // the previous chunk's readers are done with the tile
   float4* row = reinterpret_cast<float4*>(tbuf + lane * TP_STRIDE);
@@ -222,7 +225,9 @@ __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const
   if (res0) {
     float4 r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)(4 * j + sub) * vstride + c4));
+    for (int j = 0; j < 8; ++j)
+      r[j] = ((vmask >> (4 * j + sub)) & 1u) ? __ldg(reinterpret_cast<const float4*>(res0 + (size_t)(4 * j + sub) * vstride + c4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j].x += r[j].x, o[j].y += r[j].y, o[j].z += r[j].z, o[j].w += r[j].w;
   }
@@ -237,7 +242,8 @@ __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(y0 + (size_t)(4 * j + sub) * vstride + c4) = o[j];
+  for (int j = 0; j < 8; ++j)
+    if ((vmask >> (4 * j + sub)) & 1u) *reinterpret_cast<float4*>(y0 + (size_t)(4 * j + sub) * vstride + c4) = o[j];
 }
 
 }  // namespace osb
