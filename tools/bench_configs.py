@@ -181,13 +181,52 @@ def c5(iters, B=8, gru_iters=16):
                        "upsample": float("%.2e" % (got[2] - want[2].reshape(got[2].shape)).abs().max().item())})
 
 
+def gw(iters):
+    """GwcNet hot path (gwc+concat volume -> 3D aggregation -> fused tail) at widths the whole-row tensor-core kernels do not serve:
+    the reference's own timing shape 1x3x544x960 (tools/measure.py:32, W' = 240) and a KITTI crop 384x1248 (W' = 312).  Three
+    columns: column-tile tcgen05 kernels, the fp32 CUDA-core kernels of the same engine (what round 1 ran at these widths) and the
+    oracle modules on cuDNN fp32."""
+    for (h, w) in ((544, 960), (384, 1248)):
+        gen = torch.Generator().manual_seed(17)
+        hq, wq = h // 4, w // 4
+        ml, mr = rnd(gen, 1, 320, hq, wq), rnd(gen, 1, 320, hq, wq)
+        cl, cr = rnd(gen, 1, 12, hq, wq), rnd(gen, 1, 12, hq, wq)
+        m = oagg.GwcDispProcessor(maxdisp=192, downsample=4, num_groups=40, use_concat_volume=True, concat_channels=12).eval()
+        m.load_state_dict(si.seeded_state_dict(m.state_dict(), seed=41, scale={"classif3.2.weight": 60.0}))
+        m.to(DEV)
+        eng = agg.GwcAggregation(m)
+
+        def ours():
+            return eng(ops.gwc_concat_volume(ml, mr, cl, cr, 48, 40), h, w)
+
+        def ref():
+            vol = torch.cat((ocv.build_gwc_volume(ml, mr, 48, 40), ocv.build_concat_volume(cl, cr, 48)), 1)
+            return m(vol, h, w)
+
+        with torch.no_grad():
+            ms, got = timeit(ours, iters)
+            agg.USE_TENSOR_CORES = False
+            try:
+                ms_cc, got_cc = timeit(lambda: agg.GwcAggregation(m)(ops.gwc_concat_volume(ml, mr, cl, cr, 48, 40), h, w), max(2, iters // 3), warm=1)
+            finally:
+                agg.USE_TENSOR_CORES = True
+            ms_ref, want = timeit(ref, max(2, iters // 3), warm=1)
+        emit(config="gw GwcNet hot path, 1 pair @%dx%d D=192 (W' = %d: column-tile tcgen05 kernels)" % (h, w, wq),
+             ms_per_step=round(ms, 3), pairs_per_s=round(1e3 / ms, 2), cuda_core_kernels_ms=round(ms_cc, 2),
+             reference_cudnn_fp32_ms=round(ms_ref, 2), speedup_vs_cuda_core=round(ms_cc / ms, 2),
+             speedup_vs_reference_gpu=round(ms_ref / ms, 2),
+             epe_vs_reference_gpu_px=float("%.3e" % (got - want.reshape(got.shape)).abs().mean().item()),
+             epe_vs_cuda_core_px=float("%.3e" % (got - got_cc).abs().mean().item()), disparity_std_px=round(want.std().item(), 2),
+             overflow_count=ops.tc_overflow_count())
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="c1,c3,c4,c5")
+    ap.add_argument("--only", default="c1,c3,c4,c5,gw")
     ap.add_argument("--iters", type=int, default=10)
     a = ap.parse_args()
     for name in a.only.split(","):
         try:
-            {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name](a.iters)
+            {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "gw": gw}[name](a.iters)
         except Exception as exc:                                               # one config must not hide the others
             emit(config=name, error=repr(exc)[:300])
