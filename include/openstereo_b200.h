@@ -165,6 +165,11 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride);
 int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* Same with FeatureAtt's gate fused: y = act(bn(conv(x)) + residual) * gate, gate_nhwc (B,H,W,Cout) = sigmoid(att) broadcast over D
+ * (stereobase/hourglass.py:80-99, igev_blocks.py:35-48).  Channels-last y / residual, 16-channel-chunk variants only. */
+int osb_conv3d_k3_tc_gate_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                              const float* residual, const float* gate_nhwc, float* y, int B, int Cin, int Cout, int D, int H, int W,
+                              int act, osb_stream_t stream);
 /* Same, reading an NCDHW input (B,Cin,D,H,W) -- the cost volume exactly as osb_gwc_concat_volume_fwd / build_*_volume return it --
  * so the first aggregation layer needs no layout-conversion pass.  Served by the W = 128 variant (Cout = 32 or <= 16). */
 int osb_conv3d_k3_tc_ncdhw_fwd(const float* x_ncdhw, const void* w_split, const float* scale, const float* shift,
@@ -184,6 +189,20 @@ int osb_deconv3d_tc_supported(int Cin, int Cout, int W);
 int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                            int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* ConvTranspose3d(k=4, stride=2, padding=1) on the tensor cores -- BasicDeconv3d of StereoBase's hourglass
+ * (stereobase/hourglass.py:35-60 conv3_up / conv2_up / conv1_up): x (B,D,H,W,Cin) channels-last -> y (B,2D,2H,2W,Cout) channels-last
+ * or (B,cout_real,2D,2H,2W).  w_split = ops.pack_tc_deconv_weight of the (Cin,Cout,4,4,4) parameter, kw slices stored as (1,3,2,0).
+ * Cout is the PACKED channel count (zero-padded channel plans: 24 -> 32, 48 -> 64); cout_real <= Cout real channels are written /
+ * added when the output / residual is NCDHW.  Supported: W=32/Cout=64, W=64/Cout=32. */
+int osb_deconv3d_k4_tc_supported(int Cin, int Cout, int W);
+int osb_deconv3d_k4_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                           const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
+                           int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* Channels-last 1x1x1 conv over the channel concatenation of two tensors (torch.cat((up, skip), 1) -> Conv3d(k=1) of
+ * stereobase/hourglass.py:91-92,96-97, never materialised): x0 (voxels,C0), x1 (voxels,C1) or NULL -> y (voxels,Cout);
+ * w_packed (C0+C1, Cout).  192 -> 96 and 128 -> 64. */
+int osb_conv1x1_ndhwc_cat_fwd(const float* x0, const float* x1, int C0, int C1, const float* w_packed, const float* scale,
+                              const float* shift, float* y, long long voxels, int Cout, int act, osb_stream_t stream);
 /* Channels-last 1x1x1 conv + folded BN + activation (the redir branches when the aggregation runs channels-last):
  * x (voxels, Cin) -> y (voxels, Cout); w_packed (Cin, Cout).  32->32 and 64->64. */
 int osb_conv1x1_ndhwc_fwd(const float* x, const float* w_packed, const float* scale, const float* shift, float* y,
@@ -261,6 +280,9 @@ int osb_context_upsample_fwd(const float* disp_low, const float* up_weights, flo
                              osb_stream_t stream);
 /* (B,C,D,H,W) -> (B,D,H,W,C) layout change feeding the tensor-core conv. */
 int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream);
+/* Same with the channel axis zero-padded to Cpad >= C: y (B,D,H,W,Cpad) -- channel plans that are not multiples of 16 (StereoBase's
+ * 24 / 48) run on the tensor-core kernels as 32 / 64 with zero weights on the padding. */
+int osb_ncdhw_to_ndhwc_pad(const float* x, float* y, int B, int C, int Cpad, int D, int H, int W, osb_stream_t stream);
 
 #ifdef __cplusplus
 }

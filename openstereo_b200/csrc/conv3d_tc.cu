@@ -498,7 +498,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
 
 // ---------------------------------------------------------------------------------------- layout conversion kernels
 // NCDHW -> NDHWC through a 32x32 shared-memory transpose (both sides coalesced).
-__global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, size_t vol) {
+__global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp,
+                                                             size_t vol) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const size_t v0 = (size_t)blockIdx.x * 32;
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(256) ncdhw_to_ndhwc_kernel(const float* __rest
   for (int i = ty; i < 32; i += 8) {
     const size_t v = v0 + i;
     const int c = c0 + tx;
-    if (c < C && v < vol) y[((size_t)b * vol + v) * C + c] = tile[tx][i];
+    if (c < Cp && v < vol) y[((size_t)b * vol + v) * Cp + c] = tile[tx][i];      // channels C .. Cp-1: zero padding
   }
 }
 
@@ -540,7 +541,8 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
 }
 
 int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
-                        int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
+                        int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream,
+                        const float* gate = nullptr);
 int launch_tcg_dilated2(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
 
@@ -558,7 +560,8 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (W == osb::TC_W && (Cout == 32 || (Cout >= 1 && Cout <= 16)) && Cin % 32 == 0 && Cin >= 32) return 32;   // conv3d_tc.cu (narrow
                                                                                                // heads: weights zero-padded to 16 rows)
   if (Cin % 16 == 0 && Cin >= 16 &&
-      ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 128)) || (W == osb::TC_W && (Cout == 64 || Cout == 128))))
+      ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 96 || Cout == 128)) ||
+       (W == osb::TC_W && (Cout == 64 || Cout == 128))))
     return 16;                                                                                  // conv3d_tcg.cu
   if (Cin % 16 == 0 && Cin >= 16 && osb_tc_general_width(W) && (Cout == 32 || Cout == 64 || Cout == 128))
     return 16;                                                                                  // conv3d_tcg.cu, column tiles
@@ -567,20 +570,24 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
 
 int osb_conv3d_tc_supported(int Cin, int Cout, int W, int stride) { return osb_conv3d_tc_kc(Cin, Cout, W, stride) != 0; }
 
-int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream) {
+int osb_ncdhw_to_ndhwc_pad(const float* x, float* y, int B, int C, int Cpad, int D, int H, int W, osb_stream_t stream) {
   using namespace osb;
   OSB_REQUIRE(x && y, "ncdhw_to_ndhwc: null pointer");
-  OSB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0 && B <= 65535, "ncdhw_to_ndhwc: bad shape");
+  OSB_REQUIRE(B > 0 && C > 0 && Cpad >= C && D > 0 && H > 0 && W > 0 && B <= 65535, "ncdhw_to_ndhwc: bad shape");
   const size_t vol = (size_t)D * H * W;
-  dim3 grid((unsigned)((vol + 31) / 32), (C + 31) / 32, B);
-  ncdhw_to_ndhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, C, vol);
+  dim3 grid((unsigned)((vol + 31) / 32), (Cpad + 31) / 32, B);
+  ncdhw_to_ndhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, C, Cpad, vol);
   count_launch();
   return check_launch("ncdhw_to_ndhwc_kernel");
 }
 
+int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int W, osb_stream_t stream) {
+  return osb_ncdhw_to_ndhwc_pad(x, y, B, C, C, D, H, W, stream);
+}
+
 static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                              const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
-                             int out_ndhwc, int res_ndhwc, int in_ncdhw, osb_stream_t stream) {
+                             int out_ndhwc, int res_ndhwc, int in_ncdhw, osb_stream_t stream, const float* gate = nullptr) {
   using namespace osb;
   OSB_REQUIRE(x_ndhwc && w_split && y, "conv3d_k3_tc: null pointer");
   OSB_REQUIRE(B > 0 && D > 0 && H > 0, "conv3d_k3_tc: empty shape");
@@ -590,9 +597,12 @@ static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const fl
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
               "conv3d_k3_tc: pointers must be 16-byte aligned");
   OSB_REQUIRE(!in_ncdhw || osb_conv3d_tc_kc(Cin, Cout, W, 1) == 32, "conv3d_k3_tc: NCDHW input is served by the W = 128 kernel only");
+  OSB_REQUIRE(!gate || (osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16 && out_ndhwc && (!residual || res_ndhwc) &&
+                        (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
+              "conv3d_k3_tc: the gate operand needs a channels-last output (and residual) on the 16-channel-chunk kernels");
   if (osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16)
     return launch_tcg_dispatch(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, gate);
   TcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.Cout = Cout, p.act = act;
@@ -618,6 +628,13 @@ int osb_conv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float*
                          const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
                          int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
   return conv3d_k3_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc, 0, stream);
+}
+
+int osb_conv3d_k3_tc_gate_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                              const float* residual, const float* gate_nhwc, float* y, int B, int Cin, int Cout, int D, int H, int W,
+                              int act, osb_stream_t stream) {
+  OSB_REQUIRE(gate_nhwc, "conv3d_k3_tc_gate: null gate");
+  return conv3d_k3_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, 1, 1, 0, stream, gate_nhwc);
 }
 
 int osb_conv3d_k3_tc_ncdhw_fwd(const float* x_ncdhw, const void* w_split, const float* scale, const float* shift,

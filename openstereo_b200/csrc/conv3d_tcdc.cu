@@ -12,6 +12,10 @@
 // GENERAL WIDTHS (GW = true, W = 128 instantiations; see conv3d_tcg.cu): an M tile is a 128-column segment of one INPUT row of
 // runtime width Wr starting at input column ct * 127; tile column 127 is the halo that provides P0[m+1] (zero beyond the image) and
 // its two output columns are not stored.
+// KS = 4: ConvTranspose3d(k=4, s=2, p=1) of StereoBase's hourglass (stereobase/hourglass.py:35-60 conv*_up): per dimension
+//   o = 2m: taps k=1 (input m) and k=3 (input m-1);   o = 2m+1: taps k=2 (input m) and k=0 (input m+1)
+// -- every parity class has 2 x 2 (kd, kh) tap pairs, the four kw slices are stacked along N as [W1 | W3 | W2 | W0] and the
+// epilogue forms  even[m] = P1[m] + P3[m-1],  odd[m] = P2[m] + P0[m+1]  (one left and one right shift).
 #include "tc_common.cuh"
 
 namespace osb {
@@ -30,17 +34,20 @@ struct TcdcParams {
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
   int Wr, ctiles;          // general-width instantiations: INPUT width and column tiles per row (whole-row kernels: W, 1)
+  int cout_real;           // channels of an NCDHW output / residual (<= COUT: zero-padded channel plans write only the real ones)
 };
 
-template <int COUT, int KC, int W, int TILES, bool GW = false>     // W = INPUT width
+template <int COUT, int KC, int W, int TILES, bool GW = false, int KS_ = 3>     // W = INPUT width, KS_ = kernel size (3 or 4)
 struct TcdcCfg {
   static_assert(!GW || W == 128, "general-width tiles are 128-column segments of one input row");
+  static_assert(KS_ == 3 || (KS_ == 4 && !GW), "kernel size 3 (any width) or 4 (whole-row tiles)");
+  static constexpr int KS = KS_;
   static constexpr int HALO = GW ? 1 : 0;                   // halo columns on the RIGHT of a column tile
   static constexpr int CSTEP = 128 - HALO;                  // input columns a column tile produces outputs for
   static constexpr int R = 128 / W;                         // input rows (= output rows of one parity) per M tile
   static constexpr int ROWB = KC * 4;                       // bytes per K-major operand row: [KC fp16 hi | KC fp16 lo]
   static constexpr int UNIT_BYTES = 128 * ROWB;
-  static constexpr int N3 = 3 * COUT;
+  static constexpr int N3 = KS_ * COUT;                     // kw slices stacked along N
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
   static constexpr int STAGES = 5;                          // one loader warp per ring slot: warps 1-4 and 10 (the former second
                                                             // weight-loader warp, idle since the slices come by TMA)
@@ -49,7 +56,7 @@ struct TcdcCfg {
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * UNIT_BYTES;
-  static constexpr int BAR_OFF = B_OFF + TC_BSLOTS * 3 * B_SLICE;
+  static constexpr int BAR_OFF = B_OFF + TC_BSLOTS * KS_ * B_SLICE;
   static constexpr int THREADS = 32 + 128 + 128 + 64;       // MMA | A loaders | epilogue | weight loaders (11 warps)
   static constexpr size_t SMEM = 1024 + (size_t)BAR_OFF + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
   static_assert(SMEM <= 232448, "shared memory budget of one CTA exceeded");
@@ -61,8 +68,15 @@ struct TcdcCfg {
 // work item = (image b, output plane od, row parity ph, block of TILES*R input rows); parity bits vary fastest so that the
 // 1/2/2/4-tap classes are interleaved over the persistent CTAs
 struct ItemDc {
-  int b, od, ph, j0, last_kd, last_kh, ct;
+  int b, od, ph, j0, last_kd, last_kh, ct, nkd;
 };
+// output index o gathers tap k from input (o + 1 - k) / 2 when that is an integer inside [0, n)
+__device__ __forceinline__ bool kd_valid(int od, int kd, int D) {
+  const int num = od + 1 - kd;
+  return !(num & 1) && num >= 0 && (num >> 1) < D;
+}
+// rows outside the image are staged as zeros rather than skipped, so only the parity decides
+__device__ __forceinline__ bool kh_valid(int ph, int kh) { return ((ph + 1 - kh) & 1) == 0; }
 template <class C>
 __device__ __forceinline__ ItemDc decode_dc(const TcdcParams& p, int it) {
   ItemDc w;
@@ -78,20 +92,18 @@ __device__ __forceinline__ ItemDc decode_dc(const TcdcParams& p, int it) {
   it /= Do;
   w.j0 = (it % p.hblocks) * C::HBLK;
   w.b = it / p.hblocks;
-  w.last_kd = (w.od & 1) ? 2 : 1;
-  w.last_kh = w.ph ? 2 : 1;
+  w.last_kd = w.last_kh = -1, w.nkd = 0;
+#pragma unroll
+  for (int k = 0; k < C::KS; ++k) {                 // last valid taps in issue order; number of input planes feeding this class
+    if (kd_valid(w.od, k, p.D)) w.last_kd = k, ++w.nkd;
+    if (kh_valid(w.ph, k)) w.last_kh = k;
+  }
   return w;
 }
-// output index o gathers tap k from input (o + 1 - k) / 2 when that is an integer inside [0, n)
-__device__ __forceinline__ bool kd_valid(int od, int kd, int D) {
-  const int num = od + 1 - kd;
-  return !(num & 1) && (num >> 1) < D;
-}
-__device__ __forceinline__ bool kh_valid(int ph, int kh) { return ((ph + 1 - kh) & 1) == 0; }
 
-template <int COUT, int KC, int W, int TILES, bool GW = false>
-__global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) conv3d_tcdc_kernel(const TcdcParams p) {
-  using C = TcdcCfg<COUT, KC, W, TILES, GW>;
+template <int COUT, int KC, int W, int TILES, bool GW = false, int KS = 3>
+__global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 1) conv3d_tcdc_kernel(const TcdcParams p) {
+  using C = TcdcCfg<COUT, KC, W, TILES, GW, KS>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem + C::A_OFF;
@@ -99,9 +111,9 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* a_ready = bars;                         // [STAGES] loaders -> MMA        (32 arrivals: one warp)
   uint64_t* a_empty = a_ready + C::STAGES;          // [STAGES] MMA -> loaders        (tcgen05.commit)
-  uint64_t* b_full = a_empty + C::STAGES;           // [2][3]   weight producer -> MMA (expect_tx + TMA bytes)
-  uint64_t* b_empty = b_full + TC_BSLOTS * 3;       // [2][3]   MMA -> weight producer (tcgen05.commit)
-  uint64_t* acc_full = b_empty + TC_BSLOTS * 3;                 // [TILES]
+  uint64_t* b_full = a_empty + C::STAGES;           // [2][KS]  weight producer -> MMA (expect_tx + TMA bytes)
+  uint64_t* b_empty = b_full + TC_BSLOTS * KS;      // [2][KS]  MMA -> weight producer (tcgen05.commit)
+  uint64_t* acc_full = b_empty + TC_BSLOTS * KS;                // [TILES]
   uint64_t* acc_empty = acc_full + TILES;           // [TILES]  (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TILES);
   float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 1024);   // [2][4 quadrants][2 sides][32]
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
       mbar_init(&a_ready[s], 32);                     // one loader warp fills a unit
       mbar_init(&a_empty[s], 1);
     }
-    for (int k = 0; k < TC_BSLOTS * 3; ++k) {
+    for (int k = 0; k < TC_BSLOTS * KS; ++k) {
       mbar_init(&b_full[k], 1);
       mbar_init(&b_empty[k], 1);
     }
@@ -149,23 +161,23 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
     const uint64_t dbase = (KC == 32) ? desc_sw128_base() : desc_sw64_base();
     const uint32_t b16 = (smem_u32(b_buf) & 0x3FFFF) >> 4;
     uint32_t unitc = 0, itc = 0;
-    uint32_t bph[3] = {0, 0, 0};                      // per-slice use counters (slices are loaded only for valid kh)
+    uint32_t bph[KS] = {};                            // per-slice use counters (slices are loaded only for valid kh)
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
       const ItemDc w = decode_dc<C>(p, it);
       const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
       uint32_t started = 0;
-      for (int kd = 0; kd < 3; ++kd) {
+      for (int kd = 0; kd < KS; ++kd) {
         if (!kd_valid(w.od, kd, p.D)) continue;
         for (int ch = 0; ch < nchunk; ++ch) {
           const bool last_phase = (kd == w.last_kd) && (ch == nchunk - 1);
 #pragma unroll
           for (int t = 0; t < TILES; ++t) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < KS; ++kh) {
               if (!kh_valid(w.ph, kh)) continue;        // warp-uniform
               const uint32_t slot = unitc % C::STAGES, ph = (unitc / C::STAGES) & 1;
               mbar_wait(&a_ready[slot], ph);
-              const uint32_t bslot = (bph[kh] & 1) * 3 + kh;   // the buffers of tap kh alternate between its uses
+              const uint32_t bslot = (bph[kh] & 1) * KS + kh;  // the buffers of tap kh alternate between its uses
               if (t == 0) mbar_wait(&b_full[bslot], (bph[kh] >> 1) & 1);   // first use of slice kh in this phase
               tc_fence_after();
               const uint32_t accum = (started >> t) & 1;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
         const size_t off = (size_t)((VPL * j) / W) * rstride + (size_t)((VPL * j) % W) * cstride;
         bool ok = hin >= 0 && hin < p.H;
         if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
-        v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const uint32_t ph = (u / C::STAGES) & 1;
       mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const ItemDc w = decode_dc<C>(p, it);
-      for (int kd = 0; kd < 3; ++kd) {
+      for (int kd = 0; kd < KS; ++kd) {
         if (!kd_valid(w.od, kd, p.D)) continue;
         const int id = (w.od + 1 - kd) >> 1;         // input plane feeding output plane od through tap kd
         const float* plane = p.x + ((size_t)w.b * p.D + id) * p.H * (size_t)Wp * p.Cin;
@@ -251,12 +263,13 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
 #pragma unroll 1
           for (int t = 0; t < TILES; ++t) {
 #pragma unroll 1
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < KS; ++kh) {
               if (!kh_valid(w.ph, kh)) continue;
               if (mine && unitc % C::STAGES == (uint32_t)lw) {
-                // operand row v = input voxel (row j0 + t*R + v / W (+1 for tap kh = 0), column v % W)
-                const int h_first = w.j0 + t * C::R + (kh == 0 ? 1 : 0);
-                const float* base = plane + ((size_t)h_first * Wp + col0) * p.Cin + ch * KC + c * 4;
+                // operand row v = input voxel (row j0 + t*R + v / W + (ph + 1 - kh) / 2, column v % W): output row 2j + ph gathers
+                // tap kh from input row j + (ph + 1 - kh) / 2  (k3: +1 for kh = 0; k4: +1 for kh = 0, -1 for kh = 3)
+                const int h_first = w.j0 + t * C::R + ((w.ph + 1 - kh) >> 1);
+                const float* base = plane + ((ptrdiff_t)h_first * Wp + col0) * p.Cin + ch * KC + c * 4;
                 fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h_first, 1, unitc, col0);
               }
               ++unitc;
@@ -273,6 +286,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
     const int m = q * 32 + lane;                     // operand row owned by this thread
     const int rr = m / W, wcol = m % W;              // input row inside the tile, input column
     const bool has_right_q = (((q + 1) * 32) % W) != 0;   // the next quadrant continues the same image row
+    const bool has_left_q = ((q * 32) % W) != 0;          // (k4 only) the previous quadrant does
     const int Do = 2 * p.D, Ho = 2 * p.H;
     const int Wo = 2 * Wp;
     uint32_t itc = 0, exc = 0;
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
       const ItemDc w = decode_dc<C>(p, it);
       const int ntiles = min(TILES, (p.H - w.j0 + C::R - 1) / C::R);
       // tap pairs of this parity class: (1 or 2 kd) x (1 or 2 kh); each adds chunks x k-steps x 3 MMAs (tc_common.cuh: rz_kappa)
-      const float corr = 1.f + p.kappa * (float)(((w.od & 1) + 1) * (w.ph + 1) * nchunk * C::KSTEPS * 3);
+      const float corr = 1.f + p.kappa * (float)(w.nkd * (KS == 4 ? 2 : w.ph + 1) * nchunk * C::KSTEPS * 3);
       // general widths: input column of this thread's tile column; the halo column and columns beyond the image are not stored
       const int col = GW ? w.ct * C::CSTEP + m : wcol;
       const bool cvalid = !GW || (m < C::CSTEP && col < Wp);
@@ -300,10 +314,14 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
         mbar_wait_relaxed(&acc_full[t], itc & 1);
         tc_fence_after();
         const size_t plane = (size_t)Do * Ho * Wo;                                   // NCDHW channel stride
-        const size_t ncdhw0 = (size_t)w.b * COUT * plane + ((size_t)w.od * Ho + oh) * Wo + 2 * col;
+        const size_t ncdhw0 = (size_t)w.b * p.cout_real * plane + ((size_t)w.od * Ho + oh) * Wo + 2 * col;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + t * C::N3;
 #pragma unroll 1
         for (int cg = 0; cg < COUT; cg += 32) {
+          float ev[32], od_[32];
+          float* xb = xchg + (exc & 1) * (4 * 2 * 32);
+          ++exc;
+          if constexpr (KS == 3) {
           // accumulator column groups: raw[0] = E (kw=1), raw[1] = P2 (kw=2), raw[2] = P0 (kw=0)
           uint32_t raw[3][32];
 #pragma unroll
@@ -315,15 +333,12 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
             tc_fence_before();
             mbar_arrive(&acc_empty[t]);
           }
-          float* xb = xchg + (exc & 1) * (4 * 2 * 32);
-          ++exc;
           if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) xb[(q * 2) * 32 + i] = __uint_as_float(raw[2][i]);
           }
           named_bar_sync(1, 128);
           const float* xr = has_right_q ? xb + ((q + 1) * 2) * 32 : zeros;
-          float ev[32], od_[32];
 #pragma unroll
           for (int i0 = 0; i0 < 32; i0 += 4) {        // neighbour values loaded unconditionally, merged with selects (no branches)
             const float4 r4 = *reinterpret_cast<const float4*>(xr + i0);
@@ -336,6 +351,57 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
               ev[i] = __uint_as_float(raw[0][i]) * corr;
               od_[i] = (__uint_as_float(raw[1][i]) + right) * corr;
             }
+          }
+          } else {
+          // k4: accumulator column groups [P1 | P3 | P2 | P0].  The two shifted groups first (their raw values die in the shuffles),
+          // then the two aligned ones: at most 128 accumulator values are live at a time.
+          uint32_t ra[32], rb[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            tmem_ld16_nowait(trow + 1 * COUT + cg + c0, &ra[c0]);       // P3
+            tmem_ld16_nowait(trow + 3 * COUT + cg + c0, &rb[c0]);       // P0
+          }
+          tmem_ld_wait();
+          if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xb[(q * 2 + 1) * 32 + i] = __uint_as_float(ra[i]);   // P3 of this quadrant's last column
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xb[(q * 2) * 32 + i] = __uint_as_float(rb[i]);       // P0 of this quadrant's first column
+          }
+          named_bar_sync(1, 128);
+          const float* xl = has_left_q ? xb + ((q - 1) * 2 + 1) * 32 : zeros;
+          const float* xr = has_right_q ? xb + ((q + 1) * 2) * 32 : zeros;
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(xl + i0);
+            const float4 r4 = *reinterpret_cast<const float4*>(xr + i0);
+            const float le[4] = {l4.x, l4.y, l4.z, l4.w}, re[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = i0 + k;
+              const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(ra[i]), 1);      // P3 of input column m-1
+              const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rb[i]), 1);   // P0 of input column m+1
+              ev[i] = (lane == 0) ? le[k] : left;          // zero before the first input column
+              od_[i] = (lane == 31) ? re[k] : right;       // zero beyond the last one
+            }
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            tmem_ld16_nowait(trow + 0 * COUT + cg + c0, &ra[c0]);       // P1
+            tmem_ld16_nowait(trow + 2 * COUT + cg + c0, &rb[c0]);       // P2
+          }
+          tmem_ld_wait();
+          if (cg + 32 >= COUT) {                      // whole tile in registers: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&acc_empty[t]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            ev[i] = (ev[i] + __uint_as_float(ra[i])) * corr;
+            od_[i] = (od_[i] + __uint_as_float(rb[i])) * corr;
+          }
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
             // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride
@@ -363,6 +429,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
+                  if (cg + i >= p.cout_real) continue;
                   const float2 rv = __ldg(reinterpret_cast<const float2*>(p.residual + ncdhw0 + (size_t)(cg + i) * plane));
                   ev[i] += rv.x, od_[i] += rv.y;
                 }
@@ -389,7 +456,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)             // columns 2w, 2w+1 of consecutive lanes: 256 contiguous bytes per warp
-                *reinterpret_cast<float2*>(p.y + ncdhw0 + (size_t)(cg + i) * plane) = make_float2(ev[i], od_[i]);
+                if (cg + i < p.cout_real) *reinterpret_cast<float2*>(p.y + ncdhw0 + (size_t)(cg + i) * plane) = make_float2(ev[i], od_[i]);
             }
           }
         }
@@ -406,16 +473,16 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
   else if (warp == 9) {
     if (elect_one()) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w);
-      uint32_t bph[3] = {0, 0, 0};
+      uint32_t bph[KS] = {};
       for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
         const ItemDc w = decode_dc<C>(p, it);
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = 0; kd < KS; ++kd) {
           if (!kd_valid(w.od, kd, p.D)) continue;         // same phase enumeration as the MMA warp and the A loaders
           for (int ch = 0; ch < nchunk; ++ch) {
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < KS; ++kh) {
               if (!kh_valid(w.ph, kh)) continue;
-              const uint32_t slot = (bph[kh] & 1) * 3 + kh;
-              const size_t slice = ((size_t)kd * nchunk + ch) * 3 + kh;
+              const uint32_t slot = (bph[kh] & 1) * KS + kh;
+              const size_t slice = ((size_t)kd * nchunk + ch) * KS + kh;
               mbar_wait_relaxed(&b_empty[slot], ((bph[kh] >> 1) & 1) ^ 1);
               mbar_arrive_expect_tx(&b_full[slot], C::B_SLICE);
               bulk_g2s(b_buf + slot * C::B_SLICE, wsrc + slice * C::B_SLICE, C::B_SLICE, &b_full[slot]);
@@ -432,10 +499,10 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES, bool GW = false>
+template <int COUT, int KC, int W, int TILES, bool GW = false, int KS = 3>
 static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
-  using C = TcdcCfg<COUT, KC, W, TILES, GW>;
-  auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES, GW>;
+  using C = TcdcCfg<COUT, KC, W, TILES, GW, KS>;
+  auto kernel = conv3d_tcdc_kernel<COUT, KC, W, TILES, GW, KS>;
   static PerDeviceFlag configured;
   if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -446,6 +513,7 @@ static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
     configured.here() = true;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
+  if (p.cout_real <= 0 || p.cout_real > COUT) p.cout_real = COUT;
   if (GW) p.ctiles = (p.Wr + C::CSTEP - 1) / C::CSTEP;
   else p.Wr = W, p.ctiles = 1;
   const long long items = (long long)p.B * (2 * p.D) * 2 * p.hblocks * p.ctiles;
@@ -475,6 +543,32 @@ int osb_deconv3d_tc_supported(int Cin, int Cout, int W) {
   if (Cin % 16 != 0 || Cin < 16) return 0;
   if ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) return 1;                          // whole-row variants
   return (osb_tc_general_width(W) && (Cout == 32 || Cout == 64)) ? 1 : 0;                   // 128-column tiles of the INPUT row
+}
+
+int osb_deconv3d_k4_tc_supported(int Cin, int Cout, int W) {
+  if (Cin % 16 != 0 || Cin < 16) return 0;
+  return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) ? 1 : 0;
+}
+
+int osb_deconv3d_k4_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                           const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
+                           int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(x_ndhwc && w_split && y, "deconv3d_k4_tc: null pointer");
+  OSB_REQUIRE(B > 0 && D > 0 && H > 0, "deconv3d_k4_tc: empty shape");
+  OSB_REQUIRE(osb_deconv3d_k4_tc_supported(Cin, Cout, W), "deconv3d_k4_tc: unsupported shape Cin=%d Cout=%d W=%d", Cin, Cout, W);
+  OSB_REQUIRE(act >= 0 && act <= 2, "deconv3d_k4_tc: unknown activation %d", act);
+  OSB_REQUIRE(cout_real >= 1 && cout_real <= Cout && (out_ndhwc == 0 || cout_real == Cout) && (!residual || res_ndhwc == 0 || cout_real == Cout),
+              "deconv3d_k4_tc: only NCDHW tensors may hold fewer (%d) channels than the packed %d", cout_real, Cout);
+  TcdcParams p{};
+  p.cout_real = cout_real;
+  p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
+  p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
+  p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (W == 32) return launch_tcdc<64, 16, 32, 2, false, 4>(p, s);
+  return launch_tcdc<32, 16, 64, 4, false, 4>(p, s);
 }
 
 int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,

@@ -25,6 +25,7 @@ struct TcgParams {
   const float* scale;
   const float* shift;
   const float* residual;
+  const float* gate;       // optional (B, H, W, Cout) channels-last multiplier applied after the activation (FeatureAtt), NDHWC output only
   float* y;
   int B, D, H, Cin;
   int act;
@@ -332,9 +333,10 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
             }
           }
           if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
+            const ptrdiff_t gvox = ((ptrdiff_t)b * p.H + h) * Wp + col - lane;     // (B, H, W) index of lane 0's voxel
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
                                 p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act,
-                                vmask);
+                                vmask, p.gate ? p.gate + gvox * COUT + cg : nullptr);
           } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
@@ -443,9 +445,10 @@ static int launch_tcg(TcgParams& p, cudaStream_t stream) {
 
 // dispatcher used by conv3d_tc.cu's C entry point; returns -1 when the shape has no generic instantiation
 int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
-                        int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream) {
+                        int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream,
+                        const float* gate) {
   TcgParams p{};
-  p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
+  p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y, p.gate = gate;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   if (!p.overflow) return OSB_ECUDA;
@@ -453,6 +456,7 @@ int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const
   if (W == 64 && Cout == 64) return launch_tcg<64, 16, 64, 2>(p, stream);
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
+  if (W == 32 && Cout == 96) return launch_tcg<96, 16, 32, 1>(p, stream);         // StereoBase 1/16 level (4c = 96)
   if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
   // every other width: 128-column tiles with a one-column halo (tc_general_width() is the single source of the W bound)

@@ -429,7 +429,7 @@ extern "C" {
 
 int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
   if (Cin % 16 != 0 || Cin < 16 || D % 2 || H % 2 || W % 2) return 0;
-  if ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 128))) return 1;      // whole-row variants
+  if ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 96 || Cout == 128))) return 1;      // whole-row variants
   return (osb_tc_general_width(W / 2) && (Cout == 64 || Cout == 128)) ? 1 : 0;              // 128-column tiles of the OUTPUT row
 }
 
@@ -451,6 +451,7 @@ int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const flo
   if (W == 128 && Cout == 64) return launch_tcs2<64, 16, 64, 2>(p, s);
   if (W == 64 && Cout == 64) return launch_tcs2<64, 16, 32, 2>(p, s);
   if (W == 64 && Cout == 128) return launch_tcs2<128, 16, 32, 1>(p, s);
+  if (W == 64 && Cout == 96) return launch_tcs2<96, 16, 32, 1>(p, s);           // StereoBase conv2[0]: 2c -> 4c = 96
   p.Wr = W / 2;
   if (Cout == 64) return launch_tcs2<64, 16, 128, 2, true>(p, s);
   return launch_tcs2<128, 16, 128, 1, true>(p, s);

@@ -205,9 +205,11 @@ constexpr int TP_BYTES = 4 * TP_WARP_FLOATS * 4;    // four epilogue warps
 // owned by lane 0; lane k's voxel lies vstride floats further per lane.  sc / sh point at channel c of the folded BN.
 // vmask: bit k set = the voxel of lane k exists in the output (general-width column tiles mask their halo columns and the part of
 // the last tile beyond the image; whole-row tiles pass all ones and the tests fold away).
+// gate0: optional channels-last multiplier of lane 0's voxel (same voxel stride), applied AFTER the activation -- FeatureAtt's
+// sigmoid(att) * cv of stereobase/hourglass.py:80-99 / igev_blocks.py:35-48 with the gate stored as (B, H, W, C).
 __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const float (&sum)[32], float* y0, const float* res0,
                                                     size_t vstride, const float* sc, const float* sh, int act,
-                                                    uint32_t vmask = 0xffffffffu) {
+                                                    uint32_t vmask = 0xffffffffu, const float* gate0 = nullptr) {
   const int c4 = 4 * (lane & 7), sub = lane >> 3;
   __syncwarp();                                     // the previous chunk's readers are done with the tile
   float4* row = reinterpret_cast<float4*>(tbuf + lane * TP_STRIDE);
@@ -239,6 +241,14 @@ __device__ __forceinline__ void store_ndhwc_chunk32(float* tbuf, int lane, const
     for (int j = 0; j < 8; ++j) {
       o[j].x = o[j].x > 0.f ? o[j].x : 0.01f * o[j].x, o[j].y = o[j].y > 0.f ? o[j].y : 0.01f * o[j].y;
       o[j].z = o[j].z > 0.f ? o[j].z : 0.01f * o[j].z, o[j].w = o[j].w > 0.f ? o[j].w : 0.01f * o[j].w;
+    }
+  }
+  if (gate0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((vmask >> (4 * j + sub)) & 1u)) continue;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate0 + (size_t)(4 * j + sub) * vstride + c4));
+      o[j].x *= g.x, o[j].y *= g.y, o[j].z *= g.z, o[j].w *= g.w;
     }
   }
 #pragma unroll

@@ -481,11 +481,12 @@ class TcWeight:
     """A conv weight packed for the tcgen05 kernels: `data` fp16 [3 kd][Cin/kc][3 kh][3*Cout (kw-major)][kc hi | kc lo] of
     w * 2^e_c with the 16-byte chunks of every row stored in UMMA swizzle order (pack_tc_weight), and `inv` = 2^-(e_c + TC_ACT_SCALE_LOG2) per output channel -- the exact factor the epilogue must apply.
     `cout` is the packed row count per kw slice (narrow heads are zero-padded to 16), `cout_real` the layer's channels."""
-    __slots__ = ("data", "inv", "kc", "cout", "cout_real", "_eff")
+    __slots__ = ("data", "inv", "kc", "cout", "cout_real", "ksize", "_eff")
 
-    def __init__(self, data, inv, kc, cout, cout_real=None):
+    def __init__(self, data, inv, kc, cout, cout_real=None, ksize=3):
         self.data, self.inv, self.kc, self.cout, self._eff = data, inv, kc, cout, None
         self.cout_real = cout if cout_real is None else cout_real
+        self.ksize = ksize                                                  # 3, or 4 for the k4-s2 transposed conv
 
     def eff_scale(self, scale):
         """Epilogue scale vector: folded-BN scale (or 1) times the exact power-of-two un-scaling of this weight."""
@@ -499,15 +500,17 @@ class TcWeight:
 
 
 def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2), pad_cout_to=None):
-    """(Cout, Cin, 3, 3, 3) fp32 Conv3d parameter -> TcWeight (see there).  Per output channel the weights are scaled by the
-    power of two that puts max |w| into [2^14, 2^15) (exact; undone by TcWeight.inv), then split with f16_split."""
+    """(Cout, Cin, k, k, k) fp32 Conv3d parameter (k = 3, or 4 for the k4-s2 transposed conv) -> TcWeight (see there).  Per output
+    channel the weights are scaled by the power of two that puts max |w| into [2^14, 2^15) (exact; undone by TcWeight.inv), then
+    split with f16_split.  kw_order lists the kw slices in the order the kernel stacks them along N."""
     w = weight.detach().float()
     cout_real, cin = w.shape[:2]
+    k = int(w.shape[2])
     if pad_cout_to is not None and cout_real < pad_cout_to:             # narrow classifier heads ride the COUT = 16 kernel variant
         w = torch.cat((w, w.new_zeros((pad_cout_to - cout_real,) + tuple(w.shape[1:]))), 0)
     cout = w.shape[0]
     kc = TC_KC if kc is None else kc
-    assert kc in (16, 32) and cin % kc == 0 and tuple(w.shape[2:]) == (3, 3, 3)
+    assert kc in (16, 32) and cin % kc == 0 and k in (3, 4) and tuple(w.shape[2:]) == (k, k, k) and len(kw_order) == k
     amax = w.abs().amax(dim=(1, 2, 3, 4))
     _, ex = torch.frexp(amax)                                           # amax = m * 2^ex, m in [0.5, 1)
     e = torch.where(amax > 0, TC_WEIGHT_TOP_LOG2 - ex, torch.zeros_like(ex)).clamp(-40, 40)
@@ -515,41 +518,48 @@ def pack_tc_weight(weight, kc=None, kw_order=(0, 1, 2), pad_cout_to=None):
     hi, lo = f16_split(ws)
     both = torch.stack((hi, lo), 0)                                    # (2, co, ci, kd, kh, kw)
     both = both[..., list(kw_order)]                                   # stride-2 kernel wants kw slices as (1, 0, 2)
-    both = both.contiguous().view(2, cout, cin // kc, kc, 3, 3, 3)     # (half, co, chunk, ci, kd, kh, kw)
+    both = both.contiguous().view(2, cout, cin // kc, kc, k, k, k)     # (half, co, chunk, ci, kd, kh, kw)
     both = both.permute(4, 2, 5, 6, 1, 0, 3)                           # (kd, chunk, kh, kw, co, half, ci)
-    data = both.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
+    data = both.reshape(k, cin // kc, k, k * cout, 2 * kc).contiguous()
     # Pre-swizzle: the kernels copy a (kd, chunk, kh) slice into shared memory with ONE 1-D TMA bulk copy, so global memory already
     # holds the UMMA K-major swizzled layout: 16-byte chunk c of row n sits at chunk c ^ (n & 7) (128-byte rows, SWIZZLE_128B) or
     # c ^ ((n >> 1) & 3) (64-byte rows, SWIZZLE_64B) -- an XOR within the row, i.e. a gather with an involutive index.
     cpr = (2 * kc) // 8                                                 # 16-byte chunks per row (8 halfs each)
-    rows = torch.arange(3 * cout, device=data.device)
+    rows = torch.arange(k * cout, device=data.device)
     key = (rows & 7) if kc == 32 else ((rows >> 1) & 3)
     src = torch.arange(cpr, device=data.device).view(1, cpr) ^ key.view(-1, 1)              # (rows, cpr): chunk stored at position c
-    data = data.view(3, cin // kc, 3, 3 * cout, cpr, 8)
-    data = torch.gather(data, 4, src.view(1, 1, 1, 3 * cout, cpr, 1).expand(3, cin // kc, 3, 3 * cout, cpr, 8).contiguous())
-    data = data.reshape(3, cin // kc, 3, 3 * cout, 2 * kc).contiguous()
+    data = data.view(k, cin // kc, k, k * cout, cpr, 8)
+    data = torch.gather(data, 4, src.view(1, 1, 1, k * cout, cpr, 1).expand(k, cin // kc, k, k * cout, cpr, 8).contiguous())
+    data = data.reshape(k, cin // kc, k, k * cout, 2 * kc).contiguous()
     inv = torch.ldexp(torch.ones_like(amax), -(e + TC_ACT_SCALE_LOG2))
-    return TcWeight(data, inv.contiguous(), kc, cout, cout_real)
+    return TcWeight(data, inv.contiguous(), kc, cout, cout_real, ksize=k)
 
 
 def _tc_args(w_split, cin, kc, scale):
     assert isinstance(w_split, TcWeight) and w_split.kc == kc
-    assert tuple(w_split.data.shape) == (3, cin // kc, 3, 3 * w_split.cout, 2 * kc) and w_split.data.dtype == torch.float16
+    k = w_split.ksize
+    assert tuple(w_split.data.shape) == (k, cin // kc, k, k * w_split.cout, 2 * kc) and w_split.data.dtype == torch.float16
     assert w_split.data.is_contiguous() and w_split.data.is_cuda
     return w_split.data.data_ptr(), w_split.eff_scale(scale)
 
 
-def to_ndhwc(x):
-    """(B,C,D,H,W) -> (B,D,H,W,C) contiguous fp32, on the device."""
+def to_ndhwc(x, pad_to=None):
+    """(B,C,D,H,W) -> (B,D,H,W,C) contiguous fp32, on the device; pad_to > C appends zero channels (channel plans that are not
+    multiples of 16 run on the tensor-core kernels zero-padded)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
     b, c, d, h, w = x.shape
-    y = torch.empty((b, d, h, w, c), dtype=torch.float32, device=x.device)
-    _call("osb_ncdhw_to_ndhwc", x.data_ptr(), y.data_ptr(), b, c, d, h, w, _stream(y))
+    cp = c if pad_to is None else int(pad_to)
+    assert cp >= c
+    y = torch.empty((b, d, h, w, cp), dtype=torch.float32, device=x.device)
+    if cp == c:
+        _call("osb_ncdhw_to_ndhwc", x.data_ptr(), y.data_ptr(), b, c, d, h, w, _stream(y))
+    else:
+        _call("osb_ncdhw_to_ndhwc_pad", x.data_ptr(), y.data_ptr(), b, c, cp, d, h, w, _stream(y))
     return y
 
 
 def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=True, res_ndhwc=True,
-                 in_ncdhw=False):
+                 in_ncdhw=False, gate=None):
     """3x3x3 stride-1 conv + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin), or the NCDHW
     tensor (B,Cin,D,H,W) with in_ncdhw=True (W = 128 layers only: the cost volume goes in as the volume kernel wrote it)."""
     assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
@@ -569,6 +579,12 @@ def conv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=AC
         want = (b, d, h, w, cout) if res_ndhwc else (b, cout, d, h, w)
         assert tuple(residual.shape) == want and residual.is_contiguous()
     assert not in_ncdhw or kc == 32
+    if gate is not None:                                                     # FeatureAtt: (B,H,W,Cout) multiplier after the activation
+        assert kc == 16 and out_ndhwc and res_ndhwc and not in_ncdhw
+        assert tuple(gate.shape) == (b, h, w, cout) and gate.is_contiguous() and gate.dtype == torch.float32 and gate.is_cuda
+        _call("osb_conv3d_k3_tc_gate_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual), gate.data_ptr(),
+              y.data_ptr(), b, cin, cout, d, h, w, act, _stream(y))
+        return y
     _call("osb_conv3d_k3_tc_ncdhw_fwd" if in_ncdhw else "osb_conv3d_k3_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
           y.data_ptr(), b, cin, cout, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
     return y
@@ -602,8 +618,48 @@ def deconv3d_tc_supported(cin, cout, w):
 
 def pack_tc_deconv_weight(weight):
     """(Cin, Cout, 3, 3, 3) ConvTranspose3d parameter -> TcWeight, 16-channel chunks, kw slices ordered (1, 2, 0):
-    even output columns come from tap 1, odd ones from taps 2 (same input column) and 0 (next input column)."""
-    return pack_tc_weight(weight.detach().float().permute(1, 0, 2, 3, 4).contiguous(), 16, kw_order=(1, 2, 0))
+    even output columns come from tap 1, odd ones from taps 2 (same input column) and 0 (next input column).
+    (Cin, Cout, 4, 4, 4) (k4 s2 p1): kw slices (1, 3, 2, 0) -- even columns taps 1 (same input column) and 3 (previous one), odd
+    columns taps 2 (same) and 0 (next)."""
+    w = weight.detach().float().permute(1, 0, 2, 3, 4).contiguous()
+    return pack_tc_weight(w, 16, kw_order=(1, 2, 0) if w.shape[2] == 3 else (1, 3, 2, 0))
+
+
+def deconv3d_k4_tc_supported(cin, cout, w):
+    return bool(_lib.lib.osb_deconv3d_k4_tc_supported(int(cin), int(cout), int(w)))
+
+
+def deconv3d_k4_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=True, res_ndhwc=True,
+                   cout_real=None):
+    """ConvTranspose3d(k4, s2, p1) + folded BN + residual + activation on the tensor cores.  x_ndhwc: (B,D,H,W,Cin); cout_real <
+    packed Cout (zero-padded channel plan) is allowed for an NCDHW output, which then holds only the real channels."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    cout = w_split.cout
+    creal = cout if cout_real is None else int(cout_real)
+    assert w_split.ksize == 4 and (out_ndhwc is False or creal == cout)
+    wptr, scale = _tc_args(w_split, cin, 16, scale)
+    shape = (b, 2 * d, 2 * h, 2 * w, cout) if out_ndhwc else (b, creal, 2 * d, 2 * h, 2 * w)
+    y = torch.empty(shape, dtype=torch.float32, device=x_ndhwc.device)
+    if residual is not None:
+        want = (b, 2 * d, 2 * h, 2 * w, cout) if res_ndhwc else (b, creal, 2 * d, 2 * h, 2 * w)
+        assert tuple(residual.shape) == want and residual.is_contiguous()
+    _call("osb_deconv3d_k4_tc_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), _ptr(residual),
+          y.data_ptr(), b, cin, cout, creal, d, h, w, act, 1 if out_ndhwc else 0, 1 if res_ndhwc else 0, _stream(y))
+    return y
+
+
+def conv1x1_ndhwc_cat(x0, x1, w_packed, scale=None, shift=None, act=ACT_NONE):
+    """Channels-last 1x1x1 conv over torch.cat((x0, x1), -1) without materialising it: (..., C0), (..., C1) -> (..., Cout);
+    w_packed (C0 + C1, Cout)."""
+    assert x0.is_cuda and x0.dtype == torch.float32 and x0.is_contiguous() and x1.is_contiguous() and x0.shape[:-1] == x1.shape[:-1]
+    c0, c1 = x0.shape[-1], x1.shape[-1]
+    cin, cout = w_packed.shape
+    assert cin == c0 + c1 and w_packed.is_contiguous()
+    y = torch.empty(x0.shape[:-1] + (cout,), dtype=torch.float32, device=x0.device)
+    _call("osb_conv1x1_ndhwc_cat_fwd", x0.data_ptr(), x1.data_ptr(), c0, c1, w_packed.data_ptr(), _ptr(scale), _ptr(shift),
+          y.data_ptr(), x0.numel() // c0, cout, act, _stream(y))
+    return y
 
 
 def deconv3d_k3_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=ACT_NONE, out_ndhwc=False, res_ndhwc=False):
