@@ -193,11 +193,22 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const floa
  * (stereobase/hourglass.py:35-60 conv3_up / conv2_up / conv1_up): x (B,D,H,W,Cin) channels-last -> y (B,2D,2H,2W,Cout) channels-last
  * or (B,cout_real,2D,2H,2W).  w_split = ops.pack_tc_deconv_weight of the (Cin,Cout,4,4,4) parameter, kw slices stored as (1,3,2,0).
  * Cout is the PACKED channel count (zero-padded channel plans: 24 -> 32, 48 -> 64); cout_real <= Cout real channels are written /
- * added when the output / residual is NCDHW.  Supported: W=32/Cout=64, W=64/Cout=32. */
+ * added when the output / residual is NCDHW.  Supported: W=32/Cout=64, W=64/Cout=32, W=16/Cout=64|32. */
 int osb_deconv3d_k4_tc_supported(int Cin, int Cout, int W);
 int osb_deconv3d_k4_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                            const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
                            int out_ndhwc, int res_ndhwc, osb_stream_t stream);
+/* Channel-SLICE variants (suffix _cs): the launch computes Cout consecutive channels of a wider channels-last tensor whose voxels
+ * hold `ystride` >= Cout floats; y (and residual / gate_nhwc) point at the slice's first channel.  Channel plans whose kw-stacked
+ * N = 3*Cout (4*Cout for the k4 transposed conv) exceeds what one CTA can hold -- StereoBase's 6c = 144 (run as 160 = 96 + 64) --
+ * are produced by two launches over output-channel slices of separately packed weights.  Channels-last in and out. */
+int osb_conv3d_k3_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, const float* residual,
+                            const float* gate_nhwc, float* y, int B, int Cin, int Cout, int D, int H, int W, int act, int ystride,
+                            osb_stream_t stream);
+int osb_conv3d_k3_s2_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, float* y, int B,
+                               int Cin, int Cout, int D, int H, int W, int act, int ystride, osb_stream_t stream);
+int osb_deconv3d_k4_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, float* y, int B,
+                              int Cin, int Cout, int D, int H, int W, int act, int ystride, osb_stream_t stream);
 /* Channels-last 1x1x1 conv over the channel concatenation of two tensors (torch.cat((up, skip), 1) -> Conv3d(k=1) of
  * stereobase/hourglass.py:91-92,96-97, never materialised): x0 (voxels,C0), x1 (voxels,C1) or NULL -> y (voxels,Cout);
  * w_packed (C0+C1, Cout).  192 -> 96 and 128 -> 64. */
@@ -283,6 +294,12 @@ int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int
 /* Same with the channel axis zero-padded to Cpad >= C: y (B,D,H,W,Cpad) -- channel plans that are not multiples of 16 (StereoBase's
  * 24 / 48) run on the tensor-core kernels as 32 / 64 with zero weights on the padding. */
 int osb_ncdhw_to_ndhwc_pad(const float* x, float* y, int B, int C, int Cpad, int D, int H, int W, osb_stream_t stream);
+/* FeatureAtt gate in one launch (igev_blocks.py:35-48 as used by stereobase/hourglass.py:62-99):
+ * gate_nhwc (B,H,W,Cpad) = sigmoid(conv1x1(act1(bn(conv1x1(feat_nchw (B,Cf,H,W)))))), channels Cv..Cpad-1 zero.
+ * w1_packed (Cf,Ch), w2_packed (Ch,Cv); scale/shift = folded BN / bias (NULL = identity).  HW = H*W. */
+int osb_feature_att_gate_fwd(const float* feat_nchw, const float* w1_packed, const float* scale1, const float* shift1,
+                             const float* w2_packed, const float* scale2, const float* shift2, float* gate_nhwc, int B,
+                             int Cf, int Ch, int Cv, int Cpad, int HW, int act1, osb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -37,8 +37,12 @@ SIGNATURES = {
     "osb_conv3d_k3_tc_ncdhw_fwd": [_f32p] * 6 + [_i] * 9 + [_s],
     "osb_conv3d_k3_tc_gate_fwd": [_f32p] * 7 + [_i] * 7 + [_s],
     "osb_deconv3d_k4_tc_supported": [_i, _i, _i],
+    "osb_conv3d_k3_tc_cs_fwd": [_f32p] * 7 + [_i] * 8 + [_s],
+    "osb_conv3d_k3_s2_tc_cs_fwd": [_f32p] * 5 + [_i] * 8 + [_s],
+    "osb_deconv3d_k4_tc_cs_fwd": [_f32p] * 5 + [_i] * 8 + [_s],
     "osb_deconv3d_k4_tc_fwd": [_f32p] * 6 + [_i] * 10 + [_s],
     "osb_conv1x1_ndhwc_cat_fwd": [_f32p, _f32p, _i, _i, _f32p, _f32p, _f32p, _f32p, ctypes.c_longlong, _i, _i, _s],
+    "osb_feature_att_gate_fwd": [_f32p] * 8 + [_i] * 7 + [_s],
     "osb_ncdhw_to_ndhwc_pad": [_f32p, _f32p, _i, _i, _i, _i, _i, _i, _s],
     "osb_conv1x1_ndhwc_fwd": [_f32p] * 5 + [ctypes.c_longlong, _i, _i, _i, _s],
     "osb_conv3d_k3_c1_ndhwc_fwd": [_f32p] * 5 + [_i] * 5 + [_s],

@@ -346,6 +346,7 @@ class _FeatureAtt:
         blk = m.feat_att[0].block
         self.a = _Packed(blk[0], blk[1])
         self.b = _Packed(m.feat_att[1])
+        self.act = ACT_LEAKY if any(isinstance(l, torch.nn.LeakyReLU) for l in blk) else ACT_NONE
 
     def __call__(self, feat):
         hidden = ops.conv3d_1x1(feat, self.a.w, self.a.scale, self.a.shift, act=ACT_LEAKY)
@@ -444,12 +445,46 @@ class StereoBaseAggregation(_Engine):
             t[name] = (cat1x1(l0), conv(l1), conv(l2))
         for name in ("conv2_up", "conv1_up"):
             t[name] = deconv(self.up[name][0])
+        # 1/32 level: 6c = 144 runs as 160 = 96 + 64 output-channel slices (N = 3 * 160 exceeds one CTA's weight buffers), the
+        # transposed conv back to 4c = 96 as 64 + 32 (N = 4 * 96 exceeds the UMMA N limit): separately packed weight slices
+        (l0, _), (l1, _) = self.conv["conv3"]
+        lu = self.up["conv3_up"][0]
+        if P(l0.cout) == 160 and P(l0.cin) == 96 and lu.kernel == 4 and all(l._w5 is not None for l in (l0, l1, lu)):
+            def slices(layer, bounds, transposed=False, kw_order=(0, 1, 2)):
+                w = layer._w5
+                if transposed:                                              # (Cin, Cout, 4, 4, 4): pad Cin, slice Cout
+                    wp = w.new_zeros((P(w.shape[0]), P(w.shape[1])) + tuple(w.shape[2:]))
+                    wp[:w.shape[0], :w.shape[1]] = w
+                    n = wp.shape[1]
+                else:
+                    wp = w.new_zeros((P(w.shape[0]), P(w.shape[1])) + tuple(w.shape[2:]))
+                    wp[:w.shape[0], :w.shape[1]] = w
+                    n = wp.shape[0]
+                sc, sh = vec(layer.scale, n, 1.0), vec(layer.shift, n, 0.0)
+                out = []
+                for lo, hi in bounds:
+                    wt = (ops.pack_tc_deconv_weight(wp[:, lo:hi].contiguous()) if transposed
+                          else ops.pack_tc_weight(wp[lo:hi].contiguous(), 16, kw_order=kw_order))
+                    out.append((lo, wt, None if sc is None else sc[lo:hi].contiguous(), None if sh is None else sh[lo:hi].contiguous()))
+                return out
+            t["conv3"] = (slices(l0, ((0, 96), (96, 160)), kw_order=(1, 0, 2)), slices(l1, ((0, 96), (96, 160))))
+            t["conv3_up"] = slices(lu, ((0, 64), (64, 96)), transposed=True)
         self._tcp, self._tcp_stamp = t, self._stamp
         return t
 
+    def _level32_tc_ok(self, shape):
+        b, c, d, h, w = shape
+        return bool(w // 8 == 16 and self._pad32(6 * c) == 160 and self._pad32(4 * c) == 96
+                    and ops.conv3d_s2_tc_supported(96, 96, d // 4, h // 4, w // 4) and ops.conv3d_s2_tc_supported(96, 64, d // 4, h // 4, w // 4)
+                    and ops.conv3d_tc_kc(160, 96, 16) == 16 and ops.conv3d_tc_kc(160, 64, 16) == 16
+                    and ops.deconv3d_k4_tc_supported(160, 64, 16) and ops.deconv3d_k4_tc_supported(160, 32, 16))
+
     def _gate_nhwc(self, name, feat, channels):
-        g = self.att[name](feat)                                            # (B, C, H, W) sigmoid gate
-        return ops.to_ndhwc(g.unsqueeze(2), pad_to=channels).squeeze(1)     # (B, H, W, C padded): padded channels are 0
+        fa = self.att[name]                                                 # one launch: (B, H, W, C padded), padded channels 0
+        if fa.a.w.shape[1] % 4 == 0 and fa.b.w.shape[1] % 4 == 0:
+            return ops.feature_att_gate(feat, fa.a.w, fa.a.scale, fa.a.shift, fa.b.w, fa.b.scale, fa.b.shift, pad_to=channels,
+                                        act1=fa.act)
+        return ops.to_ndhwc(fa(feat).unsqueeze(2), pad_to=channels).squeeze(1)
 
     def _call_tc(self, x, feats):
         t = self._tc_pack()
@@ -463,11 +498,26 @@ class StereoBaseAggregation(_Engine):
         (w0, sc0, sh0), (w1, sc1, sh1) = t["conv2"]
         c2 = ops.conv3d_k3_s2_tc(conv1, w0, sc0, sh0, None, act("conv2", 0), out_ndhwc=True)
         conv2 = ops.conv3d_k3_tc(c2, w1, sc1, sh1, None, act("conv2", 1), gate=self._gate_nhwc("16", feats[2], p4))
-        # 1/32 level on the fp32 CUDA-core kernels (NCDHW): 6 % of the MACs, 768 voxels per pair at config 3
-        conv2_ncdhw = conv2[..., :4 * c].permute(0, 4, 1, 2, 3).contiguous()
-        conv3 = self._pair("conv3", conv2_ncdhw, self.att["32"](feats[3]))
-        l, a = self.up["conv3_up"]
-        up3 = ops.to_ndhwc(_deconv(l, conv3, a), pad_to=p4)
+        if "conv3" in t and self._level32_tc_ok(x.shape):
+            # 1/32 level (768 voxels per pair at config 3: one 8 x 16 plane = one M tile) as output-channel slices
+            b, d4, h4, w4, _ = conv2.shape
+            s0, s1 = t["conv3"]
+            y = conv2.new_empty((b, d4 // 2, h4 // 2, w4 // 2, 160))
+            for lo, wt, sc, sh in s0:
+                ops.tc_slice("s2", conv2, wt, sc, sh, y, lo, act("conv3", 0))
+            g32 = self._gate_nhwc("32", feats[3], 160)
+            conv3 = torch.empty_like(y)
+            for lo, wt, sc, sh in s1:
+                ops.tc_slice("s1", y, wt, sc, sh, conv3, lo, act("conv3", 1), gate=g32)
+            up3 = conv2.new_empty((b, d4, h4, w4, p4))
+            for lo, wt, sc, sh in t["conv3_up"]:
+                ops.tc_slice("dc4", conv3, wt, sc, sh, up3, lo, self.up["conv3_up"][1])
+        else:
+            # 1/32 level on the fp32 CUDA-core kernels (NCDHW): 6 % of the MACs
+            conv2_ncdhw = conv2[..., :4 * c].permute(0, 4, 1, 2, 3).contiguous()
+            conv3 = self._pair("conv3", conv2_ncdhw, self.att["32"](feats[3]))
+            l, a = self.up["conv3_up"]
+            up3 = ops.to_ndhwc(_deconv(l, conv3, a), pad_to=p4)
         (wc, scc, shc), (w1, sc1, sh1), (w2, sc2, sh2) = t["agg_0"]
         y = ops.conv1x1_ndhwc_cat(up3, conv2, wc, scc, shc, act("agg_0", 0))
         y = ops.conv3d_k3_tc(y, w1, sc1, sh1, None, act("agg_0", 1))
@@ -513,7 +563,23 @@ class StereoBaseCostHead(_Engine):
     def __call__(self, geo, maxdisp_lowres):
         geo = self._check(geo)
         self._ensure(geo.device)
-        logits = _conv(self.layer, geo)                         # (B,1,D',H',W')
+        lay = self.layer
+        cp = (lay.cin + 31) // 32 * 32
+        if (USE_TENSOR_CORES and lay.cout == 1 and lay._w5 is not None and lay.kernel == 3 and lay.stride == 1
+                and ops.conv3d_tc_kc(cp, 1, geo.shape[-1]) == 32):
+            # 24 -> 1 head on the narrow tensor-core variant: channels zero-padded to 32 while the layout changes (one pass), the
+            # generic CUDA-core conv took 0.71 ms at config 3 (profiles/r2_c3_launches.csv)
+            if "head" not in lay._tc:
+                w = lay._w5.new_zeros((1, cp) + tuple(lay._w5.shape[2:]))
+                w[:, :lay.cin] = lay._w5
+                lay._tc["head"] = ops.pack_tc_weight(w, 32, pad_cout_to=16)
+            mon = self._watch(geo.device)
+            logits = ops.conv3d_k3_tc(ops.to_ndhwc(geo, pad_to=cp), lay._tc["head"], lay.scale, lay.shift, None, ACT_NONE,
+                                      out_ndhwc=False, res_ndhwc=False)
+            if mon is not None:
+                mon.poll()
+        else:
+            logits = _conv(lay, geo)                            # (B,1,D',H',W')
         return ops.softargmin(logits.squeeze(1), maxdisp_lowres, keepdim=True)
 
 

@@ -653,10 +653,11 @@ static bool aligned16(const void* q) { return q == nullptr || (reinterpret_cast<
 
 // ------------------------------------------------------------------------------- channels-last 1x1 conv over two channel slabs
 // StereoBase's agg_0[0] / agg_1[0] (stereobase/hourglass.py:91-92,96-97): Conv3d(k=1) on torch.cat((up, skip), 1) without
-// materialising the concat, channels-last in and out: x0 (V, C0) and x1 (V, CIN - C0) -> y (V, COUT).  A warp owns 32 voxels: their
-// CIN channels are staged in a shared-memory tile by coalesced float4 loads (both slabs), one thread then multiplies one voxel's row
-// with the (Cin, Cout) weight matrix (warp-uniform __ldg: L1 broadcast) 16 output channels at a time, and the outputs leave
-// through the same tile so that the stores are coalesced.  0.34 GMAC per pair at BASELINE config 3: HBM/latency bound, not FMA bound.
+// materialising the concat, channels-last in and out: x0 (V, C0) and x1 (V, CIN - C0) -> y (V, COUT).  Persistent CTAs of 4 warps;
+// the (Cin, Cout) weight matrix sits in shared memory for the CTA's lifetime; a CTA tile is 128 voxels staged by coalesced float4
+// loads of both slabs.  Thread (warp w, lane l) owns voxels l, l+32, l+64, l+96 and the output channels [w, w+1) * COUT/4: per
+// four input channels it issues 4 LDS.128 of activations and COUT/4 broadcast LDS.128 of weights for 4 * COUT FMAs (FMA-bound, not
+// LSU-bound: the first version -- one voxel per thread, weights through L1 -- ran at 2.4 TFLOP/s).  Outputs leave through the tile.
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(128) conv1x1_ndhwc_cat_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0,
                                                                const float* __restrict__ w, const float* __restrict__ scale,
@@ -664,17 +665,27 @@ __global__ void __launch_bounds__(128) conv1x1_ndhwc_cat_kernel(const float* __r
                                                                int act) {
   constexpr int TS = CIN + 4;                       // tile row stride (floats): LDS.128 of a quarter warp hit distinct bank groups
   constexpr int F4 = CIN / 4, O4 = COUT / 4;
-  static_assert(COUT <= CIN && CIN % 4 == 0 && COUT % 16 == 0, "the output rides the input tile");
+  constexpr int NC = COUT / 4;                      // output channels per warp
+  static_assert(COUT <= CIN && CIN % 4 == 0 && NC % 4 == 0, "the output rides the input tile; a warp owns whole float4s");
   extern __shared__ __align__(16) float cat_smem[];
+  float* ws = cat_smem;                             // [CIN][COUT]
+  float* tl = cat_smem + CIN * COUT;                // [128][TS]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tl = cat_smem + warp * 32 * TS;
+  for (int i = threadIdx.x; i < CIN * COUT / 4; i += 128) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   const int c0f4 = C0 / 4, C1 = CIN - C0;
-  const size_t ngroups = (V + 31) / 32;
-  for (size_t g = (size_t)blockIdx.x * 4 + warp; g < ngroups; g += (size_t)gridDim.x * 4) {
-    const size_t v0 = g * 32;
-    const int nv = (int)min((size_t)32, V - v0);
-    __syncwarp();
-    for (int f = lane; f < 32 * F4; f += 32) {
+  const int cbase = warp * NC;
+  float sc[NC], sh[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    sc[j] = scale ? __ldg(scale + cbase + j) : 1.f;
+    sh[j] = shift ? __ldg(shift + cbase + j) : 0.f;
+  }
+  const size_t ntiles = (V + 127) / 128;
+  for (size_t g = blockIdx.x; g < ntiles; g += gridDim.x) {
+    const size_t v0 = g * 128;
+    const int nv = (int)min((size_t)128, V - v0);
+    __syncthreads();                                // the previous tile's stores have read the tile (first pass: weights staged)
+    for (int f = threadIdx.x; f < 128 * F4; f += 128) {
       const int vox = f / F4, ch = f % F4;
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       if (vox < nv)
@@ -682,41 +693,51 @@ __global__ void __launch_bounds__(128) conv1x1_ndhwc_cat_kernel(const float* __r
                       : __ldg(reinterpret_cast<const float4*>(x1 + (v0 + vox) * C1) + (ch - c0f4));
       *reinterpret_cast<float4*>(tl + vox * TS + 4 * ch) = t;
     }
-    __syncwarp();
-    float out[COUT];
-#pragma unroll 1
-    for (int c0 = 0; c0 < COUT; c0 += 16) {
-      float acc[16];
+    __syncthreads();
+    float acc[4][NC];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[v][j] = 0.f;
 #pragma unroll 2
-      for (int ci = 0; ci < CIN; ci += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(tl + lane * TS + ci);
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    for (int ci = 0; ci < CIN; ci += 4) {
+      float xs[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4* wr = reinterpret_cast<const float4*>(w + (size_t)(ci + k) * COUT + c0);
+      for (int v = 0; v < 4; ++v) {
+        const float4 t = *reinterpret_cast<const float4*>(tl + (lane + 32 * v) * TS + ci);
+        xs[v][0] = t.x, xs[v][1] = t.y, xs[v][2] = t.z, xs[v][3] = t.w;
+      }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t = __ldg(wr + q);
-            acc[4 * q + 0] = fmaf(xs[k], t.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xs[k], t.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xs[k], t.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xs[k], t.w, acc[4 * q + 3]);
+      for (int k = 0; k < 4; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + (ci + k) * COUT + cbase);
+#pragma unroll
+        for (int q = 0; q < NC / 4; ++q) {
+          const float4 t = wr[q];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[v][4 * q + 0] = fmaf(xs[v][k], t.x, acc[v][4 * q + 0]);
+            acc[v][4 * q + 1] = fmaf(xs[v][k], t.y, acc[v][4 * q + 1]);
+            acc[v][4 * q + 2] = fmaf(xs[v][k], t.z, acc[v][4 * q + 2]);
+            acc[v][4 * q + 3] = fmaf(xs[v][k], t.w, acc[v][4 * q + 3]);
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        out[c0 + j] = activate(fmaf(acc[j], scale ? __ldg(scale + c0 + j) : 1.f, shift ? __ldg(shift + c0 + j) : 0.f), act);
     }
-    __syncwarp();                                   // every lane has read its input row: the tile can take the outputs
+    __syncthreads();                                // every warp has read its input rows: the tile can take the outputs
 #pragma unroll
-    for (int q = 0; q < O4; ++q)
-      *reinterpret_cast<float4*>(tl + lane * TS + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-    __syncwarp();
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        float4 o;
+        o.x = activate(fmaf(acc[v][4 * q + 0], sc[4 * q + 0], sh[4 * q + 0]), act);
+        o.y = activate(fmaf(acc[v][4 * q + 1], sc[4 * q + 1], sh[4 * q + 1]), act);
+        o.z = activate(fmaf(acc[v][4 * q + 2], sc[4 * q + 2], sh[4 * q + 2]), act);
+        o.w = activate(fmaf(acc[v][4 * q + 3], sc[4 * q + 3], sh[4 * q + 3]), act);
+        *reinterpret_cast<float4*>(tl + (lane + 32 * v) * TS + cbase + 4 * q) = o;
+      }
+    __syncthreads();
     float4* dst = reinterpret_cast<float4*>(y + v0 * COUT);
-    for (int f = lane; f < 32 * O4; f += 32) {
+    for (int f = threadIdx.x; f < 128 * O4; f += 128) {
       const int vox = f / O4, ch = f % O4;
       if (vox < nv) dst[f] = *reinterpret_cast<const float4*>(tl + vox * TS + 4 * ch);
     }
@@ -726,7 +747,8 @@ __global__ void __launch_bounds__(128) conv1x1_ndhwc_cat_kernel(const float* __r
 template <int CIN, int COUT>
 static int launch_conv1x1_cat(const float* x0, const float* x1, int C0, const float* w, const float* scale, const float* shift, float* y,
                               long long voxels, int act, cudaStream_t s) {
-  constexpr size_t smem = (size_t)4 * 32 * (CIN + 4) * sizeof(float);
+  constexpr size_t smem = ((size_t)CIN * COUT + (size_t)128 * (CIN + 4)) * sizeof(float);
+  static_assert(smem <= 232448, "shared memory budget of one CTA exceeded");
   auto kernel = conv1x1_ndhwc_cat_kernel<CIN, COUT>;
   static PerDeviceFlag configured;
   if (!configured.here()) {
@@ -737,8 +759,9 @@ static int launch_conv1x1_cat(const float* x0, const float* x1, int C0, const fl
     }
     configured.here() = true;
   }
-  const long long groups = (voxels + 31) / 32;
-  const unsigned blocks = (unsigned)std::min<long long>((groups + 3) / 4, (long long)sm_count() * 2);
+  const long long tiles = (voxels + 127) / 128;
+  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  const unsigned blocks = (unsigned)std::min<long long>(tiles, (long long)sm_count() * per_sm);
   kernel<<<blocks, 128, smem, s>>>(x0, x1, C0, w, scale, shift, y, (size_t)voxels, act);
   count_launch();
   return check_launch("conv1x1_ndhwc_cat_kernel");

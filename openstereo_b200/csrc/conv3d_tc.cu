@@ -542,7 +542,7 @@ static int launch_tc(const TcParams& p, cudaStream_t stream) {
 
 int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream,
-                        const float* gate = nullptr);
+                        const float* gate = nullptr, int ystride = 0);
 int launch_tcg_dilated2(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream);
 
@@ -560,7 +560,7 @@ int osb_conv3d_tc_kc(int Cin, int Cout, int W, int stride) {
   if (W == osb::TC_W && (Cout == 32 || (Cout >= 1 && Cout <= 16)) && Cin % 32 == 0 && Cin >= 32) return 32;   // conv3d_tc.cu (narrow
                                                                                                // heads: weights zero-padded to 16 rows)
   if (Cin % 16 == 0 && Cin >= 16 &&
-      ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 96 || Cout == 128)) ||
+      ((W == 64 && Cout == 64) || (W == 32 && (Cout == 64 || Cout == 96 || Cout == 128)) || (W == 16 && (Cout == 64 || Cout == 96)) ||
        (W == osb::TC_W && (Cout == 64 || Cout == 128))))
     return 16;                                                                                  // conv3d_tcg.cu
   if (Cin % 16 == 0 && Cin >= 16 && osb_tc_general_width(W) && (Cout == 32 || Cout == 64 || Cout == 128))
@@ -587,7 +587,8 @@ int osb_ncdhw_to_ndhwc(const float* x, float* y, int B, int C, int D, int H, int
 
 static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                              const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
-                             int out_ndhwc, int res_ndhwc, int in_ncdhw, osb_stream_t stream, const float* gate = nullptr) {
+                             int out_ndhwc, int res_ndhwc, int in_ncdhw, osb_stream_t stream, const float* gate = nullptr,
+                             int ystride = 0) {
   using namespace osb;
   OSB_REQUIRE(x_ndhwc && w_split && y, "conv3d_k3_tc: null pointer");
   OSB_REQUIRE(B > 0 && D > 0 && H > 0, "conv3d_k3_tc: empty shape");
@@ -597,12 +598,15 @@ static int conv3d_k3_tc_impl(const float* x_ndhwc, const void* w_split, const fl
                   (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
               "conv3d_k3_tc: pointers must be 16-byte aligned");
   OSB_REQUIRE(!in_ncdhw || osb_conv3d_tc_kc(Cin, Cout, W, 1) == 32, "conv3d_k3_tc: NCDHW input is served by the W = 128 kernel only");
+  OSB_REQUIRE(ystride == 0 || (ystride >= Cout && ystride % 4 == 0 && osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16 && out_ndhwc &&
+                                (!residual || res_ndhwc)),
+              "conv3d_k3_tc: a channel slice (ystride %d) needs channels-last tensors on the 16-channel-chunk kernels", ystride);
   OSB_REQUIRE(!gate || (osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16 && out_ndhwc && (!residual || res_ndhwc) &&
                         (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
               "conv3d_k3_tc: the gate operand needs a channels-last output (and residual) on the 16-channel-chunk kernels");
   if (osb_conv3d_tc_kc(Cin, Cout, W, 1) == 16)
     return launch_tcg_dispatch(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc,
-                               (cudaStream_t)stream, gate);
+                               (cudaStream_t)stream, gate, ystride);
   TcParams p{};
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.Cout = Cout, p.act = act;
@@ -635,6 +639,12 @@ int osb_conv3d_k3_tc_gate_fwd(const float* x_ndhwc, const void* w_split, const f
                               int act, osb_stream_t stream) {
   OSB_REQUIRE(gate_nhwc, "conv3d_k3_tc_gate: null gate");
   return conv3d_k3_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, 1, 1, 0, stream, gate_nhwc);
+}
+
+int osb_conv3d_k3_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, const float* residual,
+                            const float* gate_nhwc, float* y, int B, int Cin, int Cout, int D, int H, int W, int act, int ystride,
+                            osb_stream_t stream) {
+  return conv3d_k3_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, 1, 1, 0, stream, gate_nhwc, ystride);
 }
 
 int osb_conv3d_k3_tc_ncdhw_fwd(const float* x_ncdhw, const void* w_split, const float* scale, const float* shift,

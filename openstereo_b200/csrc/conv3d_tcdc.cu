@@ -34,6 +34,7 @@ struct TcdcParams {
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
   int Wr, ctiles;          // general-width instantiations: INPUT width and column tiles per row (whole-row kernels: W, 1)
+  int ystride;             // channels per voxel of the channels-last y / residual (0 = COUT); > COUT: this launch writes a channel slice
   int cout_real;           // channels of an NCDHW output / residual (<= COUT: zero-padded channel plans write only the real ones)
 };
 
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // INPUT width (the output is 2 * Wp wide)
+  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
         if (live && cvalid && p.residual && p.res_ndhwc) {
           // the residual streams from HBM: start pulling this thread's two voxels (2*COUT floats, contiguous) into L2 while
           // the tile is still being accumulated, so the loads after the transpose do not expose the DRAM latency per tile
-          const float* rp = p.residual + vox * COUT;
+          const float* rp = p.residual + vox * YS;
 #pragma unroll
           for (int k = 0; k < 2 * COUT; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k));
         }
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
               const int i = i0 + k;
               float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), 1);   // P0 of input column m+1
               right = (lane == 31) ? re[k] : right;                                        // zero beyond the last input column
+              if (W < 32) right = (wcol == W - 1) ? 0.f : right;                           // row seams inside the warp
               ev[i] = __uint_as_float(raw[0][i]) * corr;
               od_[i] = (__uint_as_float(raw[1][i]) + right) * corr;
             }
@@ -385,6 +388,10 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
               const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rb[i]), 1);   // P0 of input column m+1
               ev[i] = (lane == 0) ? le[k] : left;          // zero before the first input column
               od_[i] = (lane == 31) ? re[k] : right;       // zero beyond the last one
+              if (W < 32) {                                // row seams inside the warp are image edges
+                ev[i] = (wcol == 0) ? 0.f : ev[i];
+                od_[i] = (wcol == W - 1) ? 0.f : od_[i];
+              }
             }
           }
 #pragma unroll
@@ -403,12 +410,14 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
             od_[i] = (od_[i] + __uint_as_float(rb[i])) * corr;
           }
           }
-          if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
+          // coalesced channels-last path (BN/residual/act inside); W < 32: the warp's two input rows map to output rows that are
+          // not adjacent in memory -> per-thread stores below
+          if (W >= 32 && live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {
             // lane k owns output voxels (vox0 + 2k) and (vox0 + 2k + 1): two transposes with a 2-voxel lane stride
-            float* y0 = p.y + (vox - 2 * lane) * COUT + cg;
-            const float* r0 = p.residual ? p.residual + (vox - 2 * lane) * COUT + cg : nullptr;
-            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, ev, y0, r0, 2 * COUT, s_scale + cg, s_shift + cg, p.act, vmask);
-            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, od_, y0 + COUT, r0 ? r0 + COUT : nullptr, 2 * COUT, s_scale + cg,
+            float* y0 = p.y + (vox - 2 * lane) * YS + cg;
+            const float* r0 = p.residual ? p.residual + (vox - 2 * lane) * YS + cg : nullptr;
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, ev, y0, r0, 2 * YS, s_scale + cg, s_shift + cg, p.act, vmask);
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, od_, y0 + YS, r0 ? r0 + YS : nullptr, 2 * YS, s_scale + cg,
                                 s_shift + cg, p.act, vmask);
           } else if (live && cvalid) {
 #pragma unroll
@@ -418,8 +427,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
             }
             if (p.residual) {
               if (p.res_ndhwc) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);
-                const float4* rq = reinterpret_cast<const float4*>(p.residual + (vox + 1) * COUT + cg);
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * YS + cg);
+                const float4* rq = reinterpret_cast<const float4*>(p.residual + (vox + 1) * YS + cg);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 a = __ldg(rp + i), bq = __ldg(rq + i);
@@ -446,8 +455,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
               }
             }
             if (p.out_ndhwc) {
-              float4* yp = reinterpret_cast<float4*>(p.y + vox * COUT + cg);
-              float4* yq = reinterpret_cast<float4*>(p.y + (vox + 1) * COUT + cg);
+              float4* yp = reinterpret_cast<float4*>(p.y + vox * YS + cg);
+              float4* yq = reinterpret_cast<float4*>(p.y + (vox + 1) * YS + cg);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 yp[i] = make_float4(ev[4 * i], ev[4 * i + 1], ev[4 * i + 2], ev[4 * i + 3]);
@@ -547,26 +556,46 @@ int osb_deconv3d_tc_supported(int Cin, int Cout, int W) {
 
 int osb_deconv3d_k4_tc_supported(int Cin, int Cout, int W) {
   if (Cin % 16 != 0 || Cin < 16) return 0;
-  return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32)) ? 1 : 0;
+  return ((W == 32 && Cout == 64) || (W == 64 && Cout == 32) || (W == 16 && (Cout == 64 || Cout == 32))) ? 1 : 0;
 }
+
+static int deconv3d_k4_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                               const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
+                               int out_ndhwc, int res_ndhwc, int ystride, osb_stream_t stream);
 
 int osb_deconv3d_k4_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
                            const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
                            int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  return deconv3d_k4_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, cout_real, D, H, W, act, out_ndhwc, res_ndhwc, 0,
+                             stream);
+}
+
+int osb_deconv3d_k4_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, float* y, int B,
+                              int Cin, int Cout, int D, int H, int W, int act, int ystride, osb_stream_t stream) {
+  return deconv3d_k4_tc_impl(x_ndhwc, w_split, scale, shift, nullptr, y, B, Cin, Cout, Cout, D, H, W, act, 1, 1, ystride, stream);
+}
+
+static int deconv3d_k4_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                               const float* residual, float* y, int B, int Cin, int Cout, int cout_real, int D, int H, int W, int act,
+                               int out_ndhwc, int res_ndhwc, int ystride, osb_stream_t stream) {
   using namespace osb;
   OSB_REQUIRE(x_ndhwc && w_split && y, "deconv3d_k4_tc: null pointer");
+  OSB_REQUIRE(ystride == 0 || (ystride >= Cout && ystride % 4 == 0 && out_ndhwc && (!residual || res_ndhwc)),
+              "deconv3d_k4_tc: a channel slice (ystride %d) needs channels-last tensors", ystride);
   OSB_REQUIRE(B > 0 && D > 0 && H > 0, "deconv3d_k4_tc: empty shape");
   OSB_REQUIRE(osb_deconv3d_k4_tc_supported(Cin, Cout, W), "deconv3d_k4_tc: unsupported shape Cin=%d Cout=%d W=%d", Cin, Cout, W);
   OSB_REQUIRE(act >= 0 && act <= 2, "deconv3d_k4_tc: unknown activation %d", act);
   OSB_REQUIRE(cout_real >= 1 && cout_real <= Cout && (out_ndhwc == 0 || cout_real == Cout) && (!residual || res_ndhwc == 0 || cout_real == Cout),
               "deconv3d_k4_tc: only NCDHW tensors may hold fewer (%d) channels than the packed %d", cout_real, Cout);
   TcdcParams p{};
-  p.cout_real = cout_real;
+  p.cout_real = cout_real, p.ystride = ystride;
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
   cudaStream_t s = (cudaStream_t)stream;
+  if (W == 16 && Cout == 64) return launch_tcdc<64, 16, 16, 2, false, 4>(p, s);   // StereoBase conv3_up: 6c -> 4c = 96 as slices 64 + 32
+  if (W == 16 && Cout == 32) return launch_tcdc<32, 16, 16, 4, false, 4>(p, s);
   if (W == 32) return launch_tcdc<64, 16, 32, 2, false, 4>(p, s);
   return launch_tcdc<32, 16, 64, 4, false, 4>(p, s);
 }

@@ -34,6 +34,8 @@ struct TcgParams {
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
   int Wr, ctiles;          // general-width instantiations: image width and column tiles per row (whole-row kernels: W, 1)
+  int ystride;             // channels per voxel of the channels-last y / residual / gate tensors (0 = COUT); > COUT when this launch
+                           // produces a channel SLICE of a wider tensor (pointers pre-offset to the slice's first channel)
 };
 
 template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // image width = row pitch in voxels
+  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual / gate
   const int ctiles = GW ? p.ctiles : 1;             // work item = (b, d, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
@@ -329,20 +332,26 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
               float right = __shfl_down_sync(0xffffffffu, __uint_as_float(raw[2][i]), DIL);
               left = (lane < DIL) ? le[k] : left;       // column w-DIL (zero at the image edge)
               right = (lane >= 32 - DIL) ? re[k] : right;   // column w+DIL
+              if (W < 32) {                             // several image rows per warp: row seams inside the warp are image edges
+                left = (wcol < DIL) ? 0.f : left;
+                right = (wcol >= W - DIL) ? 0.f : right;
+              }
               out[i] = ((left + __uint_as_float(raw[1][i])) + right) * corr;
             }
           }
-          if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
+          // voxels of this warp that exist (W < 32: the warp spans two image rows, the second may lie below the image)
+          const uint32_t vm = (W < 32) ? __ballot_sync(0xffffffffu, live) : (live ? vmask : 0u);
+          if (vm && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {     // coalesced channels-last path (BN/residual/act inside)
             const ptrdiff_t gvox = ((ptrdiff_t)b * p.H + h) * Wp + col - lane;     // (B, H, W) index of lane 0's voxel
-            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
-                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act,
-                                vmask, p.gate ? p.gate + gvox * COUT + cg : nullptr);
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * YS + cg,
+                                p.residual ? p.residual + (vox - lane) * YS + cg : nullptr, YS, s_scale + cg, s_shift + cg, p.act,
+                                vm, p.gate ? p.gate + gvox * YS + cg : nullptr);
           } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
             if (p.residual) {
               if (p.res_ndhwc) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * YS + cg);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 rv = __ldg(rp + i);
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
               for (int i = 0; i < 32; ++i) out[i] = out[i] > 0.f ? out[i] : 0.01f * out[i];
             }
             if (p.out_ndhwc) {
-              float4* yp = reinterpret_cast<float4*>(p.y + vox * COUT + cg);
+              float4* yp = reinterpret_cast<float4*>(p.y + vox * YS + cg);
 #pragma unroll
               for (int i = 0; i < 8; ++i) yp[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
             } else {
@@ -446,9 +455,10 @@ static int launch_tcg(TcgParams& p, cudaStream_t stream) {
 // dispatcher used by conv3d_tc.cu's C entry point; returns -1 when the shape has no generic instantiation
 int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y,
                         int B, int Cin, int Cout, int D, int H, int W, int act, int out_ndhwc, int res_ndhwc, cudaStream_t stream,
-                        const float* gate) {
+                        const float* gate, int ystride) {
   TcgParams p{};
   p.x = x, p.w = w, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y, p.gate = gate;
+  p.ystride = ystride;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   if (!p.overflow) return OSB_ECUDA;
@@ -457,6 +467,8 @@ int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
   if (W == 32 && Cout == 96) return launch_tcg<96, 16, 32, 1>(p, stream);         // StereoBase 1/16 level (4c = 96)
+  if (W == 16 && Cout == 96) return launch_tcg<96, 16, 16, 1>(p, stream);         // StereoBase 1/32 level: 6c = 144 -> 160 channels as
+  if (W == 16 && Cout == 64) return launch_tcg<64, 16, 16, 2>(p, stream);         // two channel slices (96 + 64), 8 image rows per tile
   if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
   // every other width: 128-column tiles with a one-column halo (tc_general_width() is the single source of the W bound)

@@ -30,6 +30,7 @@ struct Tcs2Params {
   int out_ndhwc, res_ndhwc;
   int items, hblocks;
   int Wr, ctiles;          // general-width instantiations: OUTPUT width and column tiles per row (whole-row kernels: W, 1)
+  int ystride;             // channels per voxel of the channels-last y / residual (0 = COUT); > COUT: this launch writes a channel slice
 };
 
 template <int COUT, int KC, int W, int TILES, bool GW = false>     // W = OUTPUT width
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // OUTPUT width (the input is 2 * Wp wide)
+  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual
   const int ctiles = GW ? p.ctiles : 1;             // work item = (b, od, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
@@ -310,19 +312,21 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
               const int i = i0 + k;
               float left = __shfl_up_sync(0xffffffffu, __uint_as_float(raw[1][i]), 1);   // P0 of output column ow-1
               left = (lane == 0) ? le[k] : left;                                        // zero at ow = 0 (left padding)
+              if (W < 32) left = (wcol == 0) ? 0.f : left;                              // row seams inside the warp
               out[i] = ((left + __uint_as_float(raw[0][i])) + __uint_as_float(raw[2][i])) * corr;
             }
           }
-          if (live && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {   // coalesced channels-last path (BN/residual/act inside)
-            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * COUT + cg,
-                                p.residual ? p.residual + (vox - lane) * COUT + cg : nullptr, COUT, s_scale + cg, s_shift + cg, p.act,
-                                vmask);
+          const uint32_t vm = (W < 32) ? __ballot_sync(0xffffffffu, live) : (live ? vmask : 0u);   // voxels of this warp that exist
+          if (vm && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {     // coalesced channels-last path (BN/residual/act inside)
+            store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * YS + cg,
+                                p.residual ? p.residual + (vox - lane) * YS + cg : nullptr, YS, s_scale + cg, s_shift + cg, p.act,
+                                vm);
           } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
             if (p.residual) {
               if (p.res_ndhwc) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * COUT + cg);
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + vox * YS + cg);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const float4 rv = __ldg(rp + i);
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
               for (int i = 0; i < 32; ++i) out[i] = out[i] > 0.f ? out[i] : 0.01f * out[i];
             }
             if (p.out_ndhwc) {
-              float4* yp = reinterpret_cast<float4*>(p.y + vox * COUT + cg);
+              float4* yp = reinterpret_cast<float4*>(p.y + vox * YS + cg);
 #pragma unroll
               for (int i = 0; i < 8; ++i) yp[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
             } else {
@@ -429,14 +433,17 @@ extern "C" {
 
 int osb_conv3d_s2_tc_supported(int Cin, int Cout, int D, int H, int W) {
   if (Cin % 16 != 0 || Cin < 16 || D % 2 || H % 2 || W % 2) return 0;
-  if ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 96 || Cout == 128))) return 1;      // whole-row variants
+  if ((W == 128 && Cout == 64) || (W == 64 && (Cout == 64 || Cout == 96 || Cout == 128)) || (W == 32 && (Cout == 64 || Cout == 96)))
+    return 1;                                                                               // whole-row variants
   return (osb_tc_general_width(W / 2) && (Cout == 64 || Cout == 128)) ? 1 : 0;              // 128-column tiles of the OUTPUT row
 }
 
-int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
-                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
-                            int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+static int conv3d_k3_s2_tc_impl(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                                const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                                int out_ndhwc, int res_ndhwc, int ystride, osb_stream_t stream) {
   using namespace osb;
+  OSB_REQUIRE(ystride == 0 || (ystride >= Cout && ystride % 4 == 0 && out_ndhwc && (!residual || res_ndhwc)),
+              "conv3d_k3_s2_tc: a channel slice (ystride %d) needs channels-last tensors", ystride);
   OSB_REQUIRE(x_ndhwc && w_split && y, "conv3d_k3_s2_tc: null pointer");
   OSB_REQUIRE(B > 0 && D > 0 && H > 0, "conv3d_k3_s2_tc: empty shape");
   OSB_REQUIRE(osb_conv3d_s2_tc_supported(Cin, Cout, D, H, W), "conv3d_k3_s2_tc: unsupported shape Cin=%d Cout=%d D=%d H=%d W=%d", Cin,
@@ -446,8 +453,11 @@ int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const flo
   p.x = x_ndhwc, p.w = w_split, p.scale = scale, p.shift = shift, p.residual = residual, p.y = y;
   p.B = B, p.D = D, p.H = H, p.Cin = Cin, p.act = act, p.out_ndhwc = out_ndhwc, p.res_ndhwc = res_ndhwc;
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
+  p.ystride = ystride;
   OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
   cudaStream_t s = (cudaStream_t)stream;
+  if (W == 32 && Cout == 96) return launch_tcs2<96, 16, 16, 1>(p, s);           // StereoBase conv3[0]: 4c -> 6c as two channel slices
+  if (W == 32 && Cout == 64) return launch_tcs2<64, 16, 16, 2>(p, s);
   if (W == 128 && Cout == 64) return launch_tcs2<64, 16, 64, 2>(p, s);
   if (W == 64 && Cout == 64) return launch_tcs2<64, 16, 32, 2>(p, s);
   if (W == 64 && Cout == 128) return launch_tcs2<128, 16, 32, 1>(p, s);
@@ -455,5 +465,16 @@ int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const flo
   p.Wr = W / 2;
   if (Cout == 64) return launch_tcs2<64, 16, 128, 2, true>(p, s);
   return launch_tcs2<128, 16, 128, 1, true>(p, s);
+}
+
+int osb_conv3d_k3_s2_tc_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift,
+                            const float* residual, float* y, int B, int Cin, int Cout, int D, int H, int W, int act,
+                            int out_ndhwc, int res_ndhwc, osb_stream_t stream) {
+  return conv3d_k3_s2_tc_impl(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, out_ndhwc, res_ndhwc, 0, stream);
+}
+
+int osb_conv3d_k3_s2_tc_cs_fwd(const float* x_ndhwc, const void* w_split, const float* scale, const float* shift, float* y, int B,
+                               int Cin, int Cout, int D, int H, int W, int act, int ystride, osb_stream_t stream) {
+  return conv3d_k3_s2_tc_impl(x_ndhwc, w_split, scale, shift, nullptr, y, B, Cin, Cout, D, H, W, act, 1, 1, ystride, stream);
 }
 }

@@ -101,3 +101,104 @@ int osb_regression_values_fwd(const float* prob, const float* values, float* out
   return check_launch("regression_values_kernel");
 }
 }
+
+// ------------------------------------------------------------------------------------------ FeatureAtt gate, one launch
+// igev_blocks.py:35-48 (FeatureAtt.feat_att) as used by stereobase/hourglass.py:62-99:
+//     gate = sigmoid(Conv2d(Cf/2 -> Cv, 1, bias)(LeakyReLU(BN(Conv2d(Cf -> Cf/2, 1)(feat)))))
+// written CHANNELS-LAST and zero-padded, (B, H, W, Cpad), the operand the tensor-core conv epilogues multiply by
+// (tc_common.cuh: store_ndhwc_chunk32 gate0).  The unfused path was two 1x1-conv launches plus a layout conversion per gate --
+// 15 launches and 0.7 ms of latency-bound work per StereoBase forward at BASELINE config 3 (profiles/r2_c3_launches.csv).
+// CTA = 32 consecutive pixels of one image x 128 threads: the feature tile [Cf][32] is staged in shared memory (128-byte rows),
+// lane = pixel, each warp produces 4 channels at a time (one broadcast LDG.128 of the (Cin, Cout)-packed weights per input channel).
+namespace osb {
+
+__global__ void __launch_bounds__(128) feature_att_gate_kernel(const float* __restrict__ feat, const float* __restrict__ w1,
+                                                               const float* __restrict__ sc1, const float* __restrict__ sh1,
+                                                               const float* __restrict__ w2, const float* __restrict__ sc2,
+                                                               const float* __restrict__ sh2, float* __restrict__ gate, int Cf,
+                                                               int Ch, int Cv, int Cpad, int HW, int act1) {
+  extern __shared__ __align__(16) float fa_smem[];
+  float* fs = fa_smem;                        // [Cf][32]
+  float* hs = fs + Cf * 32;                   // [Ch][32]
+  float* os = hs + Ch * 32;                   // [32][Cpad + 4]
+  const int OS = Cpad + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (HW + 31) / 32;
+  const int b = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * 32;
+  const int np = min(32, HW - p0);
+  const float* fb = feat + (size_t)b * Cf * HW + p0;
+  for (int c = warp; c < Cf; c += 4) fs[c * 32 + lane] = lane < np ? __ldg(fb + (size_t)c * HW + lane) : 0.f;
+  for (int i = threadIdx.x; i < 32 * OS; i += 128) os[i] = 0.f;     // padded channels stay zero
+  __syncthreads();
+  for (int hc = warp * 4; hc < Ch; hc += 16) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < Cf; ++c) {
+      const float x = fs[c * 32 + lane];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w1 + (size_t)c * Ch + hc));
+      a0 = fmaf(x, w.x, a0), a1 = fmaf(x, w.y, a1), a2 = fmaf(x, w.z, a2), a3 = fmaf(x, w.w, a3);
+    }
+    float v[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = fmaf(v[j], sc1 ? __ldg(sc1 + hc + j) : 1.f, sh1 ? __ldg(sh1 + hc + j) : 0.f);
+      if (act1 == OSB_ACT_LEAKY) t = t > 0.f ? t : 0.01f * t;
+      else if (act1 == OSB_ACT_RELU) t = fmaxf(t, 0.f);
+      hs[(hc + j) * 32 + lane] = t;
+    }
+  }
+  __syncthreads();
+  for (int oc = warp * 4; oc < Cv; oc += 16) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < Ch; ++c) {
+      const float x = hs[c * 32 + lane];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + (size_t)c * Cv + oc));
+      a0 = fmaf(x, w.x, a0), a1 = fmaf(x, w.y, a1), a2 = fmaf(x, w.z, a2), a3 = fmaf(x, w.w, a3);
+    }
+    float v[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = fmaf(v[j], sc2 ? __ldg(sc2 + oc + j) : 1.f, sh2 ? __ldg(sh2 + oc + j) : 0.f);
+      os[lane * OS + oc + j] = 1.f / (1.f + expf(-t));
+    }
+  }
+  __syncthreads();
+  float* gb = gate + ((size_t)b * HW + p0) * Cpad;
+  const int q4 = Cpad / 4;
+  for (int i = threadIdx.x; i < np * q4; i += 128) {
+    const int px = i / q4, c4 = i % q4;
+    reinterpret_cast<float4*>(gb)[i] = *reinterpret_cast<const float4*>(os + px * OS + 4 * c4);
+  }
+}
+
+}  // namespace osb
+
+extern "C" int osb_feature_att_gate_fwd(const float* feat_nchw, const float* w1_packed, const float* scale1, const float* shift1,
+                                        const float* w2_packed, const float* scale2, const float* shift2, float* gate_nhwc, int B,
+                                        int Cf, int Ch, int Cv, int Cpad, int HW, int act1, osb_stream_t stream) {
+  using namespace osb;
+  OSB_REQUIRE(feat_nchw && w1_packed && w2_packed && gate_nhwc, "feature_att_gate: null pointer");
+  OSB_REQUIRE(B > 0 && Cf > 0 && Ch > 0 && Cv > 0 && HW > 0 && Ch % 4 == 0 && Cv % 4 == 0 && Cpad % 4 == 0 && Cpad >= Cv,
+              "feature_att_gate: bad shape (hidden / output channels must be multiples of 4)");
+  OSB_REQUIRE(act1 >= 0 && act1 <= 2, "feature_att_gate: unknown activation %d", act1);
+  OSB_REQUIRE(((reinterpret_cast<uintptr_t>(w1_packed) | reinterpret_cast<uintptr_t>(w2_packed) | reinterpret_cast<uintptr_t>(gate_nhwc)) & 15) == 0,
+              "feature_att_gate: pointers must be 16-byte aligned");
+  const size_t smem = ((size_t)(Cf + Ch) * 32 + (size_t)32 * (Cpad + 4)) * sizeof(float);
+  OSB_REQUIRE(smem <= 200 * 1024, "feature_att_gate: %d + %d channels exceed the shared-memory tile", Cf, Ch);
+  static PerDeviceFlag configured;
+  if (!configured.here()) {
+    cudaError_t e = cudaFuncSetAttribute(feature_att_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("feature_att_gate: cannot reserve shared memory: %s", cudaGetErrorString(e));
+      return OSB_ECUDA;
+    }
+    configured.here() = true;
+  }
+  const long long blocks = (long long)B * ((HW + 31) / 32);
+  OSB_REQUIRE(blocks < (1ll << 31), "feature_att_gate: too many tiles");
+  feature_att_gate_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(feat_nchw, w1_packed, scale1, shift1, w2_packed, scale2,
+                                                                                 shift2, gate_nhwc, Cf, Ch, Cv, Cpad, HW, act1);
+  count_launch();
+  return check_launch("feature_att_gate_kernel");
+}

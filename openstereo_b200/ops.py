@@ -649,6 +649,50 @@ def deconv3d_k4_tc(x_ndhwc, w_split, scale=None, shift=None, residual=None, act=
     return y
 
 
+def tc_slice(kind, x_ndhwc, w_split, scale, shift, y, coff, act=ACT_NONE, gate=None):
+    """One output-channel SLICE of a tensor-core conv (include/openstereo_b200.h: *_cs_fwd): channels [coff, coff + w_split.cout) of
+    the preallocated channels-last `y` (..., Ctot).  kind: "s1" (3x3x3 stride 1, optional (B,H,W,Ctot) gate), "s2" (stride 2) or
+    "dc4" (ConvTranspose3d k4 s2 p1).  scale / shift: this slice's folded BN."""
+    assert x_ndhwc.is_cuda and x_ndhwc.dtype == torch.float32 and x_ndhwc.is_contiguous() and x_ndhwc.dim() == 5
+    assert y.is_contiguous() and y.dtype == torch.float32 and y.dim() == 5
+    b, d, h, w, cin = x_ndhwc.shape
+    cout, ctot = w_split.cout, y.shape[-1]
+    assert 0 <= coff and coff + cout <= ctot and coff % 4 == 0
+    wptr, scale = _tc_args(w_split, cin, 16, scale)
+    yp = y.data_ptr() + 4 * coff
+    if kind == "s1":
+        assert tuple(y.shape[:4]) == (b, d, h, w)
+        gp = None
+        if gate is not None:
+            assert tuple(gate.shape) == (b, h, w, ctot) and gate.is_contiguous()
+            gp = gate.data_ptr() + 4 * coff
+        _call("osb_conv3d_k3_tc_cs_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), None, gp, yp, b, cin, cout, d, h, w, act,
+              ctot, _stream(y))
+    elif kind == "s2":
+        assert tuple(y.shape[:4]) == (b, d // 2, h // 2, w // 2) and gate is None
+        _call("osb_conv3d_k3_s2_tc_cs_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), yp, b, cin, cout, d, h, w, act, ctot,
+              _stream(y))
+    else:
+        assert kind == "dc4" and tuple(y.shape[:4]) == (b, 2 * d, 2 * h, 2 * w) and gate is None and w_split.ksize == 4
+        _call("osb_deconv3d_k4_tc_cs_fwd", x_ndhwc.data_ptr(), wptr, _ptr(scale), _ptr(shift), yp, b, cin, cout, d, h, w, act, ctot,
+              _stream(y))
+    return y
+
+
+def feature_att_gate(feat, w1, scale1, shift1, w2, scale2, shift2, pad_to=None, act1=ACT_LEAKY):
+    """FeatureAtt's gate (igev_blocks.py:35-48) in one launch: feat (B,Cf,H,W) NCHW -> sigmoid gate (B,H,W,Cpad) channels-last,
+    zero beyond the Cv real channels.  w1 (Cf,Ch), w2 (Ch,Cv) packed (Cin, Cout)."""
+    assert feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.dim() == 4
+    b, cf, h, w = feat.shape
+    ch, cv = w1.shape[1], w2.shape[1]
+    assert w1.shape[0] == cf and w2.shape[0] == ch and w1.is_contiguous() and w2.is_contiguous()
+    cp = cv if pad_to is None else int(pad_to)
+    gate = torch.empty((b, h, w, cp), dtype=torch.float32, device=feat.device)
+    _call("osb_feature_att_gate_fwd", feat.data_ptr(), w1.data_ptr(), _ptr(scale1), _ptr(shift1), w2.data_ptr(), _ptr(scale2),
+          _ptr(shift2), gate.data_ptr(), b, cf, ch, cv, cp, h * w, act1, _stream(gate))
+    return gate
+
+
 def conv1x1_ndhwc_cat(x0, x1, w_packed, scale=None, shift=None, act=ACT_NONE):
     """Channels-last 1x1x1 conv over torch.cat((x0, x1), -1) without materialising it: (..., C0), (..., C1) -> (..., Cout);
     w_packed (C0 + C1, Cout)."""

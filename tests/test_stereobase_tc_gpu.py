@@ -131,6 +131,64 @@ def test_conv1x1_ndhwc_cat(osb):
         rel_close(got, want, 1e-5, "1x1 over the concat %d+%d->%d" % (c0, c1, cout))
 
 
+@pytest.mark.parametrize("b,cf,cv,h,w", [(2, 64, 48, 8, 16), (1, 192, 96, 5, 7), (1, 160, 144, 3, 5)])
+def test_feature_att_gate_one_launch(osb, b, cf, cv, h, w):
+    """sigmoid(conv1x1(leaky(bn(conv1x1(feat))))) written channels-last and zero-padded, vs PyTorch (igev_blocks.py:35-48)."""
+    _, ops = osb
+    ch, cp = cf // 2, (cv + 31) // 32 * 32
+    feat = rnd(470, b, cf, h, w)
+    w1, w2 = rnd(471, ch, cf, scale=0.2), rnd(472, cv, ch, scale=0.2)
+    sc1, sh1 = _bn(ch, 473)
+    bias = rnd(475, cv, scale=0.3)
+    hid = F.leaky_relu(F.conv2d(feat.double(), w1.double()[:, :, None, None]).float() * sc1.view(1, -1, 1, 1) + sh1.view(1, -1, 1, 1))
+    want = torch.sigmoid(F.conv2d(hid.double(), w2.double()[:, :, None, None]).float() + bias.view(1, -1, 1, 1))
+    got = ops.feature_att_gate(feat.cuda(), w1.t().contiguous().cuda(), sc1.cuda(), sh1.cuda(), w2.t().contiguous().cuda(), None,
+                               bias.cuda(), pad_to=cp)
+    assert got.shape == (b, h, w, cp) and (got[..., cv:] == 0).all()
+    assert (got[..., :cv].cpu() - want.permute(0, 2, 3, 1)).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("b,d,h", [(1, 2, 8), (2, 1, 5), (1, 3, 16)])
+def test_channel_slices_at_width_16(osb, b, d, h):
+    """The 1/32 level of StereoBase's hourglass: W' = 16 (eight image rows per M tile, two per epilogue warp), 6c = 144 channels
+    run as 160 = 96 + 64 output-channel slices; stride-2 conv, stride-1 conv with gate, k4 transposed conv (96 = 64 + 32)."""
+    _, ops = osb
+    cin, ctot, w = 96, 160, 16
+    # stride 2: (b, 96, 2d, 2h, 32) -> (b, 160, d, h, 16)
+    x, wt = rnd(480, b, cin, 2 * d, 2 * h, 2 * w), rnd(481, ctot, cin, 3, 3, 3, scale=0.2)
+    sc, sh = _bn(ctot, 482)
+    want = F.leaky_relu(F.conv3d(x.double(), wt.double(), stride=2, padding=1).float() * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    y = torch.full((b, d, h, w, ctot), float("nan"), device="cuda")
+    xc = ops.to_ndhwc(x.cuda())
+    for lo, hi in ((0, 96), (96, 160)):
+        ops.tc_slice("s2", xc, ops.pack_tc_weight(wt[lo:hi].cuda(), 16, kw_order=(1, 0, 2)), sc[lo:hi].contiguous().cuda(),
+                     sh[lo:hi].contiguous().cuda(), y, lo, ops.ACT_LEAKY)
+    rel_close(y.permute(0, 4, 1, 2, 3), want, 1e-5, "s2 slices @16")
+    # stride 1 with gate: 160 -> 160
+    x1, wt1 = want, rnd(483, ctot, ctot, 3, 3, 3, scale=0.1)
+    gate = torch.sigmoid(rnd(484, b, ctot, h, w))
+    want1 = F.leaky_relu(F.conv3d(x1.double(), wt1.double(), padding=1).float() * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    want1 = want1 * gate.unsqueeze(2)
+    y1 = torch.full_like(y, float("nan"))
+    gp = gate.permute(0, 2, 3, 1).contiguous().cuda()
+    x1c = ops.to_ndhwc(x1.cuda())
+    for lo, hi in ((0, 96), (96, 160)):
+        ops.tc_slice("s1", x1c, ops.pack_tc_weight(wt1[lo:hi].cuda(), 16), sc[lo:hi].contiguous().cuda(), sh[lo:hi].contiguous().cuda(),
+                     y1, lo, ops.ACT_LEAKY, gate=gp)
+    rel_close(y1.permute(0, 4, 1, 2, 3), want1, 1e-5, "s1 slices + gate @16")
+    # k4 transposed conv: 160 -> 96 at (d, h, 16) -> (2d, 2h, 32)
+    wt2 = rnd(485, ctot, 96, 4, 4, 4, scale=0.1)
+    sc2, sh2 = _bn(96, 486)
+    want2 = F.leaky_relu(F.conv_transpose3d(want1.double(), wt2.double(), stride=2, padding=1).float() * sc2.view(1, -1, 1, 1, 1)
+                         + sh2.view(1, -1, 1, 1, 1))
+    y2 = torch.full((b, 2 * d, 2 * h, 2 * w, 96), float("nan"), device="cuda")
+    x2c = ops.to_ndhwc(want1.cuda())
+    for lo, hi in ((0, 64), (64, 96)):
+        ops.tc_slice("dc4", x2c, ops.pack_tc_deconv_weight(wt2[:, lo:hi].contiguous().cuda()), sc2[lo:hi].contiguous().cuda(),
+                     sh2[lo:hi].contiguous().cuda(), y2, lo, ops.ACT_LEAKY)
+    rel_close(y2.permute(0, 4, 1, 2, 3), want2, 1e-5, "k4 deconv slices @16")
+
+
 def _stereobase_case(osb, b, dq, hq, wq, seed):
     agg, ops = osb
     m = oagg.StereoBaseCostHead(24, [96, 64, 192, 160], max_disp=4 * dq).eval()
@@ -152,7 +210,7 @@ def test_stereobase_hourglass_tensor_cores(osb):
     eng = agg.StereoBaseAggregation(m.cost_agg)
     fg = [f.cuda() for f in feats]
     eng._ensure(torch.device("cuda", 0))
-    assert eng.tc_route_ok(vol.shape)
+    assert eng.tc_route_ok(vol.shape) and eng._level32_tc_ok(vol.shape)
     from openstereo_b200 import _lib
     before = _lib.launch_count()
     got = eng(vol.cuda(), fg)
