@@ -108,9 +108,12 @@ int osb_regression_values_fwd(const float* prob, const float* values, float* out
 // written CHANNELS-LAST and zero-padded, (B, H, W, Cpad), the operand the tensor-core conv epilogues multiply by
 // (tc_common.cuh: store_ndhwc_chunk32 gate0).  The unfused path was two 1x1-conv launches plus a layout conversion per gate --
 // 15 launches and 0.7 ms of latency-bound work per StereoBase forward at BASELINE config 3 (profiles/r2_c3_launches.csv).
-// CTA = 32 consecutive pixels of one image x 128 threads: the feature tile [Cf][32] is staged in shared memory (128-byte rows),
-// lane = pixel, each warp produces 4 channels at a time (one broadcast LDG.128 of the (Cin, Cout)-packed weights per input channel).
+// CTA = 8 consecutive pixels of one image x 128 threads (16 channel groups x 8 pixels): the feature tile [Cf][8] is staged in shared
+// memory, a thread produces 4 channels of one pixel at a time (one LDG.128 of the (Cin, Cout)-packed weights per input channel,
+// shared by the 8 pixel lanes).  A first version with 32-pixel tiles left the 1/16-resolution gates on 64 CTAs: 244 us.
 namespace osb {
+
+constexpr int FA_PT = 8;                      // pixels per CTA: small tiles -> B*H*W/8 CTAs (the 1/16 maps have 512 pixels per image)
 
 __global__ void __launch_bounds__(128) feature_att_gate_kernel(const float* __restrict__ feat, const float* __restrict__ w1,
                                                                const float* __restrict__ sc1, const float* __restrict__ sh1,
@@ -118,23 +121,24 @@ __global__ void __launch_bounds__(128) feature_att_gate_kernel(const float* __re
                                                                const float* __restrict__ sh2, float* __restrict__ gate, int Cf,
                                                                int Ch, int Cv, int Cpad, int HW, int act1) {
   extern __shared__ __align__(16) float fa_smem[];
-  float* fs = fa_smem;                        // [Cf][32]
-  float* hs = fs + Cf * 32;                   // [Ch][32]
-  float* os = hs + Ch * 32;                   // [32][Cpad + 4]
+  float* fs = fa_smem;                        // [Cf][PT]
+  float* hs = fs + Cf * FA_PT;                // [Ch][PT]
+  float* os = hs + Ch * FA_PT;                // [PT][Cpad + 4]
   const int OS = Cpad + 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = (HW + 31) / 32;
-  const int b = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * 32;
-  const int np = min(32, HW - p0);
+  const int px = threadIdx.x % FA_PT, grp = threadIdx.x / FA_PT;      // 8 pixels x 16 channel groups
+  constexpr int NG = 128 / FA_PT;
+  const int tiles = (HW + FA_PT - 1) / FA_PT;
+  const int b = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * FA_PT;
+  const int np = min(FA_PT, HW - p0);
   const float* fb = feat + (size_t)b * Cf * HW + p0;
-  for (int c = warp; c < Cf; c += 4) fs[c * 32 + lane] = lane < np ? __ldg(fb + (size_t)c * HW + lane) : 0.f;
-  for (int i = threadIdx.x; i < 32 * OS; i += 128) os[i] = 0.f;     // padded channels stay zero
+  for (int i = threadIdx.x; i < Cf * FA_PT; i += 128) fs[i] = (i % FA_PT) < np ? __ldg(fb + (size_t)(i / FA_PT) * HW + (i % FA_PT)) : 0.f;
+  for (int i = threadIdx.x; i < FA_PT * OS; i += 128) os[i] = 0.f;     // padded channels stay zero
   __syncthreads();
-  for (int hc = warp * 4; hc < Ch; hc += 16) {
+  for (int hc = grp * 4; hc < Ch; hc += 4 * NG) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = 0; c < Cf; ++c) {
-      const float x = fs[c * 32 + lane];
+      const float x = fs[c * FA_PT + px];
       const float4 w = __ldg(reinterpret_cast<const float4*>(w1 + (size_t)c * Ch + hc));
       a0 = fmaf(x, w.x, a0), a1 = fmaf(x, w.y, a1), a2 = fmaf(x, w.z, a2), a3 = fmaf(x, w.w, a3);
     }
@@ -144,15 +148,15 @@ __global__ void __launch_bounds__(128) feature_att_gate_kernel(const float* __re
       float t = fmaf(v[j], sc1 ? __ldg(sc1 + hc + j) : 1.f, sh1 ? __ldg(sh1 + hc + j) : 0.f);
       if (act1 == OSB_ACT_LEAKY) t = t > 0.f ? t : 0.01f * t;
       else if (act1 == OSB_ACT_RELU) t = fmaxf(t, 0.f);
-      hs[(hc + j) * 32 + lane] = t;
+      hs[(hc + j) * FA_PT + px] = t;
     }
   }
   __syncthreads();
-  for (int oc = warp * 4; oc < Cv; oc += 16) {
+  for (int oc = grp * 4; oc < Cv; oc += 4 * NG) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = 0; c < Ch; ++c) {
-      const float x = hs[c * 32 + lane];
+      const float x = hs[c * FA_PT + px];
       const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + (size_t)c * Cv + oc));
       a0 = fmaf(x, w.x, a0), a1 = fmaf(x, w.y, a1), a2 = fmaf(x, w.z, a2), a3 = fmaf(x, w.w, a3);
     }
@@ -160,15 +164,15 @@ __global__ void __launch_bounds__(128) feature_att_gate_kernel(const float* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t = fmaf(v[j], sc2 ? __ldg(sc2 + oc + j) : 1.f, sh2 ? __ldg(sh2 + oc + j) : 0.f);
-      os[lane * OS + oc + j] = 1.f / (1.f + expf(-t));
+      os[px * OS + oc + j] = 1.f / (1.f + expf(-t));
     }
   }
   __syncthreads();
   float* gb = gate + ((size_t)b * HW + p0) * Cpad;
   const int q4 = Cpad / 4;
   for (int i = threadIdx.x; i < np * q4; i += 128) {
-    const int px = i / q4, c4 = i % q4;
-    reinterpret_cast<float4*>(gb)[i] = *reinterpret_cast<const float4*>(os + px * OS + 4 * c4);
+    const int p = i / q4, c4 = i % q4;
+    reinterpret_cast<float4*>(gb)[i] = *reinterpret_cast<const float4*>(os + p * OS + 4 * c4);
   }
 }
 
@@ -184,7 +188,7 @@ extern "C" int osb_feature_att_gate_fwd(const float* feat_nchw, const float* w1_
   OSB_REQUIRE(act1 >= 0 && act1 <= 2, "feature_att_gate: unknown activation %d", act1);
   OSB_REQUIRE(((reinterpret_cast<uintptr_t>(w1_packed) | reinterpret_cast<uintptr_t>(w2_packed) | reinterpret_cast<uintptr_t>(gate_nhwc)) & 15) == 0,
               "feature_att_gate: pointers must be 16-byte aligned");
-  const size_t smem = ((size_t)(Cf + Ch) * 32 + (size_t)32 * (Cpad + 4)) * sizeof(float);
+  const size_t smem = ((size_t)(Cf + Ch) * FA_PT + (size_t)FA_PT * (Cpad + 4)) * sizeof(float);
   OSB_REQUIRE(smem <= 200 * 1024, "feature_att_gate: %d + %d channels exceed the shared-memory tile", Cf, Ch);
   static PerDeviceFlag configured;
   if (!configured.here()) {
@@ -195,7 +199,7 @@ extern "C" int osb_feature_att_gate_fwd(const float* feat_nchw, const float* w1_
     }
     configured.here() = true;
   }
-  const long long blocks = (long long)B * ((HW + 31) / 32);
+  const long long blocks = (long long)B * ((HW + FA_PT - 1) / FA_PT);
   OSB_REQUIRE(blocks < (1ll << 31), "feature_att_gate: too many tiles");
   feature_att_gate_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(feat_nchw, w1_packed, scale1, shift1, w2_packed, scale2,
                                                                                  shift2, gate_nhwc, Cf, Ch, Cv, Cpad, HW, act1);
