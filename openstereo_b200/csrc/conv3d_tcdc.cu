@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // INPUT width (the output is 2 * Wp wide)
-  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual
+  const int YS = (W < 32 && p.ystride) ? p.ystride : COUT;   // (compile-time COUT in the wide instantiations: slices exist at W' = 16 only)      // channel stride of the channels-last output / residual
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -520,6 +520,10 @@ static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
       return OSB_ECUDA;
     }
     configured.here() = true;
+  }
+  if (W >= 32 && p.ystride && p.ystride != COUT) {
+    set_error("conv3d_tcdc: channel slices are instantiated for W = 16 only");
+    return OSB_EUNSUPPORTED;
   }
   p.hblocks = (p.H + C::HBLK - 1) / C::HBLK;
   if (p.cout_real <= 0 || p.cout_real > COUT) p.cout_real = COUT;

@@ -77,7 +77,7 @@ struct TcgCfg {
   static constexpr bool used(int s) { return tile_of(s, 0) >= 0 || tile_of(s, 1) >= 0 || tile_of(s, 2) >= 0; }
 };
 
-template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
+template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false, bool GATE = false>
 __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 1) conv3d_tcg_kernel(const TcgParams p) {
   using C = TcgCfg<COUT, KC, W, TILES, DIL, GW>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // image width = row pitch in voxels
-  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual / gate
+  const int YS = (W < 32 && p.ystride) ? p.ystride : COUT;   // (compile-time COUT in the wide instantiations: slices exist at W' = 16 only)      // channel stride of the channels-last output / residual / gate
   const int ctiles = GW ? p.ctiles : 1;             // work item = (b, d, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
@@ -342,10 +342,10 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
           // voxels of this warp that exist (W < 32: the warp spans two image rows, the second may lie below the image)
           const uint32_t vm = (W < 32) ? __ballot_sync(0xffffffffu, live) : (live ? vmask : 0u);
           if (vm && p.out_ndhwc && (!p.residual || p.res_ndhwc)) {     // coalesced channels-last path (BN/residual/act inside)
-            const ptrdiff_t gvox = ((ptrdiff_t)b * p.H + h) * Wp + col - lane;     // (B, H, W) index of lane 0's voxel
+            const ptrdiff_t gvox = GATE ? ((ptrdiff_t)b * p.H + h) * Wp + col - lane : 0;   // (B, H, W) index of lane 0's voxel
             store_ndhwc_chunk32(tpose + q * TP_WARP_FLOATS, lane, out, p.y + (vox - lane) * YS + cg,
                                 p.residual ? p.residual + (vox - lane) * YS + cg : nullptr, YS, s_scale + cg, s_shift + cg, p.act,
-                                vm, p.gate ? p.gate + gvox * YS + cg : nullptr);
+                                vm, (GATE && p.gate) ? p.gate + gvox * YS + cg : nullptr);
           } else if (live && cvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) out[i] = fmaf(out[i], s_scale[cg + i], s_shift[cg + i]);
@@ -417,10 +417,18 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false>
+template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false, bool GATE = false>
 static int launch_tcg(TcgParams& p, cudaStream_t stream) {
   using C = TcgCfg<COUT, KC, W, TILES, DIL, GW>;
-  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL, GW>;
+  auto kernel = conv3d_tcg_kernel<COUT, KC, W, TILES, DIL, GW, GATE>;
+  if (!GATE && p.gate) {
+    set_error("conv3d_tcg: no gated instantiation for Cout=%d W=%d", COUT, W);
+    return OSB_EUNSUPPORTED;
+  }
+  if (W >= 32 && p.ystride && p.ystride != COUT) {
+    set_error("conv3d_tcg: channel slices are instantiated for W = 16 only");
+    return OSB_EUNSUPPORTED;
+  }
   static PerDeviceFlag configured;
   if (!configured.here()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -463,12 +471,14 @@ int launch_tcg_dispatch(const float* x, const void* w, const float* scale, const
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   if (!p.overflow) return OSB_ECUDA;
   if (Cin % 16 != 0 || Cin < 16) return -1;
+  if (W == 64 && Cout == 64 && gate) return launch_tcg<64, 16, 64, 2, 1, false, true>(p, stream);   // StereoBase 1/8 level (FeatureAtt gate)
+  if (W == 32 && Cout == 96 && gate) return launch_tcg<96, 16, 32, 1, 1, false, true>(p, stream);   // ... 1/16 level
   if (W == 64 && Cout == 64) return launch_tcg<64, 16, 64, 2>(p, stream);
   if (W == 32 && Cout == 64) return launch_tcg<64, 16, 32, 2>(p, stream);
   if (W == 32 && Cout == 128) return launch_tcg<128, 16, 32, 1>(p, stream);
   if (W == 32 && Cout == 96) return launch_tcg<96, 16, 32, 1>(p, stream);         // StereoBase 1/16 level (4c = 96)
-  if (W == 16 && Cout == 96) return launch_tcg<96, 16, 16, 1>(p, stream);         // StereoBase 1/32 level: 6c = 144 -> 160 channels as
-  if (W == 16 && Cout == 64) return launch_tcg<64, 16, 16, 2>(p, stream);         // two channel slices (96 + 64), 8 image rows per tile
+  if (W == 16 && Cout == 96) return launch_tcg<96, 16, 16, 1, 1, false, true>(p, stream);   // StereoBase 1/32 level: 6c = 144 -> 160 channels
+  if (W == 16 && Cout == 64) return launch_tcg<64, 16, 16, 2, 1, false, true>(p, stream);   // as two slices (96 + 64), 8 image rows per tile
   if (W == 128 && Cout == 64) return launch_tcg<64, 16, 128, 2>(p, stream);      // 2D backbone stages as one-plane volumes
   if (W == 128 && Cout == 128) return launch_tcg<128, 16, 128, 1>(p, stream);
   // every other width: 128-column tiles with a one-column halo (tc_general_width() is the single source of the W bound)

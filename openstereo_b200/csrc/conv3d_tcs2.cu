@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.Cin / KC;
   const int Wp = GW ? p.Wr : W;                     // OUTPUT width (the input is 2 * Wp wide)
-  const int YS = p.ystride ? p.ystride : COUT;      // channel stride of the channels-last output / residual
+  const int YS = (W < 32 && p.ystride) ? p.ystride : COUT;   // (compile-time COUT in the wide instantiations: slices exist at W' = 16 only)      // channel stride of the channels-last output / residual
   const int ctiles = GW ? p.ctiles : 1;             // work item = (b, od, row block, column tile), column tile fastest
 
   if (threadIdx.x == 0) {
@@ -404,6 +404,10 @@ static int launch_tcs2(Tcs2Params& p, cudaStream_t stream) {
       return OSB_ECUDA;
     }
     configured.here() = true;
+  }
+  if (W >= 32 && p.ystride && p.ystride != COUT) {
+    set_error("conv3d_tcs2: channel slices are instantiated for W = 16 only");
+    return OSB_EUNSUPPORTED;
   }
   p.hblocks = (p.H / 2 + C::HBLK - 1) / C::HBLK;
   if (GW) p.ctiles = (p.Wr + C::CSTEP - 1) / C::CSTEP;
