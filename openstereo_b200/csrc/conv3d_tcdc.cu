@@ -50,8 +50,15 @@ struct TcdcCfg {
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = KS_ * COUT;                     // kw slices stacked along N
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
-  static constexpr int STAGES = 5;                          // one loader warp per ring slot: warps 1-4 and 10 (the former second
-                                                            // weight-loader warp, idle since the slices come by TMA)
+  // A-unit ring.  NLW loader warps (1-4 and 10) fill the units round-robin (unit u belongs to warp u mod NLW) into a ring as deep as
+  // shared memory allows (at most 10 units).  Each loader warp enumerates ONLY ITS OWN units: when every warp walked the whole
+  // (tile, tap) sequence and picked every NLW-th unit, that scalar control flow was the bound of these kernels -- a conv6 run with
+  // loads, conversions, MMAs and stores all disabled still took 0.37 of 0.69 ms, two thirds of the loader warps' stall samples on
+  // the loop lines (profiles/r2_conv6_barrier_skeleton_stalls.txt).
+  static constexpr int NLW = 5;
+  static constexpr int FIXED_SMEM = 1024 + TC_BSLOTS * KS_ * B_SLICE + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
+  static constexpr int STAGES = (232448 - FIXED_SMEM) / UNIT_BYTES < 10 ? (232448 - FIXED_SMEM) / UNIT_BYTES : 10;
+  static_assert(STAGES >= NLW, "the ring must hold at least one unit per loader warp");
   static constexpr int HBLK = TILES * R;                    // output rows per work item
   static constexpr int KSTEPS = KC / 16;                    // K = 16 fp16 channels per MMA
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
@@ -231,8 +238,8 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
     static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
     const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
     float amax = 0.f;
-    const bool mine = lw < C::STAGES;
-    uint32_t unitc = 0;
+    uint32_t ubase = 0;                              // global index of the current phase's first unit
+    int first = lw;                                  // this warp's first local unit index in the current phase: (ubase + first) % NLW == lw
     auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
       // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
@@ -246,13 +253,13 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
         if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
         v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const uint32_t ph = (u / C::STAGES) & 1;
-      mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
+      const uint32_t slot = u % C::STAGES, ph = (u / C::STAGES) & 1;   // u = global unit index
+      mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+      uint8_t* tile = a_buf + slot * C::UNIT_BYTES;
 #pragma unroll
       for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
-      mbar_arrive(&a_ready[lw]);
+      mbar_arrive(&a_ready[slot]);
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const ItemDc w = decode_dc<C>(p, it);
@@ -261,22 +268,21 @@ __global__ void __launch_bounds__(TcdcCfg<COUT, KC, W, TILES, GW, KS>::THREADS, 
         const int id = (w.od + 1 - kd) >> 1;         // input plane feeding output plane od through tap kd
         const float* plane = p.x + ((size_t)w.b * p.D + id) * p.H * (size_t)Wp * p.Cin;
         const int col0 = w.ct * C::CSTEP + v0;       // INPUT column of this lane's first load (whole-row kernels: v0)
+        // valid kh taps of this row parity in issue order: k3: ph 0 -> {1}, ph 1 -> {0, 2};  k4: ph 0 -> {1, 3}, ph 1 -> {0, 2}
+        const int nkh = (KS == 4 || w.ph) ? 2 : 1, kh0 = w.ph ? 0 : 1;
+        const int upp = TILES * nkh;                 // units per (kd, chunk) phase, local index = t * nkh + tap index
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
-          for (int t = 0; t < TILES; ++t) {
-#pragma unroll 1
-            for (int kh = 0; kh < KS; ++kh) {
-              if (!kh_valid(w.ph, kh)) continue;
-              if (mine && unitc % C::STAGES == (uint32_t)lw) {
-                // operand row v = input voxel (row j0 + t*R + v / W + (ph + 1 - kh) / 2, column v % W): output row 2j + ph gathers
-                // tap kh from input row j + (ph + 1 - kh) / 2  (k3: +1 for kh = 0; k4: +1 for kh = 0, -1 for kh = 3)
-                const int h_first = w.j0 + t * C::R + ((w.ph + 1 - kh) >> 1);
-                const float* base = plane + ((ptrdiff_t)h_first * Wp + col0) * p.Cin + ch * KC + c * 4;
-                fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h_first, 1, unitc, col0);
-              }
-              ++unitc;
-            }
+          for (int j = first; j < upp; j += C::NLW) {
+            const int t = nkh == 2 ? (j >> 1) : j, kh = kh0 + 2 * (nkh == 2 ? (j & 1) : 0);
+            // operand row v = input voxel (row j0 + t*R + v / W + (ph + 1 - kh) / 2, column v % W): output row 2j + ph gathers
+            // tap kh from input row j + (ph + 1 - kh) / 2  (k3: +1 for kh = 0; k4: +1 for kh = 0, -1 for kh = 3)
+            const int h_first = w.j0 + t * C::R + ((w.ph + 1 - kh) >> 1);
+            const float* base = plane + ((ptrdiff_t)h_first * Wp + col0) * p.Cin + ch * KC + c * 4;
+            fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h_first, 1, ubase + j, col0);
           }
+          ubase += upp;
+          first = (first + C::NLW - upp % C::NLW) % C::NLW;
         }
       }
     }

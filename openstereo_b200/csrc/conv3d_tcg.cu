@@ -53,8 +53,15 @@ struct TcgCfg {
   static constexpr int NMMA = (N3 <= 256) ? 1 : 3;          // MMAs per (A unit, weight slice, k step)
   static constexpr int NPER = N3 / NMMA;
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
-  static constexpr int STAGES = 5;                          // one loader warp per ring slot: warps 1-4 and 10 (the former second
-                                                            // weight-loader warp, idle since the slices come by TMA)
+  // A-unit ring.  NLW loader warps (1-4 and 10) fill the units round-robin (unit u belongs to warp u mod NLW) into a ring as deep as
+  // shared memory allows (at most 10 units).  Each loader warp enumerates ONLY ITS OWN units: when every warp walked the whole
+  // (tile, tap) sequence and picked every NLW-th unit, that scalar control flow was the bound of these kernels -- a conv6 run with
+  // loads, conversions, MMAs and stores all disabled still took 0.37 of 0.69 ms, two thirds of the loader warps' stall samples on
+  // the loop lines (profiles/r2_conv6_barrier_skeleton_stalls.txt).
+  static constexpr int NLW = 5;
+  static constexpr int FIXED_SMEM = 1024 + TC_BSLOTS * 3 * B_SLICE + 1024 + 2 * 4 * 2 * DIL * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
+  static constexpr int STAGES = (232448 - FIXED_SMEM) / UNIT_BYTES < 10 ? (232448 - FIXED_SMEM) / UNIT_BYTES : 10;
+  static_assert(STAGES >= NLW, "the ring must hold at least one unit per loader warp");
   static constexpr int S_FIRST = -DIL;                      // unit start rows run from S_FIRST to S_LAST (block-relative)
   static constexpr int S_LAST = (TILES - 1) * R + DIL;
   static constexpr int HBLK = TILES * R;                    // output rows per work item
@@ -75,6 +82,22 @@ struct TcgCfg {
     return (num >= 0 && num % R == 0 && num / R < TILES) ? num / R : -1;
   }
   static constexpr bool used(int s) { return tile_of(s, 0) >= 0 || tile_of(s, 1) >= 0 || tile_of(s, 2) >= 0; }
+  // units of one (kd, chunk) phase in issue order: their number and the start row of the j-th one
+  static constexpr int units_per_phase() {
+    int n = 0;
+    for (int s = S_FIRST; s <= S_LAST; ++s) n += used(s) ? 1 : 0;
+    return n;
+  }
+  static constexpr int NU = units_per_phase();
+  static constexpr int unit_s(int j) {
+    int k = 0;
+    for (int s = S_FIRST; s <= S_LAST; ++s)
+      if (used(s)) {
+        if (k == j) return s;
+        ++k;
+      }
+    return S_LAST;
+  }
 };
 
 template <int COUT, int KC, int W, int TILES, int DIL = 1, bool GW = false, bool GATE = false>
@@ -215,8 +238,8 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
     static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
     const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
     float amax = 0.f;
-    const bool mine = lw < C::STAGES;
-    uint32_t unitc = 0;
+    uint32_t ubase = 0;                              // global index of the current phase's first unit
+    int first = lw;                                  // this warp's first local unit index in the current phase: (ubase + first) % NLW == lw
     auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
       // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
@@ -230,13 +253,13 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
         if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
         v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const uint32_t ph = (u / C::STAGES) & 1;
-      mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
+      const uint32_t slot = u % C::STAGES, ph = (u / C::STAGES) & 1;   // u = global unit index
+      mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+      uint8_t* tile = a_buf + slot * C::UNIT_BYTES;
 #pragma unroll
       for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
-      mbar_arrive(&a_ready[lw]);
+      mbar_arrive(&a_ready[slot]);
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int ct = it % ctiles;
@@ -251,15 +274,14 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
         const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)Wp * p.Cin;
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
-          for (int s = C::S_FIRST; s <= C::S_LAST; ++s) {
-            if (!C::used(s)) continue;
-            if (mine && unitc % C::STAGES == (uint32_t)lw) {
-              // unit = R consecutive image rows starting at h0 + s: operand row v is voxel (h0 + s) * W + v of the plane
-              const float* base = plane + ((ptrdiff_t)(h0 + s) * Wp + col0) * p.Cin + ch * KC + c * 4;
-              fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h0 + s, 1, unitc, col0);
-            }
-            ++unitc;
+          for (int j = first; j < C::NU; j += C::NLW) {
+            // unit = R consecutive image rows starting at h0 + s: operand row v is voxel (h0 + s) * W + v of the plane
+            const int s = C::unit_s(j);
+            const float* base = plane + ((ptrdiff_t)(h0 + s) * Wp + col0) * p.Cin + ch * KC + c * 4;
+            fill(base, (size_t)Wp * p.Cin, (size_t)p.Cin, h0 + s, 1, ubase + j, col0);
           }
+          ubase += C::NU;
+          first = (first + C::NLW - C::NU % C::NLW) % C::NLW;
         }
       }
     }

@@ -43,8 +43,16 @@ struct Tcs2Cfg {
   static constexpr int UNIT_BYTES = 128 * ROWB;
   static constexpr int N3 = 3 * COUT;
   static constexpr int B_SLICE = N3 * ROWB;                 // one kh weight slice (hi and lo halves of every row)
-  static constexpr int STAGES = 5;                          // one loader warp per ring slot: warps 1-4 and 10 (the former second
-                                                            // weight-loader warp, idle since the slices come by TMA)
+  // A-unit ring.  NLW loader warps (1-4 and 10) fill the units round-robin (unit u belongs to warp u mod NLW) into a ring as deep as
+  // shared memory allows (at most 10 units).  Each loader warp enumerates ONLY ITS OWN units: when every warp walked the whole
+  // (tile, tap) sequence and picked every NLW-th unit, that scalar control flow was the bound of these kernels -- a conv6 run with
+  // loads, conversions, MMAs and stores all disabled still took 0.37 of 0.69 ms, two thirds of the loader warps' stall samples on
+  // the loop lines (profiles/r2_conv6_barrier_skeleton_stalls.txt).
+  static constexpr int NLW = 5;
+  static constexpr int FIXED_SMEM = 1024 + TC_BSLOTS * 3 * B_SLICE + 1024 + 2 * 4 * 2 * 32 * 4 + 3 * COUT * 4 + TP_BYTES;
+  static constexpr int STAGES = (232448 - FIXED_SMEM) / UNIT_BYTES < 10 ? (232448 - FIXED_SMEM) / UNIT_BYTES : 10;
+  static_assert(STAGES >= NLW, "the ring must hold at least one unit per loader warp");
+  static constexpr int NU = TILES * 3 * 2;                   // units of one (kd, chunk) phase: (tile, kh, column parity)
   static constexpr int HBLK = TILES * R;                    // output rows per work item
   static constexpr int KSTEPS = KC / 16;                    // K = 16 fp16 channels per MMA
   static constexpr int LO = KC / 8;                         // descriptor offset (16-byte units) of the lo half of a row
@@ -193,10 +201,10 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
     static_assert(W % VPL == 0, "a load instruction must not straddle image rows");
     const int v0 = lane_voxel<KC>(lane), c = lane % CPR;   // permuted voxel order: conflict-free STS.64 (tc_common.cuh)
     float amax = 0.f;
-    const bool mine = lw < C::STAGES;
     const int WI = 2 * Wp;                           // input width
     const int Do = p.D / 2;
-    uint32_t unitc = 0;
+    uint32_t ubase = 0;                              // global index of the current phase's first unit
+    int first = lw;                                  // this warp's first local unit index in the current phase: (ubase + first) % NLW == lw
     auto fill = [&](const float* base, size_t rstride, size_t cstride, int h_first, int h_step, uint32_t u, int col0) {
       // base: this lane's address for load 0; load j covers operand rows VPL*j .. VPL*j + VPL - 1 = columns (VPL*j) % W ..
       // of tile row (VPL*j) / W, read from image row h_first + h_step * tile row (rstride / cstride floats per tile row / column).
@@ -210,13 +218,13 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
         if (GW) ok = ok && (unsigned)(col0 + VPL * j) < (unsigned)Wp;
         v[j] = ok ? __ldg(reinterpret_cast<const float4*>(base + (ptrdiff_t)off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const uint32_t ph = (u / C::STAGES) & 1;
-      mbar_wait_relaxed(&a_empty[lw], ph ^ 1);
-      uint8_t* tile = a_buf + lw * C::UNIT_BYTES;
+      const uint32_t slot = u % C::STAGES, ph = (u / C::STAGES) & 1;   // u = global unit index
+      mbar_wait_relaxed(&a_empty[slot], ph ^ 1);
+      uint8_t* tile = a_buf + slot * C::UNIT_BYTES;
 #pragma unroll
       for (int j = 0; j < NLD; ++j) stage_f16_split<KC>(tile, v0 + VPL * j, c, v[j], amax);
       fence_proxy_async();
-      mbar_arrive(&a_ready[lw]);
+      mbar_arrive(&a_ready[slot]);
     };
     for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int ct = it % ctiles;
@@ -231,21 +239,15 @@ __global__ void __launch_bounds__(Tcs2Cfg<COUT, KC, W, TILES, GW>::THREADS, 1) c
         const float* plane = p.x + ((size_t)b * p.D + din) * p.H * (size_t)WI * p.Cin;
         for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll 1
-          for (int t = 0; t < TILES; ++t) {
-#pragma unroll 1
-            for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll 1
-              for (int par = 0; par < 2; ++par) {
-                if (mine && unitc % C::STAGES == (uint32_t)lw) {
-                  // operand row v = output voxel (row h0 + t*R + v / W, column v % W) reading input (2*row + kh - 1, 2*col + par)
-                  const int h_first = 2 * (h0 + t * C::R) + kh - 1;
-                  const float* base = plane + ((ptrdiff_t)h_first * WI + 2 * col0 + par) * p.Cin + ch * KC + c * 4;
-                  fill(base, (size_t)2 * WI * p.Cin, (size_t)2 * p.Cin, h_first, 2, unitc, col0);
-                }
-                ++unitc;
-              }
-            }
+          for (int j = first; j < C::NU; j += C::NLW) {       // local unit index = (t * 3 + kh) * 2 + par
+            const int t = j / 6, kh = (j >> 1) % 3, par = j & 1;
+            // operand row v = output voxel (row h0 + t*R + v / W, column v % W) reading input (2*row + kh - 1, 2*col + par)
+            const int h_first = 2 * (h0 + t * C::R) + kh - 1;
+            const float* base = plane + ((ptrdiff_t)h_first * WI + 2 * col0 + par) * p.Cin + ch * KC + c * 4;
+            fill(base, (size_t)2 * WI * p.Cin, (size_t)2 * p.Cin, h_first, 2, ubase + j, col0);
           }
+          ubase += C::NU;
+          first = (first + C::NLW - C::NU % C::NLW) % C::NLW;
         }
       }
     }

@@ -38,13 +38,13 @@ def main():
         w5 = torch.zeros(cout, cin, 3, 3, 3, device=dev)
         w5[:, :, 1] = torch.randn(cout, cin, 3, 3, device=dev, generator=g) * 0.05
         wp = ops.pack_tc_weight(w5, ops.conv2d_tc_kc(cin, cout, w, 1))
-        res = torch.randn(B, h, w, cout, device=dev, generator=g)
+        res = None if os.environ.get("OSB_LP_NORES") else torch.randn(B, h, w, cout, device=dev, generator=g)
         fn = lambda: ops.conv2d_k3_tc(x, wp, None, sh, res, ops.ACT_RELU)  # noqa: E731
         macs = B * h * w * 9 * cin * cout
     elif kind == "dc":
         wgt = torch.randn(cin, cout, 3, 3, 3, device=dev, generator=g) * 0.05
         wp = ops.pack_tc_deconv_weight(wgt)
-        res = torch.randn(B, 2 * d, 2 * h, 2 * w, cout, device=dev, generator=g)
+        res = None if os.environ.get("OSB_LP_NORES") else torch.randn(B, 2 * d, 2 * h, 2 * w, cout, device=dev, generator=g)
         fn = lambda: ops.deconv3d_k3_tc(x, wp, sc, sh, res, ops.ACT_RELU, out_ndhwc=True, res_ndhwc=True)  # noqa: E731
         macs = B * d * h * w * 27 * cin * cout
     elif kind == "s2":
