@@ -292,6 +292,33 @@ class _PSMHourglass:
         return _deconv(self.conv6, post, ACT_NONE, residual=skip), pre, post
 
 
+def _psm_hg_channels_last_ok(hg, shape_ndhwc):
+    """True when every layer of a PSMNet hourglass has a tensor-core kernel for this channels-last input."""
+    if not USE_TENSOR_CORES:
+        return False
+    b, d, h, w, c = shape_ndhwc
+    if d % 4 or h % 4 or w % 4 or any(l._w5 is None for l in (hg.conv1, hg.conv2, hg.conv3, hg.conv4, hg.conv5, hg.conv6)):
+        return False
+    return (ops.conv3d_s2_tc_supported(hg.conv1.cin, hg.conv1.cout, d, h, w) and _tc_ok(hg.conv2, w // 2)
+            and ops.conv3d_s2_tc_supported(hg.conv3.cin, hg.conv3.cout, d // 2, h // 2, w // 2) and _tc_ok(hg.conv4, w // 4)
+            and hg.conv5.kernel == 3 and hg.conv6.kernel == 3
+            and ops.deconv3d_tc_supported(hg.conv5.cin, hg.conv5.cout, w // 4)
+            and ops.deconv3d_tc_supported(hg.conv6.cin, hg.conv6.cout, w // 2))
+
+
+def _psm_hourglass_channels_last(hg, x, presqu, postsqu, skip):
+    """PSMNet hourglass (psmnet_cost_processor.py:108-132) with every tensor channels-last: the NCDHW route converted the layout in
+    front of every layer.  Returns (out + skip, pre, post) like _PSMHourglass.__call__, all NDHWC."""
+    out = ops.conv3d_k3_s2_tc(x, _s2_weight(hg.conv1), hg.conv1.scale, hg.conv1.shift, None, ACT_RELU, out_ndhwc=True)
+    pre = _conv_tc(hg.conv2, out, ACT_RELU, residual=postsqu)
+    out = ops.conv3d_k3_s2_tc(pre, _s2_weight(hg.conv3), hg.conv3.scale, hg.conv3.shift, None, ACT_RELU, out_ndhwc=True)
+    out = _conv_tc(hg.conv4, out, ACT_RELU)
+    post = ops.deconv3d_k3_tc(out, _dc_weight(hg.conv5), hg.conv5.scale, hg.conv5.shift, presqu if presqu is not None else pre, ACT_RELU,
+                              out_ndhwc=True, res_ndhwc=True)
+    out = ops.deconv3d_k3_tc(post, _dc_weight(hg.conv6), hg.conv6.scale, hg.conv6.shift, skip, ACT_NONE, out_ndhwc=True, res_ndhwc=True)
+    return out, pre, post
+
+
 class PSMAggregation(_Engine):
     """PSMAggregator + FasterSoftArgmin: raw concat volume -> [disp1, disp2, disp3], each (B,H,W)."""
 
@@ -306,7 +333,22 @@ class PSMAggregation(_Engine):
         raw_cost = self._check(raw_cost)
         self._ensure(raw_cost.device)
         width = raw_cost.shape[-1]
-        if all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1])):
+        stem_tc = all(_tc_ok(l, width) for l in (self.dres0[0], self.dres0[1], self.dres1[0], self.dres1[1]))
+        b, _, dd, hh, ww = raw_cost.shape
+        if (stem_tc and all(_psm_hg_channels_last_ok(hg, (b, dd, hh, ww, 32)) for hg in self.hg)
+                and all(_tc_ok(a, width) and _tc_ok(bb, width) for a, bb in self.heads)):
+            # everything channels-last on the tensor cores: the stacked-hourglass skips (pre / post / cost0) never change layout
+            c = _conv_tc(self.dres0[1], _stem_in(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
+            cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c)
+            out1, pre1, post1 = _psm_hourglass_channels_last(self.hg[0], cost0, None, None, cost0)
+            out2, pre2, post2 = _psm_hourglass_channels_last(self.hg[1], out1, pre1, post1, cost0)
+            out3, _, _ = _psm_hourglass_channels_last(self.hg[2], out2, pre2, post2, cost0)
+            costs, prev = [], None
+            for (a, bb), x in zip(self.heads, (out1, out2, out3)):
+                prev = _conv_tc(bb, _conv_tc(a, x, ACT_RELU), ACT_NONE, residual=prev, out_ndhwc=False, res_ndhwc=False)
+                costs.append(prev)
+            return costs
+        if stem_tc:
             c = _conv_tc(self.dres0[1], _stem_in(self.dres0[0], raw_cost, ACT_RELU), ACT_RELU)
             cost0 = _conv_tc(self.dres1[1], _conv_tc(self.dres1[0], c, ACT_RELU), ACT_NONE, residual=c, out_ndhwc=False)
         else:
