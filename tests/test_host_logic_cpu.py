@@ -131,3 +131,58 @@ def test_packed_layer_refuses_unsupported_hyperparameters():
                 nn.Conv3d(8, 8, 3, 1, 0), nn.Conv3d(8, 8, 5, 1, 2), nn.ConvTranspose3d(8, 8, 3, 2, 1, 0), nn.ConvTranspose3d(8, 8, 4, 2, 0)):
         with pytest.raises(NotImplementedError):
             agg._Packed(bad)
+
+
+def test_pack_tc_weight_k4_transposed():
+    """ConvTranspose3d(k4) packing for conv3d_tcdc<KS = 4>: [4 kd][chunks][4 kh][4 * Cout (kw order 1, 3, 2, 0)][16 hi | 16 lo]."""
+    cin, cout = 32, 16
+    w = rnd(5, cin, cout, 4, 4, 4)
+    p = ops.pack_tc_deconv_weight(w)
+    assert p.ksize == 4 and p.kc == 16 and p.cout == cout
+    assert p.data.shape == (4, cin // 16, 4, 4 * cout, 32) and p.data.dtype == torch.float16 and p.data.is_contiguous()
+    cpr = 4
+    rows = torch.arange(4 * cout)
+    key = (rows >> 1) & 3
+    src = (torch.arange(cpr).view(1, cpr) ^ key.view(-1, 1)).view(1, 1, 1, 4 * cout, cpr, 1).expand(4, cin // 16, 4, 4 * cout, cpr, 8)
+    lin = torch.gather(p.data.view(4, cin // 16, 4, 4 * cout, cpr, 8), 4, src).reshape(4, cin // 16, 4, 4 * cout, 32)
+    t = lin.double().view(4, cin // 16, 4, 4, cout, 2, 16).permute(5, 4, 1, 6, 0, 2, 3).reshape(2, cout, cin, 4, 4, 4)
+    scale = 2.0 ** -ops.TC_ACT_SCALE_LOG2 / p.inv.double()
+    want = w.permute(1, 0, 2, 3, 4)[..., [1, 3, 2, 0]].double() * scale.view(-1, 1, 1, 1, 1)
+    assert ((t[0] + t[1] - want).abs() <= torch.maximum(want.abs() * 2.0 ** -22, torch.tensor(2.0 ** -25, dtype=torch.float64))).all()
+    p3 = ops.pack_tc_deconv_weight(rnd(6, cin, cout, 3, 3, 3))                               # the k3 packing is unchanged
+    assert p3.ksize == 3 and p3.data.shape == (3, cin // 16, 3, 3 * cout, 32)
+
+
+def test_tensor_core_capability_queries():
+    """Which shapes the tcgen05 variants serve (answered by the C library without a GPU): whole-row widths, general widths through
+    column tiles (>= OSB_TC_MIN_WIDTH = 24), the StereoBase plan (Cout 96, k4 transposed conv, W' = 16 channel slices)."""
+    assert ops.conv3d_tc_kc(32, 32, 128) == 32 and ops.conv3d_tc_kc(64, 64, 64) == 16 and ops.conv3d_tc_kc(128, 128, 32) == 16
+    for w in (240, 312, 160, 120, 78, 60, 24):
+        assert ops.conv3d_tc_kc(32, 32, w) == 16 and ops.conv3d_tc_kc(128, 128, w) == 16
+        assert ops.deconv3d_tc_supported(64, 32, w) and ops.deconv3d_tc_supported(128, 64, w)
+        assert ops.conv3d_s2_tc_supported(32, 64, 8, 8, 2 * w)
+    assert ops.conv3d_tc_kc(32, 32, 20) == 0 and not ops.deconv3d_tc_supported(64, 32, 20)
+    assert ops.conv3d_tc_kc(24, 32, 240) == 0 and ops.conv3d_tc_kc(32, 48, 240) == 0          # channels must be multiples of 16 / known Cout
+    assert not ops.conv3d_s2_tc_supported(32, 64, 7, 8, 128)                                  # odd extents have no stride-2 variant
+    assert ops.conv3d_tc_kc(96, 96, 32) == 16 and ops.conv3d_s2_tc_supported(64, 96, 8, 8, 64)
+    assert ops.deconv3d_k4_tc_supported(96, 64, 32) and ops.deconv3d_k4_tc_supported(64, 32, 64)
+    assert ops.conv3d_tc_kc(160, 96, 16) == 16 and ops.conv3d_tc_kc(160, 64, 16) == 16 and ops.deconv3d_k4_tc_supported(160, 32, 16)
+    assert not ops.deconv3d_k4_tc_supported(96, 96, 16) and not ops.deconv3d_k4_tc_supported(24, 32, 64)
+
+
+def test_stereobase_tc_route_gating_without_gpu():
+    """StereoBaseAggregation.tc_route_ok: shape / channel-plan gates of the tcgen05 route (pure host logic)."""
+    from openstereo_b200 import aggregation as agg
+    from oracle import aggregation as oagg
+    m = oagg.StereoBaseHourglass(24, [96, 64, 192, 160]).eval()
+    eng = agg.StereoBaseAggregation(m)
+    with torch.no_grad():
+        eng._pack()
+    assert eng.tc_route_ok((4, 24, 48, 64, 128)) and eng._level32_tc_ok((4, 24, 48, 64, 128))
+    assert not eng.tc_route_ok((4, 24, 48, 64, 120)) and not eng.tc_route_ok((4, 24, 44, 64, 128))   # width 120 / D' not a multiple of 8
+    assert not eng.tc_route_ok((4, 32, 48, 64, 128))                                                  # not this module's channel plan
+    agg.USE_TENSOR_CORES = False
+    try:
+        assert not eng.tc_route_ok((4, 24, 48, 64, 128))
+    finally:
+        agg.USE_TENSOR_CORES = True
