@@ -224,11 +224,12 @@ __global__ void __launch_bounds__(TcgCfg<COUT, KC, W, TILES, DIL, GW>::THREADS, 
     }
   }
   // ---------------------------------------------------------------------------------------------- A-unit loaders
-  // One loader WARP per unit: warp lw fills ring slot lw (units with unitc % STAGES == lw), so STAGES units' global loads are
-  // in flight per SM and every slot is refilled in order by a single warp (no mbarrier phase can be skipped).  ncu
-  // (profiles/r1_ncu_summary.md, r1_tcdc_conv6): with all four warps on one unit at a time the loaders sat on the load
-  // latency and the tensor pipe was 17 % busy.  The (tile, tap) loops are runtime loops: one copy of the body (unrolled
-  // bodies took the kernel to 254 KB of code).
+  // One loader WARP per unit, units round-robin over the NLW loader warps (unit u -> warp u % NLW, ring slot u % STAGES), so NLW
+  // units' global loads are in flight per SM; a slot is refilled in unit order (the a_empty wait of use n cannot be overtaken: use
+  // n + 1 of that slot belongs to a warp that has not filled it yet, so no mbarrier phase is skipped).  ncu
+  // (profiles/r1_ncu_summary.md, r1_tcdc_conv6): with all four warps on one unit at a time the loaders sat on the load latency and
+  // the tensor pipe was 17 % busy.  Each warp enumerates ONLY its own units (see the Cfg note): one runtime loop, one copy of the
+  // body (unrolled bodies took the kernel to 254 KB of code).
   else if (warp < 5 || warp == 10) {
     const int lw = warp < 5 ? warp - 1 : 4;
     static_assert(KC == 16, "lane_voxel / unit-row mapping below is written for 64-byte operand rows");
