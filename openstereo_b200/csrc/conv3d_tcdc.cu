@@ -16,6 +16,8 @@
 //   o = 2m: taps k=1 (input m) and k=3 (input m-1);   o = 2m+1: taps k=2 (input m) and k=0 (input m+1)
 // -- every parity class has 2 x 2 (kd, kh) tap pairs, the four kw slices are stacked along N as [W1 | W3 | W2 | W0] and the
 // epilogue forms  even[m] = P1[m] + P3[m-1],  odd[m] = P2[m] + P0[m+1]  (one left and one right shift).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace osb {
@@ -555,6 +557,10 @@ static int launch_tcdc(TcdcParams& p, cudaStream_t stream) {
   return OSB_OK;
 }
 
+// conv3d_tcdq.cu: one work item per output-parity quad (conv6 shape); -1 = shape not instantiated there
+int launch_tcdq(const float* x, const void* w, const float* scale, const float* shift, const float* residual, float* y, int B,
+                int Cin, int Cout, int D, int H, int W, int act, cudaStream_t stream);
+
 }  // namespace osb
 
 extern "C" {
@@ -625,6 +631,14 @@ int osb_deconv3d_k3_tc_fwd(const float* x_ndhwc, const void* w_split, const floa
   p.kappa = rz_kappa(), p.overflow = tc_overflow_flag();
   OSB_REQUIRE(p.overflow, "tensor-core conv: cannot allocate the overflow flag");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    // conv6 (64 -> 32 at W' = 64), channels-last: the parity-quad kernel stages 4 units where this file's kernel stages 9
+    static const int quad = [] { const char* e = getenv("OSB_TCDQ"); return e ? atoi(e) : 1; }();
+    if (quad && W == 64 && Cout == 32 && out_ndhwc && (!residual || res_ndhwc)) {
+      const int rc = launch_tcdq(x_ndhwc, w_split, scale, shift, residual, y, B, Cin, Cout, D, H, W, act, s);
+      if (rc >= 0) return rc;
+    }
+  }
   if (W == 32 && Cout == 64) return launch_tcdc<64, 16, 32, 2>(p, s);
   if (W == 64 && Cout == 32) return launch_tcdc<32, 16, 64, 5>(p, s);
   p.Wr = W;
