@@ -40,13 +40,33 @@ from oracle import seeded_init as si                    # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-DEV = torch.device("cuda", 0)
+# under torchrun (python -m torch.distributed.run --nproc-per-node N tools/bench_configs.py --only c3): one process per GPU, every
+# rank times the same per-GPU workload (weak scaling: BASELINE config 3 is batch 32 over 8 GPUs = 4 pairs per GPU), the step time is
+# the max over ranks, rank 0 prints the aggregate
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+DEV = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(DEV)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=DEV)
+
+
+def over_ranks(ms):
+    """max over ranks of a per-rank time (ms)"""
+    if WORLD == 1:
+        return ms
+    t = torch.tensor([ms], device=DEV, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def timeit(fn, iters, warm=3):
     for _ in range(warm):
         out = fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
@@ -64,7 +84,8 @@ def rnd(gen, *shape, scale=1.0):
 
 
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    if RANK == 0:
+        print(json.dumps(kw), flush=True)
 
 
 def c1(iters):
@@ -106,9 +127,10 @@ def c3(iters, B=4):
 
     with torch.no_grad():
         ms, got = timeit(ours, iters, warm=1 if NO_REF else 3)
+        ms = over_ranks(ms)
         ms_ref, want = (float("nan"), got) if NO_REF else timeit(ref, max(2, iters // 3), warm=1)
     emit(config="c3 StereoBase hot sub-graph, B=%d/GPU @256x512 (volume -> Hourglass(24)+FeatureAtt -> classifier -> soft-argmin)" % B,
-         ms_per_step=round(ms, 3), pairs_per_s=round(B * 1e3 / ms, 2), reference_cudnn_fp32_ms=round(ms_ref, 2),
+         n_gpus=WORLD, ms_per_step=round(ms, 3), pairs_per_s=round(WORLD * B * 1e3 / ms, 2), reference_cudnn_fp32_ms=round(ms_ref, 2),
          speedup_vs_reference_gpu=round(ms_ref / ms, 2), init_disp_epe_vs_reference_gpu_px=float("%.3e" % (got - want).abs().mean().item()),
          gmac_per_pair=23.48)
 
@@ -233,3 +255,5 @@ if __name__ == "__main__":
             {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "gw": gw}[name](a.iters)
         except Exception as exc:                                               # one config must not hide the others
             emit(config=name, error=repr(exc)[:300])
+    if WORLD > 1:
+        dist.destroy_process_group()
