@@ -16,6 +16,9 @@ kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
 L = [(r[kn], float(r[mv].replace(",", "")) / 1e3) for r in rows[hi + 2:] if len(r) == len(hdr)]
 idx = [i for i, (k, _) in enumerate(L) if a.first in k]
 last = L[idx[-1]:] if idx else L
-print("launches %d, total %.1f us" % (len(last), sum(t for _, t in last)))
-for k, t in last:
-    print("%8.1f  %s" % (t, k[:a.width]))
+try:
+    print("launches %d, total %.1f us" % (len(last), sum(t for _, t in last)))
+    for k, t in last:
+        print("%8.1f  %s" % (t, k[:a.width]))
+except BrokenPipeError:                                  # piped into head
+    pass
